@@ -1,0 +1,125 @@
+"""The `cfg` argument of the hot path.
+
+The reference passes an `EasyDict` built from `dpc/resources/default_config.yaml` plus an
+experiment YAML plus `--key=value` overrides (dpc/util/config.py:7-29,105-149).  easydict
+is not installed, so this module provides the same attribute-style mapping with the
+reference's defaults for every key the projection path reads and the
+reference's merge rules: unknown keys raise KeyError (config.py:16-17), values are coerced
+to the type of the default, and a bool can only be overridden by a bool (config.py:19-29).
+YAML is read with `yaml.safe_load` (the reference's bare `yaml.load` fails on PyYAML >= 6).
+"""
+import copy
+
+_DEFAULTS = {
+    # shapes set by the caller (default_config.yaml:25-31,107-108,37)
+    "pc_num_points": 8000,
+    "pc_point_dropout": 1.0,
+    "pc_point_dropout_scheduled": True,
+    "pc_point_dropout_exponential_schedule": False,
+    "pc_point_dropout_end_step": 1.0,
+    "pc_point_dropout_start_step": 0.0,
+    "batch_size": 8,
+    "step_size": 4,
+    "pose_predict_num_candidates": 1,
+    "max_number_of_steps": 600000,
+    # pose (default_config.yaml:33-47)
+    "predict_pose": False,
+    "pose_quaternion": True,
+    "predict_translation": False,
+    # points -> grid (default_config.yaml:49-58)
+    "pc_relative_sigma": 1.0,
+    "pc_relative_sigma_end": 0.2,
+    "pc_fast": True,
+    "pc_gauss_kernel_size": 11,
+    "pc_separable_gauss_filter": True,
+    "pc_learn_occupancy_scaling": True,
+    "pc_occupancy_scaling_maximum": 1.0,
+    # rgb (default_config.yaml:60-66)
+    "pc_rgb": False,
+    "pc_rgb_stop_points_gradient": False,
+    "pc_rgb_clip_after_conv": False,
+    "pc_rgb_divide_by_occupancies": False,
+    "pc_rgb_divide_by_occupancies_epsilon": 0.01,
+    "learn_focal_length": False,
+    # projection (default_config.yaml:77-90)
+    "vox_size": 64,
+    "vox_size_z": -1,
+    "focal_length": 1.875,
+    "camera_distance": 2.0,
+    "ptn_max_projection": False,
+    "max_depth": 10.0,
+    "drc_logsum": True,
+    "drc_logsum_clip_val": 0.00001,
+    "drc_tf_cumulative": True,
+}
+
+
+class AttrDict(dict):
+    """dict with attribute access (stand-in for easydict.EasyDict)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def copy(self):
+        return AttrDict(copy.deepcopy(dict(self)))
+
+
+def _coerce(key, old, new):
+    if isinstance(old, bool):
+        if not isinstance(new, bool):
+            raise ValueError("config key %r is a bool and can only be overridden by a bool, got %r" % (key, new))
+        return new
+    if isinstance(old, float) and isinstance(new, (int, float)) and not isinstance(new, bool):
+        return float(new)
+    if isinstance(old, int) and isinstance(new, int) and not isinstance(new, bool):
+        return int(new)
+    if type(old) is type(new):
+        return new
+    raise ValueError("type mismatch for config key %r: default %r (%s) vs %r (%s)"
+                     % (key, old, type(old).__name__, new, type(new).__name__))
+
+
+def default_config(**overrides):
+    """Reference defaults for the projection path, then `overrides` merged with the
+    reference's rules (KeyError for an unknown key)."""
+    cfg = AttrDict(copy.deepcopy(_DEFAULTS))
+    merge_into(cfg, overrides)
+    return cfg
+
+
+def merge_into(cfg, overrides):
+    for k, v in overrides.items():
+        if k not in cfg:
+            raise KeyError("%s is not a valid config key" % k)
+        cfg[k] = _coerce(k, cfg[k], v)
+    return cfg
+
+
+def experiment_config(name):
+    """The two experiment overrides that exist in the reference
+    (experiments/chair_camera_supervision/config.yaml, experiments/chair_unsupervised/config.yaml)."""
+    common = dict(vox_size=64, pc_gauss_kernel_size=21, pc_relative_sigma=3.0,
+                  pc_num_points=8000, pc_point_dropout=0.07)
+    if name == "chair_camera_supervision":
+        return default_config(**common)
+    if name == "chair_unsupervised":
+        return default_config(predict_pose=True, pose_predict_num_candidates=4, **common)
+    raise KeyError(name)
+
+
+def load_config(path, **overrides):
+    """Defaults <- YAML file (only keys known here are taken; the reference's YAML carries many
+    keys for subsystems outside this package) <- overrides."""
+    import yaml
+    with open(path) as f:
+        data = yaml.safe_load(f) or {}
+    cfg = default_config()
+    merge_into(cfg, {k: v for k, v in data.items() if k in cfg})
+    merge_into(cfg, overrides)
+    return cfg
