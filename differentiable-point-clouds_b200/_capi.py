@@ -1,0 +1,139 @@
+"""ctypes binding of the C-ABI in include/dpc_b200.h (libdpc_b200.so, hand-written sm_100a CUDA).
+
+There is no CPU fallback: if the shared library is missing or a tensor is not on a CUDA device
+the call raises.  (`_LIB` / `_REQUIRE_CUDA` are module attributes only so that tests/emu can
+drive this same host code over the CPU emulation build of the kernels; nothing in the package
+ever sets them.)
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC_DIR, "libdpc_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_LIB = None
+_REQUIRE_CUDA = True
+
+c_f = ctypes.c_float
+c_i = ctypes.c_int
+c_p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+
+
+class ProjectParams(ctypes.Structure):
+    _fields_ = [("B", c_i), ("N", c_i), ("Vz", c_i), ("V", c_i), ("pose_kind", c_i), ("mode", c_i),
+                ("K", c_i), ("Kz", c_i), ("focal_const", c_f), ("cam_dist", c_f), ("clip_eps", c_f),
+                ("max_depth", c_f)]
+
+
+POSE_NONE, POSE_QUAT, POSE_MATRIX = -1, 0, 1
+PROJ_NONE, PROJ_DRC, PROJ_MAX, PROJ_DRC_PROD = -1, 0, 1, 2
+MAX_TAPS = 63
+MAX_V = 128
+
+_PP = ctypes.POINTER(ProjectParams)
+_SIGNATURES = {
+    "dpc_abi_version": (c_i, []),
+    "dpc_error_string": (ctypes.c_char_p, [c_i]),
+    "dpc_last_cuda_error": (c_i, []),
+    "dpc_is_cuda_build": (c_i, []),
+    "dpc_splat_fwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i,
+                            c_p, c_p, c_p, c_p, c_p, c_p]),
+    "dpc_splat_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i, c_i,
+                            c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "dpc_conv_xy": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "dpc_conv_z_fwd": (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i,
+                             c_p, c_p, c_p, c_p, c_p, c_p]),
+    "dpc_conv_z_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i,
+                             c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "dpc_project_fast_workspace_bytes": (c_i64, [_PP]),
+    "dpc_project_fast_fwd": (c_i, [_PP, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                   c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
+    "dpc_project_fast_bwd": (c_i, [_PP, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
+    "dpc_gather_points": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "dpc_gather_points_bwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def build(verbose=False):
+    """Compile csrc/dpc_capi.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+    src = os.path.join(CSRC_DIR, "dpc_capi.cu")
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return res.stderr if verbose else LIB_PATH
+
+
+def _declare(lib):
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+def load_library(path):
+    return _declare(ctypes.CDLL(path))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "dpc_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        _LIB = load_library(LIB_PATH)
+    return _LIB
+
+
+class DpcError(RuntimeError):
+    pass
+
+
+def check(code):
+    if code != 0:
+        L = lib()
+        msg = L.dpc_error_string(code).decode()
+        if code == -4:
+            msg += " [cudaError %d]" % L.dpc_last_cuda_error()
+        if code in (-2, -3):
+            raise ValueError("dpc_b200: " + msg)
+        raise DpcError("dpc_b200: " + msg)
+
+
+def ptr(t):
+    """Raw device pointer of a contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if _REQUIRE_CUDA and not t.is_cuda:
+        raise ValueError("dpc_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+    if not t.is_contiguous():
+        raise ValueError("dpc_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream_of(t):
+    if t.is_cuda:
+        return torch.cuda.current_stream(t.device).cuda_stream
+    return None
+
+
+def f32c(t):
+    """contiguous float32 view/copy (None passes through)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

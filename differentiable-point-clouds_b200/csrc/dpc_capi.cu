@@ -1,0 +1,314 @@
+// C-ABI of the projection path (include/dpc_b200.h): argument checks and kernel launches.
+// No torch types, no host synchronisation, no static mutable state.
+#include "dpc_common.cuh"
+#include "dpc_math.cuh"
+#include "dpc_splat.cuh"
+#include "dpc_smooth.cuh"
+#include "dpc_smooth_fast.cuh"
+
+static thread_local int g_last_cuda_error = 0;
+
+static int dpc_check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DPC_ERR_CUDA; }
+  return DPC_OK;
+}
+#define DPC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_last_cuda_error = (int)e__; return DPC_ERR_CUDA; } } while (0)
+#define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
+
+static bool shape_ok(int B, int Vz, int V) {
+  return B >= 1 && B <= 65535 && V >= 1 && V <= DPC_MAX_V && Vz >= 1 && Vz <= DPC_MAX_V;
+}
+
+extern "C" {
+
+int dpc_abi_version(void) { return 1; }
+int dpc_last_cuda_error(void) { return g_last_cuda_error; }
+int dpc_is_cuda_build(void) {
+#ifdef DPC_EMU
+  return 0;
+#else
+  return 1;
+#endif
+}
+const char* dpc_error_string(int code) {
+  switch (code) {
+    case DPC_OK: return "ok";
+    case DPC_ERR_NULL: return "required pointer is NULL";
+    case DPC_ERR_SHAPE: return "unsupported shape (B, N, V, Vz or tap count out of range)";
+    case DPC_ERR_ARG: return "inconsistent arguments";
+    case DPC_ERR_CUDA: return "CUDA error (see dpc_last_cuda_error)";
+    case DPC_ERR_WORKSPACE: return "workspace too small or misaligned";
+    default: return "unknown error";
+  }
+}
+
+int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float* trans,
+                  const float* focal, float focal_const, float cam_dist, const float* rgb,
+                  int B, int N, int Vz, int V,
+                  float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
+                  void* stream) {
+  if (!pc) return DPC_ERR_NULL;
+  if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
+  if (pose_kind < DPC_POSE_NONE || pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
+  if (trans && pose_kind != DPC_POSE_QUAT) return DPC_ERR_ARG;  // reference: tf.slice rank error
+  if (rgb && !vox_rgb && vox) return DPC_ERR_NULL;
+  if (!shape_ok(B, Vz, V) || N < 1) return DPC_ERR_SHAPE;
+  DpcSplatArgs a;
+  a.pc = pc; a.pose = pose; a.trans = trans; a.focal = (pose_kind == DPC_POSE_QUAT) ? focal : nullptr; a.rgb = rgb;
+  a.pose_kind = pose_kind; a.focal_const = focal_const; a.cam_dist = cam_dist;
+  a.B = B; a.N = N; a.Vz = Vz; a.V = V;
+  a.tr_pc = tr_pc; a.vox = vox; a.vox_rgb = vox_rgb; a.idx_out = idx_out; a.valid_out = valid_out;
+  dim3 grid((N + DPC_SPLAT_THREADS - 1) / DPC_SPLAT_THREADS, B);
+  DPC_LAUNCH(dpc_splat_fwd_kernel, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a);
+  return dpc_check_launch();
+}
+
+int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float* trans,
+                  const float* focal, float focal_const, float cam_dist, const float* rgb,
+                  int rgb_stop_grad, int B, int N, int Vz, int V,
+                  const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
+                  float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
+                  void* stream) {
+  if (!pc) return DPC_ERR_NULL;
+  if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
+  if (pose_kind < DPC_POSE_NONE || pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
+  if (trans && pose_kind != DPC_POSE_QUAT) return DPC_ERR_ARG;
+  if (d_vox_rgb && !rgb) return DPC_ERR_NULL;
+  if (!shape_ok(B, Vz, V) || N < 1) return DPC_ERR_SHAPE;
+  DpcSplatBwdArgs a;
+  a.pc = pc; a.pose = pose; a.trans = trans; a.focal = (pose_kind == DPC_POSE_QUAT) ? focal : nullptr; a.rgb = rgb;
+  a.pose_kind = pose_kind; a.focal_const = focal_const; a.cam_dist = cam_dist; a.rgb_stop_grad = rgb_stop_grad;
+  a.B = B; a.N = N; a.Vz = Vz; a.V = V;
+  a.d_vox = d_vox; a.d_vox_rgb = d_vox_rgb; a.d_tr_pc_in = d_tr_pc_in;
+  a.d_pc = d_pc; a.d_pose = d_pose; a.d_trans = d_trans; a.d_focal = d_focal; a.d_rgb = d_rgb;
+  dim3 grid((N + DPC_SPLAT_THREADS - 1) / DPC_SPLAT_THREADS, B);
+  DPC_LAUNCH(dpc_splat_bwd_kernel, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a);
+  return dpc_check_launch();
+}
+
+int dpc_conv_xy(const float* in, float* out, const float* taps_x, int Kx, int pad_lo_x,
+                const float* taps_y, int Ky, int pad_lo_y, int B, int Vz, int V,
+                int clip_in, uint32_t* mask_bits_out, const uint32_t* mask_bits_in, void* stream) {
+  if (!in || !out || !taps_x || !taps_y) return DPC_ERR_NULL;
+  if (!shape_ok(B, Vz, V) || Kx < 1 || Ky < 1 || Kx > DPC_MAX_TAPS || Ky > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
+  if (pad_lo_x < 0 || pad_lo_x >= Kx || pad_lo_y < 0 || pad_lo_y >= Ky) return DPC_ERR_ARG;
+  if ((mask_bits_out || mask_bits_in) && ((V * V) % 32 != 0)) return DPC_ERR_SHAPE;
+  if ((int64_t)B * Vz > 2147483647LL) return DPC_ERR_SHAPE;
+  if (dpc_conv_xy_fast_supported(V, Kx, pad_lo_x, Ky, pad_lo_y)) {
+    DPC_TRY(dpc_conv_xy_fast_launch(in, out, taps_x, taps_y, Kx, B, Vz, V, clip_in, mask_bits_out, mask_bits_in, stream));
+    return dpc_check_launch();
+  }
+  DpcConvXYArgs a;
+  a.in = in; a.out = out; a.taps_x = taps_x; a.Kx = Kx; a.plx = pad_lo_x;
+  a.taps_y = taps_y; a.Ky = Ky; a.ply = pad_lo_y; a.B = B; a.Vz = Vz; a.V = V; a.clip_in = clip_in;
+  a.mask_out = mask_bits_out; a.mask_in = mask_bits_in;
+  const size_t smem = (size_t)(2 * V * V + 2 * (DPC_MAX_TAPS + 1)) * sizeof(float);
+#ifndef DPC_EMU
+  if (smem > 48 * 1024) DPC_CUDA(cudaFuncSetAttribute(dpc_conv_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+  DPC_LAUNCH(dpc_conv_xy_kernel, dim3(B * Vz), dim3(DPC_CONV_THREADS), smem, stream, a);
+  return dpc_check_launch();
+}
+
+static int conv_z_ty(int V) {
+  int ty = 128 / V;
+  return ty < 1 ? 1 : ty;
+}
+
+int dpc_conv_z_fwd(const float* in, const float* taps_z, int Kz, int pad_lo_z,
+                   const float* scale, int mode, float clip_eps, float cam_dist, float max_depth,
+                   int flip_y, int B, int Vz, int V,
+                   float* vox_out, uint32_t* mask2_out, float* proj, float* drc_probs,
+                   float* proj_depth, void* stream) {
+  if (!in || !taps_z || !vox_out) return DPC_ERR_NULL;
+  if (mode < DPC_PROJ_NONE || mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
+  if (mode != DPC_PROJ_NONE && !proj) return DPC_ERR_NULL;
+  if ((drc_probs || proj_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
+  if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
+  if (pad_lo_z < 0 || pad_lo_z >= Kz) return DPC_ERR_ARG;
+  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z)) {
+    DPC_TRY(dpc_conv_z_fwd_fast_launch(in, taps_z, Kz, scale, mode, clip_eps, cam_dist, max_depth, flip_y, B, Vz, V,
+                                       vox_out, mask2_out, proj, drc_probs, proj_depth, stream));
+    return dpc_check_launch();
+  }
+  DpcConvZArgs a;
+  a.in = in; a.taps = taps_z; a.K = Kz; a.pl = pad_lo_z; a.scale = scale; a.mode = mode; a.eps = clip_eps;
+  a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = conv_z_ty(V);
+  a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = drc_probs; a.depth = proj_depth;
+  const size_t smem = ((size_t)Vz * a.TY * V + DPC_MAX_TAPS + 1) * sizeof(float);
+#ifndef DPC_EMU
+  if (smem > 48 * 1024) DPC_CUDA(cudaFuncSetAttribute(dpc_conv_z_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+  dim3 grid((V + a.TY - 1) / a.TY, B);
+  DPC_LAUNCH(dpc_conv_z_fwd_kernel, grid, dim3(128), smem, stream, a);
+  return dpc_check_launch();
+}
+
+int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
+                   const float* taps_z_rev, int Kz, int pad_lo_z_rev,
+                   int mode, float clip_eps, float cam_dist, float max_depth, int flip_y,
+                   int B, int Vz, int V,
+                   const float* g_proj, const float* g_vox, const float* g_probs, const float* g_depth,
+                   float* d_in, float* d_scale, void* stream) {
+  if (!vox || !taps_z_rev || !d_in) return DPC_ERR_NULL;
+  if (mode < DPC_PROJ_NONE || mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
+  if ((g_probs || g_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
+  if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
+  if (pad_lo_z_rev < 0 || pad_lo_z_rev >= Kz) return DPC_ERR_ARG;
+  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z_rev)) {
+    DPC_TRY(dpc_conv_z_bwd_fast_launch(vox, mask2, scale, taps_z_rev, Kz, mode, clip_eps, cam_dist, max_depth, flip_y,
+                                       B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, stream));
+    return dpc_check_launch();
+  }
+  DpcConvZBwdArgs a;
+  a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps_z_rev; a.K = Kz; a.pl = pad_lo_z_rev;
+  a.mode = mode; a.eps = clip_eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
+  a.B = B; a.Vz = Vz; a.V = V; a.TY = conv_z_ty(V);
+  a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;
+  const size_t smem = ((size_t)2 * Vz * a.TY * V + DPC_MAX_TAPS + 1) * sizeof(float);
+#ifndef DPC_EMU
+  if (smem > 48 * 1024) DPC_CUDA(cudaFuncSetAttribute(dpc_conv_z_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+  dim3 grid((V + a.TY - 1) / a.TY, B);
+  DPC_LAUNCH(dpc_conv_z_bwd_kernel, grid, dim3(128), smem, stream, a);
+  return dpc_check_launch();
+}
+
+// ------------------------------------------------------------------------------------ fused path
+static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+struct DpcWs { float* raw; float* tmp; uint32_t* mask1; uint32_t* mask2; float* taps_rev; int64_t total; };
+
+static DpcWs ws_layout(const dpc_project_params* p, void* base) {
+  const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
+  const int64_t nw = (p->Vz + 31) / 32;
+  int64_t off = 0;
+  DpcWs w;
+  char* c = (char*)base;
+  w.raw = (float*)(c + off); off += align256(g * 4);
+  w.tmp = (float*)(c + off); off += align256(g * 4);
+  w.mask1 = (uint32_t*)(c + off); off += align256((g / 32 + 1) * 4);
+  w.mask2 = (uint32_t*)(c + off); off += align256((int64_t)p->B * p->V * p->V * nw * 4);
+  w.taps_rev = (float*)(c + off); off += align256(4 * (DPC_MAX_TAPS + 1) * 4);
+  w.total = off;
+  return w;
+}
+
+static int params_ok(const dpc_project_params* p) {
+  if (!p) return DPC_ERR_NULL;
+  if (!shape_ok(p->B, p->Vz, p->V) || p->N < 1) return DPC_ERR_SHAPE;
+  if ((p->V * p->V) % 32 != 0) return DPC_ERR_SHAPE;
+  if (p->K < 0 || p->K > DPC_MAX_TAPS || p->Kz < 0 || p->Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
+  if ((p->K == 0) != (p->Kz == 0)) return DPC_ERR_ARG;
+  if (p->mode < DPC_PROJ_DRC || p->mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
+  if (p->pose_kind < DPC_POSE_NONE || p->pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
+  return DPC_OK;
+}
+
+int64_t dpc_project_fast_workspace_bytes(const dpc_project_params* p) {
+  if (params_ok(p) != DPC_OK) return -1;
+  return ws_layout(p, nullptr).total;
+}
+
+// identity tap used when the caller passes no smoothing kernel (kernel=None in the reference):
+// 1.0 * x + exact zeros is exact, so the same kernels serve both cases.
+#ifndef DPC_EMU
+__global__ void
+#else
+static void
+#endif
+dpc_prepare_taps_kernel(const float* taps_xy, int K, const float* taps_z, int Kz, float* out) {
+  // out: [0..63] xy taps, [64..127] z taps, [128..191] reversed xy, [192..255] reversed z
+  const int t = threadIdx.x;
+  const int S = DPC_MAX_TAPS + 1;
+  const int k = K > 0 ? K : 1, kz = Kz > 0 ? Kz : 1;
+  if (t < k) { const float v = K > 0 ? taps_xy[t] : 1.0f; out[t] = v; out[2 * S + (k - 1 - t)] = v; }
+  if (t < kz) { const float v = Kz > 0 ? taps_z[t] : 1.0f; out[S + t] = v; out[3 * S + (kz - 1 - t)] = v; }
+}
+
+int dpc_project_fast_fwd(const dpc_project_params* p,
+                         const float* pc, const float* pose, const float* trans, const float* focal,
+                         const float* scale, const float* taps_xy, const float* taps_z,
+                         float* tr_pc, float* voxels, float* proj, float* drc_probs, float* proj_depth,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  DPC_TRY(params_ok(p));
+  if (!pc || !voxels || !proj || !workspace) return DPC_ERR_NULL;
+  if (p->K > 0 && (!taps_xy || !taps_z)) return DPC_ERR_NULL;
+  if (((uintptr_t)workspace & 15) != 0) return DPC_ERR_WORKSPACE;
+  DpcWs w = ws_layout(p, workspace);
+  if (workspace_bytes < w.total) return DPC_ERR_WORKSPACE;
+  const int S = DPC_MAX_TAPS + 1;
+  const int K = p->K > 0 ? p->K : 1, Kz = p->Kz > 0 ? p->Kz : 1;
+  const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
+  DPC_LAUNCH(dpc_prepare_taps_kernel, dim3(1), dim3(64), 0, stream, taps_xy, p->K, taps_z, p->Kz, w.taps_rev);
+  DPC_TRY(dpc_check_launch());
+  DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
+  DPC_TRY(dpc_splat_fwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
+                        p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, stream));
+  DPC_TRY(dpc_conv_xy(w.raw, w.tmp, w.taps_rev, K, (K - 1) / 2, w.taps_rev, K, (K - 1) / 2,
+                      p->B, p->Vz, p->V, /*clip_in=*/1, w.mask1, nullptr, stream));
+  const bool want_probs = (p->mode != DPC_PROJ_MAX);
+  DPC_TRY(dpc_conv_z_fwd(w.tmp, w.taps_rev + S, Kz, (Kz - 1) / 2, scale, p->mode, p->clip_eps, p->cam_dist,
+                         p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V, voxels, scale ? w.mask2 : nullptr, proj,
+                         want_probs ? drc_probs : nullptr, want_probs ? proj_depth : nullptr, stream));
+  return DPC_OK;
+}
+
+int dpc_project_fast_bwd(const dpc_project_params* p,
+                         const float* pc, const float* pose, const float* trans, const float* focal,
+                         const float* scale, const float* taps_xy, const float* taps_z,
+                         const float* voxels,
+                         const float* g_proj, const float* g_voxels, const float* g_tr_pc,
+                         const float* g_probs, const float* g_depth,
+                         float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_scale,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  DPC_TRY(params_ok(p));
+  if (!pc || !voxels || !workspace) return DPC_ERR_NULL;
+  (void)taps_xy; (void)taps_z;  // the forward left both tap sets (and their reversals) in the workspace
+  if (((uintptr_t)workspace & 15) != 0) return DPC_ERR_WORKSPACE;
+  DpcWs w = ws_layout(p, workspace);
+  if (workspace_bytes < w.total) return DPC_ERR_WORKSPACE;
+  const int S = DPC_MAX_TAPS + 1;
+  const int K = p->K > 0 ? p->K : 1, Kz = p->Kz > 0 ? p->Kz : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_pose) DPC_CUDA(cudaMemsetAsync(d_pose, 0, (size_t)p->B * (p->pose_kind == DPC_POSE_MATRIX ? 16 : 4) * 4, st));
+  if (d_trans) DPC_CUDA(cudaMemsetAsync(d_trans, 0, (size_t)p->B * 3 * 4, st));
+  if (d_focal) DPC_CUDA(cudaMemsetAsync(d_focal, 0, (size_t)p->B * 4, st));
+  if (d_scale) DPC_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->B * 4, st));
+  const bool any_grid_grad = g_proj || g_voxels || g_probs || g_depth;
+  const float* d_raw = nullptr;
+  if (any_grid_grad) {
+    // voxels/proj -> d(xy-smoothed) in tmp -> d(raw) in raw (the clip mask saved by the forward applied)
+    DPC_TRY(dpc_conv_z_bwd(voxels, scale ? w.mask2 : nullptr, scale, w.taps_rev + 3 * S, Kz, Kz - 1 - (Kz - 1) / 2,
+                           p->mode, p->clip_eps, p->cam_dist, p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V,
+                           g_proj, g_voxels, g_probs, g_depth, w.tmp, d_scale, stream));
+    DPC_TRY(dpc_conv_xy(w.tmp, w.raw, w.taps_rev + 2 * S, K, K - 1 - (K - 1) / 2, w.taps_rev + 2 * S, K,
+                        K - 1 - (K - 1) / 2, p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, w.mask1, stream));
+    d_raw = w.raw;
+  }
+  DPC_TRY(dpc_splat_bwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
+                        p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr, stream));
+  return DPC_OK;
+}
+
+int dpc_gather_points(const float* in, const int64_t* sel, int B, int N, int n_keep, int C, float* out, void* stream) {
+  if (!in || !sel || !out) return DPC_ERR_NULL;
+  if (B < 1 || B > 65535 || N < 1 || n_keep < 0 || n_keep > N || C < 1) return DPC_ERR_SHAPE;
+  if (n_keep == 0) return DPC_OK;
+  dim3 grid((n_keep * C + 255) / 256, B);
+  DPC_LAUNCH(dpc_gather_kernel, grid, dim3(256), 0, stream, in, sel, N, n_keep, C, out);
+  return dpc_check_launch();
+}
+
+int dpc_gather_points_bwd(const float* g_out, const int64_t* sel, int B, int N, int n_keep, int C, float* g_in, void* stream) {
+  if (!g_out || !sel || !g_in) return DPC_ERR_NULL;
+  if (B < 1 || B > 65535 || N < 1 || n_keep < 0 || n_keep > N || C < 1) return DPC_ERR_SHAPE;
+  DPC_CUDA(cudaMemsetAsync(g_in, 0, (size_t)B * N * C * 4, (cudaStream_t)stream));
+  if (n_keep == 0) return DPC_OK;
+  dim3 grid((n_keep * C + 255) / 256, B);
+  DPC_LAUNCH(dpc_gather_bwd_kernel, grid, dim3(256), 0, stream, g_out, sel, N, n_keep, C, g_in);
+  return dpc_check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Common definitions for the sm_100a kernels.  The same sources compile in two ways:
+//   * nvcc -gencode arch=compute_100a,code=sm_100a   -> the product library (libdpc_b200.so)
+//   * g++ -x c++ -DDPC_EMU                            -> tests/emu: every CUDA thread is an OS
+//     thread, used ONLY by the CPU test-suite to check indexing / gradient logic of these very
+//     kernels before GPU time is spent.  The emulation build is never loaded by the product.
+#pragma once
+
+#include <stdint.h>
+
+#ifdef DPC_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include "../../include/dpc_b200.h"
+
+#define DPC_WARP 32
+#define DPC_FULL 0xffffffffu
+
+#ifndef DPC_EMU
+#define DPC_DEV __device__ __forceinline__
+#define DPC_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define DPC_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; \
+  type* name = reinterpret_cast<type*>(name##_raw)
+#else
+#define DPC_DEV static inline
+#define DPC_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  dpc_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+#define DPC_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dpc_emu::dyn_smem())
+#endif
+
+// ------------------------------------------------------------------ small PTX wrappers
+// red.global.add.f32: fire-and-forget fp32 add at L2 (SASS REDG.E.ADD.F32).
+DPC_DEV void dpc_red_add(float* addr, float v) {
+#ifndef DPC_EMU
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+#else
+  atomicAdd(addr, v);
+#endif
+}
+
+// red.global.add.v2.f32 (sm_90+): two adjacent floats in one L2 reduction (REDG.E.ADD.F32x2).
+// addr must be 8-byte aligned.
+DPC_DEV void dpc_red_add2(float* addr, float a, float b) {
+#ifndef DPC_EMU
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+#else
+  atomicAdd(addr, a);
+  atomicAdd(addr + 1, b);
+#endif
+}
+
+// Packed fp32x2 FMA (Blackwell FFMA2): d = a*b+c on both halves.
+DPC_DEV float2 dpc_ffma2(float2 a, float2 b, float2 c) {
+#ifndef DPC_EMU
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
+// ---- 1-D bulk async copy global -> shared through the TMA engine (SASS UBLKCP), completion
+// on an mbarrier.  Requirements: 16-byte aligned src/dst, bytes % 16 == 0.
+DPC_DEV void dpc_mbar_init(uint64_t* bar, unsigned count) {
+#ifndef DPC_EMU
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  *bar = 0;
+  (void)count;
+#endif
+}
+
+DPC_DEV void dpc_bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+#ifndef DPC_EMU
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+#else
+  memcpy(smem_dst, gmem_src, bytes);
+  *bar = 1;
+#endif
+}
+
+DPC_DEV void dpc_mbar_wait(uint64_t* bar, unsigned phase) {
+#ifndef DPC_EMU
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(phase) : "memory");
+#else
+  (void)bar; (void)phase;
+#endif
+}
+
+// bulk async copy shared -> global (TMA store), bulk-group completion.
+DPC_DEV void dpc_bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes) {
+#ifndef DPC_EMU
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(s), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#else
+  memcpy(gmem_dst, smem_src, bytes);
+#endif
+}
+
+DPC_DEV float dpc_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DPC_FULL, v, o);
+  return v;
+}
+
+DPC_DEV float dpc_clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }

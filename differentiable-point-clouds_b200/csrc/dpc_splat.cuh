@@ -1,0 +1,318 @@
+// K1 / K1b: fused camera transform + validity + trilinear splat, and its backward.
+//
+// Replaces ~55 element-wise TF kernels, 9-17 boolean_mask compactions (dynamic shapes, host
+// syncs), eight zero-filled dense grids + eight scatter_nd + add_n of the reference
+// (point_cloud.py:60-136,157-216; quaternion.py:96-117) by ONE pass: a point tile is staged
+// into shared memory by the TMA engine (cp.async.bulk, mbarrier completion), transformed in
+// registers with the reference's exact fp32 op order, written back coalesced as tr_pc, and its
+// 8 corner weights are added to the single grid with warp-aggregated REDG (v2 where aligned).
+#pragma once
+#include "dpc_math.cuh"
+
+#define DPC_SPLAT_THREADS 256
+
+struct DpcSplatArgs {
+  const float* pc; const float* pose; const float* trans; const float* focal; const float* rgb;
+  int pose_kind; float focal_const; float cam_dist;
+  int B, N, Vz, V;
+  float* tr_pc; float* vox; float* vox_rgb; int32_t* idx_out; uint8_t* valid_out;
+};
+
+// Stage `n` points (3n floats) of sample b starting at point p0 into smem.
+DPC_DEV void dpc_stage_points(float* tile, uint64_t* bar, const float* src, int n) {
+  const unsigned bytes = (unsigned)n * 12u;
+  const bool bulk_ok = ((((uintptr_t)src) & 15u) == 0) && ((bytes & 15u) == 0);
+  if (bulk_ok) {
+    if (threadIdx.x == 0) {
+      dpc_mbar_init(bar, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) dpc_bulk_load(tile, src, bytes, bar);
+    dpc_mbar_wait(bar, 0);
+  } else {
+    for (int i = threadIdx.x; i < n * 3; i += blockDim.x) tile[i] = src[i];
+  }
+  __syncthreads();
+}
+
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(DPC_SPLAT_THREADS)
+#else
+static void
+#endif
+dpc_splat_fwd_kernel(DpcSplatArgs a) {
+  __shared__ __align__(128) float tile[DPC_SPLAT_THREADS * 3];
+  __shared__ __align__(8) uint64_t bar;
+  const int b = blockIdx.y;
+  const int p_first = blockIdx.x * DPC_SPLAT_THREADS;
+  const int n = min(DPC_SPLAT_THREADS, a.N - p_first);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+
+  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n);
+
+  DpcPose P;
+  dpc_pose_load(P, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+
+  const bool live = tid < n;
+  float z = 0.f, y = 0.f, x = 0.f;
+  if (live) {
+    DpcCamPoint cam;
+    dpc_transform_point(P, tile[tid * 3 + 0], tile[tid * 3 + 1], tile[tid * 3 + 2], z, y, x, cam);
+  }
+  __syncthreads();  // everyone has read its point
+  if (a.tr_pc) {
+    if (live) { tile[tid * 3 + 0] = z; tile[tid * 3 + 1] = y; tile[tid * 3 + 2] = x; }
+    __syncthreads();
+    float* dst = a.tr_pc + ((size_t)b * a.N + p_first) * 3;
+    for (int i = tid; i < n * 3; i += DPC_SPLAT_THREADS) dst[i] = tile[i];
+  }
+
+  DpcCell c = dpc_cell(z, y, x, a.Vz, a.V);
+  c.valid = c.valid && live;
+  if (live) {
+    const size_t pi = (size_t)b * a.N + p_first + tid;
+    if (a.idx_out) { a.idx_out[pi * 3 + 0] = c.iz; a.idx_out[pi * 3 + 1] = c.iy; a.idx_out[pi * 3 + 2] = c.ix; }
+    if (a.valid_out) a.valid_out[pi] = c.valid ? 1 : 0;
+  }
+  if (!a.vox) return;
+
+  // corner weights, reference association: (rr[k].z * rr[j].y) * rr[i].x  (point_cloud.py:99)
+  const float wz[2] = {__fsub_rn(1.0f, c.rz), c.rz};
+  const float wy[2] = {__fsub_rn(1.0f, c.ry), c.ry};
+  const float wx[2] = {__fsub_rn(1.0f, c.rx), c.rx};
+  float w[8];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) w[k * 4 + j * 2 + i] = c.valid ? __fmul_rn(__fmul_rn(wz[k], wy[j]), wx[i]) : 0.0f;
+
+  const int V = a.V, Vz = a.Vz;
+  const int base = (c.iz * V + c.iy) * V + c.ix;
+
+  if (a.rgb) {
+    // 3-channel grid (point_cloud.py:111-118): plain per-lane reductions (non-default path).
+    if (c.valid) {
+      const float* col = a.rgb + ((size_t)b * a.N + p_first + tid) * 3;
+      const float cr = col[0], cg = col[1], cb = col[2];
+      float* g3 = a.vox_rgb + (size_t)b * Vz * V * V * 3;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (c.iz + k < Vz && c.iy + j < V && c.ix + i < V) {
+              const float ww = w[k * 4 + j * 2 + i];
+              float* q = g3 + (size_t)(base + (k * V + j) * V + i) * 3;
+              dpc_red_add(q + 0, __fmul_rn(ww, cr));
+              dpc_red_add(q + 1, __fmul_rn(ww, cg));
+              dpc_red_add(q + 2, __fmul_rn(ww, cb));
+            }
+          }
+    }
+  }
+
+  // ---- warp aggregation: lanes whose points share a base voxel fold their 8 weights into the
+  // lowest lane of the group, so a clustered cloud (decoder init, stddev 0.025) issues one
+  // reduction per corner per group instead of 32 serialised same-address ones.
+  const int key = c.valid ? base : (-1 - lane);
+  const unsigned peers = __match_any_sync(DPC_FULL, key);
+  const int cnt = __popc(peers);
+  const int maxcnt = __reduce_max_sync(DPC_FULL, cnt);
+  if (maxcnt > 1) {
+    float s[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = w[q];
+    unsigned rem = peers & ~(1u << lane);
+    for (int it = 1; it < maxcnt; ++it) {
+      const int src = rem ? (__ffs(rem) - 1) : lane;
+      rem &= rem - 1;
+      const bool take = it < cnt;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float v = __shfl_sync(DPC_FULL, w[q], src);
+        if (take) s[q] += v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) w[q] = s[q];
+  }
+  const bool leader = c.valid && (lane == (__ffs(peers) - 1));
+  if (!leader) return;
+
+  float* g = a.vox + (size_t)b * Vz * V * V + base;
+  const bool pair_ok = ((V & 1) == 0) && ((c.ix & 1) == 0) && ((((uintptr_t)a.vox) & 7u) == 0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (c.iz + k >= Vz) continue;  // only for a coordinate of exactly +0.5 (weight is 0): TF-GPU drops it
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (c.iy + j >= V) continue;
+      float* row = g + (k * V + j) * V;
+      if (pair_ok) {
+        dpc_red_add2(row, w[k * 4 + j * 2 + 0], w[k * 4 + j * 2 + 1]);
+      } else {
+        dpc_red_add(row, w[k * 4 + j * 2 + 0]);
+        if (c.ix + 1 < V) dpc_red_add(row + 1, w[k * 4 + j * 2 + 1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ backward
+struct DpcSplatBwdArgs {
+  const float* pc; const float* pose; const float* trans; const float* focal; const float* rgb;
+  int pose_kind; float focal_const; float cam_dist; int rgb_stop_grad;
+  int B, N, Vz, V;
+  const float* d_vox; const float* d_vox_rgb; const float* d_tr_pc_in;
+  float* d_pc; float* d_pose; float* d_trans; float* d_focal; float* d_rgb;
+};
+
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(DPC_SPLAT_THREADS)
+#else
+static void
+#endif
+dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
+  __shared__ __align__(128) float tile[DPC_SPLAT_THREADS * 3];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float red[DPC_SPLAT_THREADS / 32][12];
+  const int b = blockIdx.y;
+  const int p_first = blockIdx.x * DPC_SPLAT_THREADS;
+  const int n = min(DPC_SPLAT_THREADS, a.N - p_first);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int V = a.V, Vz = a.Vz;
+
+  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n);
+
+  DpcPose P;
+  dpc_pose_load(P, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+
+  const bool live = tid < n;
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  if (live) {
+    const float p0 = tile[tid * 3 + 0], p1 = tile[tid * 3 + 1], p2 = tile[tid * 3 + 2];
+    float z, y, x;
+    DpcCamPoint cam;
+    dpc_transform_point(P, p0, p1, p2, z, y, x, cam);  // same code as forward => same indices
+    const DpcCell c = dpc_cell(z, y, x, Vz, V);
+    float gz = 0.f, gy = 0.f, gx = 0.f;
+    const size_t pi = (size_t)b * a.N + p_first + tid;
+    if (c.valid && (a.d_vox || a.d_vox_rgb)) {
+      const float wz[2] = {1.0f - c.rz, c.rz}, wy[2] = {1.0f - c.ry, c.ry}, wx[2] = {1.0f - c.rx, c.rx};
+      const int base = (c.iz * V + c.iy) * V + c.ix;
+      const float* dv = a.d_vox ? a.d_vox + (size_t)b * Vz * V * V : nullptr;
+      const float* dv3 = a.d_vox_rgb ? a.d_vox_rgb + (size_t)b * Vz * V * V * 3 : nullptr;
+      float cr = 0.f, cg = 0.f, cb = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
+      if (dv3) { const float* col = a.rgb + pi * 3; cr = col[0]; cg = col[1]; cb = col[2]; }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (c.iz + k < Vz && c.iy + j < V && c.ix + i < V) {
+              const int off = base + (k * V + j) * V + i;
+              float dw = dv ? __ldg(dv + off) : 0.0f;  // dL/dw of this corner
+              if (dv3) {
+                const float e0 = __ldg(dv3 + (size_t)off * 3 + 0), e1 = __ldg(dv3 + (size_t)off * 3 + 1),
+                            e2 = __ldg(dv3 + (size_t)off * 3 + 2);
+                const float ww = (wz[k] * wy[j]) * wx[i];
+                dr += ww * e0; dg += ww * e1; db += ww * e2;
+                if (!a.rgb_stop_grad) dw += e0 * cr + e1 * cg + e2 * cb;
+              }
+              gz += (k ? dw : -dw) * (wy[j] * wx[i]);
+              gy += (j ? dw : -dw) * (wz[k] * wx[i]);
+              gx += (i ? dw : -dw) * (wz[k] * wy[j]);
+            }
+          }
+      gz *= (float)(Vz - 1); gy *= (float)(V - 1); gx *= (float)(V - 1);  // d grid / d coordinate
+      if (a.d_rgb) { a.d_rgb[pi * 3 + 0] = dr; a.d_rgb[pi * 3 + 1] = dg; a.d_rgb[pi * 3 + 2] = db; }
+    } else if (a.d_rgb) {
+      a.d_rgb[pi * 3 + 0] = 0.f; a.d_rgb[pi * 3 + 1] = 0.f; a.d_rgb[pi * 3 + 2] = 0.f;
+    }
+    if (a.d_tr_pc_in) {
+      gz += a.d_tr_pc_in[pi * 3 + 0]; gy += a.d_tr_pc_in[pi * 3 + 1]; gx += a.d_tr_pc_in[pi * 3 + 2];
+    }
+    // chain rule applied unconditionally: an invalid but finite point gets exact zeros, a NaN
+    // point propagates NaN into the pose gradient exactly as TF's autodiff does (0 * NaN).
+    dpc_transform_point_bwd(P, p0, p1, p2, cam, gz, gy, gx, d0, d1, d2, acc);
+  }
+  __syncthreads();
+  if (a.d_pc) {
+    if (live) { tile[tid * 3 + 0] = d0; tile[tid * 3 + 1] = d1; tile[tid * 3 + 2] = d2; }
+    __syncthreads();
+    float* dst = a.d_pc + ((size_t)b * a.N + p_first) * 3;
+    for (int i = tid; i < n * 3; i += DPC_SPLAT_THREADS) dst[i] = tile[i];
+  }
+  if (a.pose_kind == DPC_POSE_NONE) return;
+  const bool want_pose = a.d_pose != nullptr, want_t = a.d_trans != nullptr, want_f = a.d_focal != nullptr;
+  if (!(want_pose || want_t || want_f)) return;
+  // block reduction of the per-sample pose gradients: warp shuffles, then one atomic per CTA
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const float v = dpc_warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid < 12) {
+    float v = 0.f;
+    for (int wgi = 0; wgi < DPC_SPLAT_THREADS / 32; ++wgi) v += red[wgi][tid];
+    red[0][tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (a.pose_kind == DPC_POSE_QUAT) {
+      if (want_pose) {
+        float dq[4];
+        dpc_quat_norm_bwd(P, red[0], dq);
+        for (int i = 0; i < 4; ++i) atomicAdd(a.d_pose + b * 4 + i, dq[i]);
+      }
+      if (want_t) for (int i = 0; i < 3; ++i) atomicAdd(a.d_trans + b * 3 + i, red[0][4 + i]);
+      if (want_f) atomicAdd(a.d_focal + b, red[0][7]);
+    } else if (want_pose) {
+      // dL/dE = K^T dL/dM: rows 1,2 scaled by f; row 3 of the extrinsic does not reach the output
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(a.d_pose + b * 16 + 0 + k, red[0][0 + k]);
+        atomicAdd(a.d_pose + b * 16 + 4 + k, red[0][4 + k] * a.focal_const);
+        atomicAdd(a.d_pose + b * 16 + 8 + k, red[0][8 + k] * a.focal_const);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ f-2: dropout gather
+#ifndef DPC_EMU
+__global__ void
+#else
+static void
+#endif
+dpc_gather_kernel(const float* in, const int64_t* sel, int N, int n_keep, int C, float* out) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keep * C) return;
+  const int r = i / C, ch = i - r * C;
+  const int64_t s = sel[(size_t)b * n_keep + r];
+  out[((size_t)b * n_keep + r) * C + ch] = in[((size_t)b * N + s) * C + ch];
+}
+
+#ifndef DPC_EMU
+__global__ void
+#else
+static void
+#endif
+dpc_gather_bwd_kernel(const float* g_out, const int64_t* sel, int N, int n_keep, int C, float* g_in) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keep * C) return;
+  const int r = i / C, ch = i - r * C;
+  const int64_t s = sel[(size_t)b * n_keep + r];
+  atomicAdd(g_in + ((size_t)b * N + s) * C + ch, g_out[((size_t)b * n_keep + r) * C + ch]);
+}

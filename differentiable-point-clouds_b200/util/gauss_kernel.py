@@ -1,0 +1,59 @@
+"""Drop-in for the reference's `dpc/util/gauss_kernel.py` (runtime Gaussian taps).
+
+  /root/reference/dpc/util/gauss_kernel.py:5   gauss_kernel_1d
+  /root/reference/dpc/util/gauss_kernel.py:27  separable_kernels
+  /root/reference/dpc/util/gauss_kernel.py:35  smoothing_kernel
+
+sigma is a run-time value (a function of the global step, model_pc.py:35-40), so the taps are a
+device buffer handed to the kernels, never a compile-time constant.  They are a few dozen
+floats; building them is plain torch on whatever device sigma lives on.
+"""
+import math
+
+import torch
+
+from .point_cloud import SeparableKernel
+
+
+def gauss_kernel_1d(l, sig):
+    """Gaussian taps of length l: x = range(-l//2 + 1, l//2 + 1) with Python's precedence
+    (l=21 -> -10..10, l=10 -> -4..5), exp(-x^2 / (2 sig^2)), normalised to sum 1."""
+    lo, hi = (-l) // 2 + 1.0, l // 2 + 1.0
+    if torch.is_tensor(sig):
+        xx = torch.arange(lo, hi, dtype=torch.float32, device=sig.device)
+        sig = sig.to(torch.float32)
+    else:
+        xx = torch.arange(lo, hi, dtype=torch.float32)
+    k = torch.exp(-xx ** 2 / (2.0 * sig ** 2))
+    return k / k.sum()
+
+
+def separable_kernels(kernel):
+    size = kernel.shape[0]
+    out = SeparableKernel([kernel.reshape(1, 1, size, 1, 1), kernel.reshape(1, size, 1, 1, 1),
+                           kernel.reshape(size, 1, 1, 1, 1)])
+    out.taps_xy = kernel.contiguous()
+    out.taps_z = out.taps_xy
+    return out
+
+
+def smoothing_kernel(cfg, sigma):
+    """[k1 (1,1,K,1,1), k2 (1,K,1,1,1), k3 (Kz,1,1,1,1)]; with cfg.vox_size_z != -1 the depth filter
+    uses sigma*Vz/V and floor(K*Vz/V) taps bumped to odd."""
+    fsz = int(cfg.pc_gauss_kernel_size)
+    k1d = gauss_kernel_1d(fsz, sigma)
+    if int(cfg.vox_size_z) != -1:
+        ratio = cfg.vox_size_z / cfg.vox_size
+        fsz_z = int(math.floor(fsz * ratio))
+        if fsz_z % 2 == 0:
+            fsz_z += 1
+        kz = gauss_kernel_1d(fsz_z, sigma * ratio)
+        out = SeparableKernel([k1d.reshape(1, 1, fsz, 1, 1), k1d.reshape(1, fsz, 1, 1, 1),
+                               kz.reshape(fsz_z, 1, 1, 1, 1)])
+        out.taps_xy = k1d.contiguous()
+        out.taps_z = kz.contiguous()
+        return out
+    if not cfg.pc_separable_gauss_filter:
+        # the reference reaches an unbound local here (gauss_kernel.py:51-54)
+        raise NotImplementedError("pc_separable_gauss_filter=false has no kernel in the reference either")
+    return separable_kernels(k1d)

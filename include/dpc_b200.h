@@ -1,0 +1,158 @@
+/* dpc_b200.h -- C-ABI of the B200-native differentiable point-cloud projection path.
+ *
+ * Drop-in boundary for the hot path of eldar/differentiable-point-clouds:
+ *   dpc/util/point_cloud.py:157-216  pc_perspective_transform      -> dpc_splat_fwd (pose stage)
+ *   dpc/util/point_cloud.py:60-136   pointcloud2voxels3d_fast      -> dpc_splat_fwd / dpc_splat_bwd
+ *   dpc/util/point_cloud.py:139-145  smoothen_voxels3d             -> dpc_conv_xy + dpc_conv_z_fwd
+ *   dpc/util/drc.py:47-123,139-153   drc_projection / depth        -> dpc_conv_z_fwd / dpc_conv_z_bwd (Kz = 1)
+ *   dpc/util/point_cloud.py:229-290  pointcloud_project_fast       -> dpc_project_fast_fwd / _bwd
+ *
+ * The reference has no FFI of its own (it is Python calling TensorFlow ops); these are the
+ * entry points a binding for this path would need -- see INTEGRATION.md for the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers to DEVICE memory (fp32 unless stated), C-contiguous, reference axis order:
+ *       point clouds [B,N,3]; grids [B,Vz,V,V]; silhouettes [B,V,V]; drc_probs [Vz+1,B,V,V].
+ *     tr_pc channel 0 is depth and indexes the Vz axis (point_cloud.py:215).
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work (no host sync),
+ *     keeps no static mutable state and is re-entrant.
+ *   - every function returns 0 on success or a negative DPC_ERR_* code; nothing throws.
+ *     dpc_last_cuda_error() reports the CUDA error behind DPC_ERR_CUDA for the calling thread.
+ *   - nullable arguments are marked; outputs are written by the callee, never read first unless
+ *     stated ("accumulates").
+ */
+#ifndef DPC_B200_H_
+#define DPC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPC_OK 0
+#define DPC_ERR_NULL (-1)     /* a required pointer is NULL                         */
+#define DPC_ERR_SHAPE (-2)    /* B/N/V/Vz/K out of the supported range              */
+#define DPC_ERR_ARG (-3)      /* inconsistent flags (e.g. translation with a matrix pose) */
+#define DPC_ERR_CUDA (-4)     /* a CUDA call failed; see dpc_last_cuda_error()      */
+#define DPC_ERR_WORKSPACE (-5)/* workspace too small                                */
+
+#define DPC_POSE_NONE (-1)   /* points are already in camera space (pointcloud2voxels3d_fast alone) */
+#define DPC_POSE_QUAT 0      /* [B,4] unnormalised quaternion, w first (cfg.pose_quaternion) */
+#define DPC_POSE_MATRIX 1    /* [B,4,4] extrinsic; intrinsic diag(1,f,f,1) applied inside (camera.py:5-13) */
+
+#define DPC_PROJ_NONE (-1)      /* no projection (smoothen_voxels3d alone)            */
+#define DPC_PROJ_DRC 0          /* ray termination sum, drc_logsum quirks (drc.py:47-123) */
+#define DPC_PROJ_MAX 1          /* tf.reduce_max over depth (point_cloud.py:265)      */
+#define DPC_PROJ_DRC_PROD 2     /* drc_logsum=false variant (cumprod, unity 1)        */
+
+#define DPC_MAX_TAPS 63
+#define DPC_MAX_V 128
+
+int dpc_abi_version(void);
+const char* dpc_error_string(int code);
+int dpc_last_cuda_error(void);
+/* compiled for sm_100a?  1 = real CUDA build, 0 = the CPU emulation build used by tests/emu */
+int dpc_is_cuda_build(void);
+
+/* ---- K1: camera transform + validity + trilinear splat, one fused kernel -----------------
+ * pose: [B,4] or [B,4,4] per pose_kind (NULL for DPC_POSE_NONE).  trans: [B,3] or NULL (quaternion
+ * pose only).  focal: [B] or NULL (then focal_const; the matrix pose always uses focal_const).
+ * rgb: [B,N,3] or NULL.  Outputs: tr_pc [B,N,3] (nullable), vox [B,Vz,V,V] (nullable = transform
+ * only; ACCUMULATES: caller zeroes it, dpc_project_fast_fwd does so itself), vox_rgb [B,Vz,V,V,3]
+ * (required iff rgb; accumulates), idx_out int32 [B,N,3] = floor((p+0.5)*(S-1)) (nullable; the
+ * bit-exact parity gate), valid_out uint8 [B,N] (nullable). */
+int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float* trans,
+                  const float* focal, float focal_const, float cam_dist, const float* rgb,
+                  int B, int N, int Vz, int V,
+                  float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
+                  void* stream);
+
+/* ---- K1b: backward of K1.  d_vox [B,Vz,V,V] (nullable), d_vox_rgb (nullable), d_tr_pc_in
+ * [B,N,3] = gradient arriving directly at the tr_pc output (nullable).  rgb_stop_grad mirrors
+ * cfg.pc_rgb_stop_points_gradient.  Outputs (each nullable): d_pc [B,N,3]; d_pose [B,4]|[B,4,4],
+ * d_trans [B,3], d_focal [B] ACCUMULATE (caller zeroes); d_rgb [B,N,3]. */
+int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float* trans,
+                  const float* focal, float focal_const, float cam_dist, const float* rgb,
+                  int rgb_stop_grad, int B, int N, int Vz, int V,
+                  const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
+                  float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
+                  void* stream);
+
+/* ---- K2a: per depth-slice: [clip to [0,1]] -> correlate along x (taps_x) -> along y (taps_y)
+ * -> [multiply by a saved pass mask].  Zero padding, pad_lo taps to the low side (TF "SAME":
+ * (K-1)/2).  The backward of a correlation with (taps, pad_lo) is this same call with reversed
+ * taps and pad_lo' = K-1-pad_lo.
+ *   clip_in != 0      : input is clipped to [0,1] first (point_cloud.py:240)
+ *   mask_bits_out     : uint32 [B*Vz*V*V/32] (nullable) bit = (0 <= in <= 1), the clip's pass mask
+ *   mask_bits_in      : (nullable) output is multiplied by the saved mask (backward of the clip) */
+int dpc_conv_xy(const float* in, float* out, const float* taps_x, int Kx, int pad_lo_x,
+                const float* taps_y, int Ky, int pad_lo_y, int B, int Vz, int V,
+                int clip_in, uint32_t* mask_bits_out, const uint32_t* mask_bits_in, void* stream);
+
+/* ---- K2b+K3 forward: correlate along depth (taps_z) -> [* scale[b], clip to [0,1]] ->
+ * projection along depth, one kernel (the depth axis is resident per ray).
+ *   scale [B] nullable.  mode: DPC_PROJ_*.  flip_y: write proj / drc_probs with the image-row
+ *   axis reversed (point_cloud.py:270,273); the standalone drc_projection uses flip_y = 0.
+ *   Outputs: vox_out [B,Vz,V,V]; mask2_out uint32 [B*Vz*V*V/32]... stored per ray as
+ *   ceil(Vz/32) words: [B,V,V,ceil(Vz/32)] (nullable) bit z = (0 <= scale*smoothed <= 1);
+ *   proj [B,V,V] (nullable iff mode NONE); drc_probs [Vz+1,B,V,V] (nullable);
+ *   proj_depth [B,V,V] (nullable; needs DRC mode). */
+int dpc_conv_z_fwd(const float* in, const float* taps_z, int Kz, int pad_lo_z,
+                   const float* scale, int mode, float clip_eps, float cam_dist, float max_depth,
+                   int flip_y, int B, int Vz, int V,
+                   float* vox_out, uint32_t* mask2_out, float* proj, float* drc_probs,
+                   float* proj_depth, void* stream);
+
+/* ---- K3b+K2b backward: from the gradients at proj / voxels / drc_probs / proj_depth (each
+ * nullable) back through projection, clip, scale and the depth correlation.
+ *   vox [B,Vz,V,V] is the forward's vox_out; mask2 its mask2_out (NULL = no scale/clip stage);
+ *   taps_z_rev / pad_lo_z_rev are the reversed taps (see dpc_conv_xy).
+ *   Outputs: d_in [B,Vz,V,V] gradient w.r.t. the forward's `in`; d_scale [B] ACCUMULATES (nullable). */
+int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
+                   const float* taps_z_rev, int Kz, int pad_lo_z_rev,
+                   int mode, float clip_eps, float cam_dist, float max_depth, int flip_y,
+                   int B, int Vz, int V,
+                   const float* g_proj, const float* g_vox, const float* g_probs, const float* g_depth,
+                   float* d_in, float* d_scale, void* stream);
+
+/* ---- the fused pipeline of pointcloud_project_fast (no rgb) -------------------------------
+ * Workspace (device, caller-owned, 16-byte aligned): dpc_project_fast_workspace_bytes().
+ * Forward keeps in the workspace what the backward needs (clip masks); pass the SAME workspace,
+ * untouched, to the backward.  taps: fp32 device arrays (NULL taps with K = 0 mean "no kernel"). */
+typedef struct {
+  int B, N, Vz, V;
+  int pose_kind;        /* DPC_POSE_* */
+  int mode;             /* DPC_PROJ_DRC | DPC_PROJ_MAX | DPC_PROJ_DRC_PROD */
+  int K, Kz;            /* tap counts along x/y and along depth; 0 = no smoothing */
+  float focal_const, cam_dist, clip_eps, max_depth;
+} dpc_project_params;
+
+int64_t dpc_project_fast_workspace_bytes(const dpc_project_params* p);
+
+int dpc_project_fast_fwd(const dpc_project_params* p,
+                         const float* pc, const float* pose, const float* trans, const float* focal,
+                         const float* scale, const float* taps_xy, const float* taps_z,
+                         float* tr_pc, float* voxels, float* proj, float* drc_probs, float* proj_depth,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+int dpc_project_fast_bwd(const dpc_project_params* p,
+                         const float* pc, const float* pose, const float* trans, const float* focal,
+                         const float* scale, const float* taps_xy, const float* taps_z,
+                         const float* voxels,
+                         const float* g_proj, const float* g_voxels, const float* g_tr_pc,
+                         const float* g_probs, const float* g_depth,
+                         float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_scale,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- f-2: point dropout gather (point_cloud.py:312-318): out[b,i,:] = in[b, sel[b,i], :] and its
+ * backward (scatter-add).  sel int64 [B,n_keep]. */
+int dpc_gather_points(const float* in, const int64_t* sel, int B, int N, int n_keep, int C,
+                      float* out, void* stream);
+int dpc_gather_points_bwd(const float* g_out, const int64_t* sel, int B, int N, int n_keep, int C,
+                          float* g_in /* zeroed by callee */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPC_B200_H_ */

@@ -82,3 +82,36 @@ def max_abs_diff(a, b):
     if not m.any():
         return 0.0
     return float(np.max(np.abs(a[m] - b[m])))
+
+
+def assert_parity(fx, outs, grads, atol=ATOL, exact_transform=None):
+    """The north-star gate: tr_pc bit-exact (quaternion pose), every grid / silhouette / gradient
+    within 1e-5 abs of the reference (gradients: relative to max(1, |g|_inf) for the per-sample sums)."""
+    if exact_transform is None:
+        exact_transform = fx["cfg_over"].get("pose_quaternion", True)
+    if exact_transform:
+        assert nan_equal_bits(outs["tr_pc"].numpy(), fx["out_tr_pc"]), "tr_pc must be bit-exact"
+    else:
+        assert max_abs_diff(outs["tr_pc"].numpy(), fx["out_tr_pc"]) <= 1e-6
+    for k in OUTPUT_KEYS:
+        ref = fx.get("out_" + k)
+        if ref is None:
+            assert outs[k] is None, k
+            continue
+        assert outs[k] is not None, k
+        assert tuple(outs[k].shape) == ref.shape, (k, tuple(outs[k].shape), ref.shape)
+        d = max_abs_diff(outs[k].numpy(), ref)
+        assert d <= atol, "%s: max abs diff %.3g" % (k, d)
+    for k, v in fx.items():
+        if not k.startswith("grad_"):
+            continue
+        name = k[5:]
+        assert name in grads, "missing gradient for " + name
+        g = grads[name].numpy()
+        finite = np.isfinite(v)
+        if not finite.all():
+            # the reference propagates NaN from a NaN input point into the per-sample sums
+            assert np.array_equal(np.isnan(g), np.isnan(v)) or name in ("transform",), name
+        scale = max(1.0, float(np.max(np.abs(v[finite])))) if finite.any() else 1.0
+        d = max_abs_diff(np.where(finite, g, 0), np.where(finite, v, 0))
+        assert d <= atol * scale, "grad %s: max abs diff %.3g (scale %.3g)" % (name, d, scale)

@@ -1,0 +1,26 @@
+"""CPU: the product's host code + the real kernel sources, executed by the CUDA-model emulator
+(tests/emu), against the golden fixtures generated from the reference's own source.  Same
+assertions as the GPU parity tests (tests/test_gpu_parity.py), on the small cases."""
+import numpy as np
+import pytest
+import torch
+
+import dpc_b200.util.gauss_kernel as gk
+import dpc_b200.util.point_cloud as pcm
+from tests import cases
+from tests.emu_support import emu  # noqa: F401
+
+
+class Product:
+    smoothing_kernel = staticmethod(gk.smoothing_kernel)
+    pointcloud_project_fast = staticmethod(pcm.pointcloud_project_fast)
+
+
+SMALL = [n for n in cases.golden_names() if n not in ("v64_small", "cfg1_drc_k21_sigma3")]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_emulated_kernels_match_golden(emu, name):  # noqa: F811
+    fx = cases.load_golden(name)
+    outs, grads = cases.run_impl(Product, fx)
+    cases.assert_parity(fx, outs, grads)
