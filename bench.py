@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the projection hot path (BASELINE.json metric):
+
+    point-cloud projections/sec (forward + backward) at B=32 N=8000 V=64, K=21 taps, sigma_rel=3.0,
+    quaternion pose, occupancy scaling, DRC projection, loss = sum((gt-proj)^2)/2/B.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+One "step" = one forward+backward pass of `pointcloud_project_fast` over one batch of B=32
+synthetic clouds per GPU (weak scaling: every rank renders its own 32 samples, no data-path
+collective).  `value` is timed on the device with CUDA events, inputs resident in HBM, calling
+the C-ABI directly; `e2e` is the same metric through the reference-shaped Python API with pinned
+HOST buffers, H2D/D2H copies inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, N, V, K, SIGMA = 32, 8000, 64, 21, 3.0
+METRIC = "point-cloud projections/sec (fwd+bwd) at B=32 N=8000 V=64"
+UNIT = "projections/s"
+G_BYTES = V * V * V * 4
+# algorithmic bytes per projection, SURVEY.md 8(d): full path 6g + 4n + 64N + 2s
+FULL_PATH_BYTES = 6 * G_BYTES + 4 * 12 * N + 64 * N + 2 * 4 * V * V
+# per-launch algorithmic bytes of each stage, per projection (DESIGN.md "kernels and rooflines")
+STAGE_BYTES = {
+    "splat_fwd": G_BYTES + 2 * 12 * N + 32 * N,          # zero grid + read pc + write tr_pc + 8 corner RMW
+    "conv_xy_fwd": 2 * G_BYTES + G_BYTES // 32,          # read raw, write xy-smoothed, clip-mask bits
+    "conv_z_fwd": 2 * G_BYTES + G_BYTES // 32 + 4 * V * V,  # read, write voxels, mask bits, silhouette
+    "conv_z_bwd": 2 * G_BYTES + G_BYTES // 32 + 4 * V * V,
+    "conv_xy_bwd": 2 * G_BYTES + G_BYTES // 32,
+    "splat_bwd": G_BYTES + 2 * 12 * N + 32 * N,          # read d_raw (gathers) + read pc + write d_pc
+}
+
+
+def make_inputs(batch, seed_shift=0, clustered=False):
+    g = lambda s: torch.Generator().manual_seed(s + 1000 * seed_shift)  # noqa: E731
+    spread, seed = (0.025, 1235) if clustered else (0.5, 1234)
+    pc = torch.tanh(spread * torch.randn(batch, N, 3, generator=g(seed))) / 2
+    q = torch.randn(batch, 4, generator=g(1236))
+    sc = torch.sigmoid(torch.randn(batch, 1, generator=g(1237)))
+    gt = (torch.rand(batch, V, V, 1, generator=g(1238)) > 0.5).float()
+    return pc, q, sc, gt
+
+
+def bench_cfg():
+    from dpc_b200.util.config import default_config
+    return default_config(vox_size=V, pc_gauss_kernel_size=K, pc_relative_sigma=SIGMA)
+
+
+# ----------------------------------------------------------------------------- reference arm / cpu baseline
+def time_oracle(batch, steps, warmup, threads):
+    """The reference's CPU implementation of the path (oracle port: torch-CPU op-for-op restatement
+    built like the reference -- 8 scatter grids + add_n, three conv3d, log-space DRC, autograd)."""
+    from oracle import dpc_oracle as O
+    torch.set_num_threads(threads)
+    cfg = bench_cfg()
+    pc, q, sc, gt = make_inputs(batch)
+    ker = O.smoothing_kernel(cfg, torch.tensor(SIGMA))
+    times = []
+    for it in range(warmup + steps):
+        a = [t.clone().requires_grad_(True) for t in (pc, q, sc)]
+        t0 = time.perf_counter()
+        out = O.pointcloud_project_fast(cfg, a[0], a[1], None, None, ker, a[2])
+        loss = ((gt - out["proj"]) ** 2).sum() / 2 / batch
+        loss.backward()
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    return sum(times), len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = args.ref_batch
+    total, n = time_oracle(batch, args.steps, max(1, min(args.warmup, 2)), threads)
+    value = batch * n / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": n, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1000.0 * total / n,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pointcloud_project_fast fwd+bwd, N=8000 V=64 K=21 sigma_rel=3.0, DRC, quaternion pose",
+                   "sample_batch": batch, "note": "reference TF1 path restated on torch-CPU (TensorFlow unavailable)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d steps of a B=%d batch of the same workload" % (n, batch)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for nm in dir(nv):
+            if nm.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, nm), int):
+                names[getattr(nv, nm)] = nm.replace("nvmlClocksThrottleReason", "")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if bit and (bits & bit) == bit and nm not in ("None", "All"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- our arm
+class Pipeline:
+    """Device buffers + C-ABI calls for one rank (B samples)."""
+
+    def __init__(self, dev, seed_shift):
+        from dpc_b200 import _capi
+        from dpc_b200.util import gauss_kernel as gk
+        self.capi, self.L, self.dev = _capi, _capi.lib(), dev
+        self.cfg = bench_cfg()
+        host = make_inputs(B, seed_shift)
+        self.host = [t.pin_memory() for t in host]
+        self.pc, self.q, self.sc, self.gt = [t.to(dev) for t in host]
+        self.sc1 = self.sc.reshape(-1).contiguous()
+        self.gt3 = self.gt.reshape(B, V, V).contiguous()
+        self.kernel = gk.smoothing_kernel(self.cfg, torch.tensor(SIGMA, device=dev))
+        self.taps = self.kernel.taps_xy
+        self.p = _capi.ProjectParams(B=B, N=N, Vz=V, V=V, pose_kind=_capi.POSE_QUAT, mode=_capi.PROJ_DRC, K=K, Kz=K,
+                                     focal_const=float(self.cfg.focal_length), cam_dist=float(self.cfg.camera_distance),
+                                     clip_eps=float(self.cfg.drc_logsum_clip_val), max_depth=float(self.cfg.max_depth))
+        self.ws_bytes = self.L.dpc_project_fast_workspace_bytes(ctypes.byref(self.p))
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.tr_pc, self.vox, self.proj, self.g_proj = f(B, N, 3), f(B, V, V, V), f(B, V, V), f(B, V, V)
+        self.d_pc, self.d_q, self.d_sc = f(B, N, 3), f(B, 4), f(B)
+        self.stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def step(self):
+        L, p, c = self.L, self.p, self.capi.check
+        c(L.dpc_project_fast_fwd(ctypes.byref(p), self.pc.data_ptr(), self.q.data_ptr(), None, None, self.sc1.data_ptr(),
+                                 self.taps.data_ptr(), self.taps.data_ptr(), self.tr_pc.data_ptr(), self.vox.data_ptr(),
+                                 self.proj.data_ptr(), None, None, self.ws.data_ptr(), self.ws_bytes, self.stream))
+        # dL/dproj of sum((gt-proj)^2)/2/B  (model_pc.py:414-415) -- loss side, plain torch
+        torch.sub(self.proj, self.gt3, out=self.g_proj)
+        self.g_proj.mul_(1.0 / B)
+        c(L.dpc_project_fast_bwd(ctypes.byref(p), self.pc.data_ptr(), self.q.data_ptr(), None, None, self.sc1.data_ptr(),
+                                 self.taps.data_ptr(), self.taps.data_ptr(), self.vox.data_ptr(), self.g_proj.data_ptr(),
+                                 None, None, None, None, self.d_pc.data_ptr(), self.d_q.data_ptr(), None, None,
+                                 self.d_sc.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self.stream))
+
+    LAUNCHES_PER_STEP = 7  # prepare_taps, splat_fwd, conv_xy, conv_z_fwd, conv_z_bwd, conv_xy, splat_bwd
+
+    def stage_times(self, steps, flush):
+        """Per-stage device time (CUDA events on the launch stream), same kernels as step()."""
+        L, c, cp = self.L, self.capi.check, self.capi
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.dev)  # noqa: E731
+        raw, tmp = f(B, V, V, V), f(B, V, V, V)
+        m1 = torch.empty(B * V * V * V // 32 + 1, dtype=torch.int32, device=self.dev)
+        m2 = torch.empty(B * V * V * 2, dtype=torch.int32, device=self.dev)
+        taps, rev = self.taps, self.taps.flip(0).contiguous()
+        st = self.stream
+        cfg = self.cfg
+        fo, cd, eps, md = float(cfg.focal_length), float(cfg.camera_distance), float(cfg.drc_logsum_clip_val), float(cfg.max_depth)
+        pl = (K - 1) // 2
+
+        def s_splat_fwd():
+            raw.zero_()
+            c(L.dpc_splat_fwd(self.pc.data_ptr(), self.q.data_ptr(), cp.POSE_QUAT, None, None, fo, cd, None, B, N, V, V,
+                              self.tr_pc.data_ptr(), raw.data_ptr(), None, None, None, st))
+
+        def s_conv_xy_fwd():
+            c(L.dpc_conv_xy(raw.data_ptr(), tmp.data_ptr(), taps.data_ptr(), K, pl, taps.data_ptr(), K, pl, B, V, V, 1,
+                            m1.data_ptr(), None, st))
+
+        def s_conv_z_fwd():
+            c(L.dpc_conv_z_fwd(tmp.data_ptr(), taps.data_ptr(), K, pl, self.sc1.data_ptr(), cp.PROJ_DRC, eps, cd, md, 1,
+                               B, V, V, self.vox.data_ptr(), m2.data_ptr(), self.proj.data_ptr(), None, None, st))
+
+        def s_conv_z_bwd():
+            self.d_sc.zero_()
+            c(L.dpc_conv_z_bwd(self.vox.data_ptr(), m2.data_ptr(), self.sc1.data_ptr(), rev.data_ptr(), K, K - 1 - pl,
+                               cp.PROJ_DRC, eps, cd, md, 1, B, V, V, self.g_proj.data_ptr(), None, None, None,
+                               tmp.data_ptr(), self.d_sc.data_ptr(), st))
+
+        def s_conv_xy_bwd():
+            c(L.dpc_conv_xy(tmp.data_ptr(), raw.data_ptr(), rev.data_ptr(), K, K - 1 - pl, rev.data_ptr(), K, K - 1 - pl,
+                            B, V, V, 0, None, m1.data_ptr(), st))
+
+        def s_splat_bwd():
+            self.d_q.zero_()
+            c(L.dpc_splat_bwd(self.pc.data_ptr(), self.q.data_ptr(), cp.POSE_QUAT, None, None, fo, cd, None, 0, B, N, V, V,
+                              raw.data_ptr(), None, None, self.d_pc.data_ptr(), self.d_q.data_ptr(), None, None, None, st))
+
+        stages = [("splat_fwd", s_splat_fwd), ("conv_xy_fwd", s_conv_xy_fwd), ("conv_z_fwd", s_conv_z_fwd),
+                  ("conv_z_bwd", s_conv_z_bwd), ("conv_xy_bwd", s_conv_xy_bwd), ("splat_bwd", s_splat_bwd)]
+        tot = {k: 0.0 for k, _ in stages}
+        for it in range(steps + 2):
+            if flush is not None:
+                flush.fill_(it)
+            evs = []
+            for name, fn in stages:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                if name == "conv_z_fwd":
+                    torch.sub(self.proj, self.gt3, out=self.g_proj)
+                e1.record()
+                evs.append((name, e0, e1))
+            torch.cuda.synchronize()
+            if it >= 2:
+                for name, e0, e1 in evs:
+                    tot[name] += e0.elapsed_time(e1)
+        return {k: v / steps for k, v in tot.items()}
+
+    def e2e_step(self):
+        """Through the public API with host buffers: H2D inputs, forward, loss, backward, D2H results."""
+        from dpc_b200.util import point_cloud as pcm
+        hp, hq, hs, hg = self.host
+        pc = hp.to(self.dev, non_blocking=True).requires_grad_(True)
+        q = hq.to(self.dev, non_blocking=True).requires_grad_(True)
+        sc = hs.to(self.dev, non_blocking=True).requires_grad_(True)
+        gt = hg.to(self.dev, non_blocking=True)
+        out = pcm.pointcloud_project_fast(self.cfg, pc, q, None, None, self.kernel, sc)
+        loss = ((gt - out["proj"]) ** 2).sum() / 2 / B
+        loss.backward()
+        res = [loss.detach(), out["proj"].detach(), pc.grad, q.grad, sc.grad]
+        host = [t.to("cpu", non_blocking=True) for t in res]
+        torch.cuda.current_stream().synchronize()
+        h2d = sum(t.numel() * t.element_size() for t in (hp, hq, hs, hg))
+        d2h = sum(t.numel() * t.element_size() for t in res)
+        return float(host[0]), h2d, d2h
+
+
+def run_ours(args, rank, local_rank, world):
+    from dpc_b200 import distributed as D
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path); "
+                           "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pipe = Pipeline(dev, seed_shift=rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if args.l2_flush else None
+    for _ in range(max(3, args.warmup)):
+        pipe.step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    D.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    evs = []
+    for it in range(args.steps):
+        if flush is not None:
+            flush.fill_(it & 0xff)          # evict L2 between steps (outside the timed events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe.step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    D.barrier()
+    clocks = sampler.stop()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    ms_total = D.reduce_scalar(ms_total, "max", dev)
+    units = D.reduce_scalar(float(B * args.steps), "sum", dev)
+    value = units / (ms_total / 1000.0)
+
+    # end-to-end through the Python API with host buffers
+    for _ in range(3):
+        pipe.e2e_step()
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(5, min(args.steps, 50))
+    for _ in range(n_e2e):
+        loss, h2d, d2h = pipe.e2e_step()
+    t_e2e = D.reduce_scalar(time.perf_counter() - t0, "max", dev)
+    e2e_value = world * B * n_e2e / t_e2e
+
+    line = None
+    if rank == 0:
+        import json as _json
+        peaks = {}
+        try:
+            peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        stages = pipe.stage_times(min(args.steps, 20), flush)
+        dom = max(stages, key=stages.get)
+        achieved = STAGE_BYTES[dom] * B / (stages[dom] * 1e-3) / 1e9
+        step_gbs = FULL_PATH_BYTES * B / ((ms_total / args.steps) * 1e-3) / 1e9 if world == 1 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: pointcloud_project_fast fwd+bwd, B=32 per GPU, N=8000, V=64, K=21, sigma_rel=3.0, "
+                                   "DRC projection, quaternion pose, occupancy scaling",
+                       "global_batch": B * world, "parallelism": "independent samples sharded over ranks, no collective",
+                       "l2": ("256 MiB written between steps (untimed) to evict L2" if args.l2_flush else
+                              "no flush; a step touches ~200 MB of grids > 126 MB L2")},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000.0 * t_e2e / n_e2e, "loss": loss},
+            "gpu_launches": Pipeline.LAUNCHES_PER_STEP * args.steps,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": STAGE_BYTES[dom] * B},
+            "roofline_step": {"algorithmic_bytes_per_projection": FULL_PATH_BYTES, "achieved": step_gbs,
+                              "frac": (step_gbs / peak) if step_gbs else None, "unit": "GB/s"},
+            "stages_ms": stages,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            total, n = time_oracle(args.ref_batch, 2, 1, threads)
+            line["cpu_baseline"] = {"value": args.ref_batch * n / total, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d fwd+bwd steps of a B=%d batch of the same workload (oracle, torch-CPU)"
+                                              % (n, args.ref_batch)}
+        print(json.dumps(line))
+    D.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=4, help="batch of the bounded CPU sample")
+    ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from dpc_b200 import distributed as D
+    rank, local_rank, world = D.env_world()
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    rank, local_rank, world = D.init()
+    run_ours(args, rank, local_rank, world)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -292,21 +292,18 @@ class _ProjectFastFn(torch.autograd.Function):
         tr_pc = torch.empty_like(pc)
         voxels = torch.empty(b, vz, v, v, dtype=torch.float32, device=dev)
         proj = torch.empty(b, v, v, dtype=torch.float32, device=dev)
-        drc = params.mode != PROJ_MAX
-        probs = torch.empty(vz + 1, b, v, v, dtype=torch.float32, device=dev) if drc else None
-        depth = torch.empty(b, v, v, dtype=torch.float32, device=dev) if drc else None
+        # drc_probs / proj_depth are NOT written here: the training loss consumes only `proj`
+        # (default_config.yaml:111-115) and the event tensor is another full grid of HBM traffic.
+        # ProjectionOutputs derives them from `voxels` on first access.
         check(L.dpc_project_fast_fwd(ctypes.byref(params), ptr(pc), ptr(pose), ptr(trans), ptr(focal), ptr(scale),
-                                     ptr(taps_xy), ptr(taps_z), ptr(tr_pc), ptr(voxels), ptr(proj), ptr(probs),
-                                     ptr(depth), ptr(ws), ws_bytes, stream_of(pc)))
+                                     ptr(taps_xy), ptr(taps_z), ptr(tr_pc), ptr(voxels), ptr(proj), None,
+                                     None, ptr(ws), ws_bytes, stream_of(pc)))
         ctx.save_for_backward(pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, ws)
         ctx.params = params
-        e = pc.new_empty(0)
-        outs = (tr_pc, voxels, proj, probs if drc else e, depth if drc else e)
-        ctx.mark_non_differentiable(*[o for o in outs if o.numel() == 0])
-        return outs
+        return tr_pc, voxels, proj
 
     @staticmethod
-    def backward(ctx, g_tr, g_vox, g_proj, g_probs, g_depth):
+    def backward(ctx, g_tr, g_vox, g_proj):
         L = _capi.lib()
         pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, ws = ctx.saved_tensors
         params = ctx.params
@@ -315,7 +312,7 @@ class _ProjectFastFn(torch.autograd.Function):
         def opt(g):
             return f32c(g) if (g is not None and g.numel()) else None
 
-        g_tr, g_vox, g_proj, g_probs, g_depth = opt(g_tr), opt(g_vox), opt(g_proj), opt(g_probs), opt(g_depth)
+        g_tr, g_vox, g_proj = opt(g_tr), opt(g_vox), opt(g_proj)
         need = ctx.needs_input_grad
         d_pc = torch.empty_like(pc) if need[0] else None
         d_pose = torch.empty_like(pose) if (pose is not None and need[1]) else None
@@ -324,7 +321,7 @@ class _ProjectFastFn(torch.autograd.Function):
         d_scale = torch.empty_like(scale) if (scale is not None and need[4]) else None
         check(L.dpc_project_fast_bwd(ctypes.byref(params), ptr(pc), ptr(pose), ptr(trans), ptr(focal), ptr(scale),
                                      ptr(taps_xy), ptr(taps_z), ptr(voxels),
-                                     ptr(g_proj), ptr(g_vox), ptr(g_tr), ptr(g_probs), ptr(g_depth),
+                                     ptr(g_proj), ptr(g_vox), ptr(g_tr), None, None,
                                      ptr(d_pc), ptr(d_pose), ptr(d_trans), ptr(d_focal), ptr(d_scale),
                                      ptr(ws), ws.numel(), stream_of(pc)))
         if d_focal is not None:
@@ -332,6 +329,46 @@ class _ProjectFastFn(torch.autograd.Function):
         if d_scale is not None:
             d_scale = d_scale.reshape(b, 1)
         return d_pc, d_pose, d_trans, d_focal, d_scale, None, None, None
+
+
+class ProjectionOutputs(dict):
+    """The reference's seven-key result dict.  In the TF graph unused outputs cost nothing; here
+    `drc_probs` and `proj_depth` are computed from `voxels` (projection kernel, autograd-connected)
+    the first time either key is read, so a caller that only uses `proj` never pays for them."""
+    _LAZY = ("drc_probs", "proj_depth")
+
+    def __init__(self, base, thunk):
+        super().__init__(base)
+        self._thunk = thunk
+
+    def _materialize(self):
+        if self._thunk is not None:
+            thunk, self._thunk = self._thunk, None
+            probs, depth = thunk()
+            super().__setitem__("drc_probs", probs)
+            super().__setitem__("proj_depth", depth)
+
+    def __getitem__(self, key):
+        if key in self._LAZY:
+            self._materialize()
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        if key in self._LAZY:
+            self._materialize()
+        return super().get(key, default)
+
+    def items(self):
+        self._materialize()
+        return super().items()
+
+    def values(self):
+        self._materialize()
+        return super().values()
+
+    def copy(self):
+        self._materialize()
+        return dict(self)
 
 
 def _fused_supported(cfg, point_cloud, kernel_parts):
@@ -369,14 +406,21 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation,
                                K=parts[0].numel() if parts else 0, Kz=parts[2].numel() if parts else 0,
                                focal_const=float(cfg.focal_length), cam_dist=float(cfg.camera_distance),
                                clip_eps=float(cfg.drc_logsum_clip_val), max_depth=float(cfg.max_depth))
-        tr_pc, voxels, proj, probs, depth = _ProjectFastFn.apply(
+        tr_pc, voxels, proj = _ProjectFastFn.apply(
             point_cloud, transform, predicted_translation, focal_length, scaling_factor,
             parts[0] if parts else None, parts[2] if parts else None, params)
-        drc = not cfg.ptn_max_projection
-        return {"proj": proj.unsqueeze(-1), "voxels": voxels.unsqueeze(-1), "tr_pc": tr_pc,
-                "voxels_rgb": None, "proj_rgb": None,
-                "drc_probs": probs.unsqueeze(-1) if drc else None,
-                "proj_depth": depth.unsqueeze(-1) if drc else None}
+        base = {"proj": proj.unsqueeze(-1), "voxels": voxels.unsqueeze(-1), "tr_pc": tr_pc,
+                "voxels_rgb": None, "proj_rgb": None, "drc_probs": None, "proj_depth": None}
+        if cfg.ptn_max_projection:
+            return base
+        mode, eps = _proj_mode(cfg), float(cfg.drc_logsum_clip_val)
+        cd, md = float(cfg.camera_distance), float(cfg.max_depth)
+
+        def events():
+            _, probs, depth = _ProjectFn.apply(voxels, mode, eps, cd, md, True, True, True)
+            return probs.unsqueeze(-1), depth.unsqueeze(-1)
+
+        return ProjectionOutputs(base, events)
     return _project_composed(cfg, point_cloud, transform, predicted_translation, all_rgb, kernel, parts,
                              scaling_factor, focal_length)
 
