@@ -351,7 +351,7 @@ def run_ours(args, rank, local_rank, world):
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            total, n = time_oracle(args.ref_batch, 2, 1, threads)
+            total, n = time_oracle(args.ref_batch, 3, 1, threads)
             line["cpu_baseline"] = {"value": args.ref_batch * n / total, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d fwd+bwd steps of a B=%d batch of the same workload (oracle, torch-CPU)"
                                               % (n, args.ref_batch)}
@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-batch", type=int, default=4, help="batch of the bounded CPU sample")
+    ap.add_argument("--ref-batch", type=int, default=32, help="batch of the bounded CPU sample")
     ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
