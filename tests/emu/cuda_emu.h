@@ -25,6 +25,8 @@ struct dim3 {
 struct uint3_emu { unsigned x, y, z; };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
@@ -73,6 +75,7 @@ static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float __shfl_sync(unsigned, float v, int src) { return u2f(dpc_emu::exchange(f2u(v), src & 31)); }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)dpc_emu::exchange((uint32_t)v, src & 31); }
 static inline float __shfl_xor_sync(unsigned, float v, int m) { return u2f(dpc_emu::exchange(f2u(v), (dpc_emu::t_lane ^ m) & 31)); }
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m) { return dpc_emu::exchange(v, (dpc_emu::t_lane ^ m) & 31); }
 static inline float __shfl_down_sync(unsigned, float v, int d) {
   int s = dpc_emu::t_lane + d; if (s > 31) s = dpc_emu::t_lane;
   return u2f(dpc_emu::exchange(f2u(v), s));

@@ -68,6 +68,10 @@ CASES = {
     "edge_points": (dict(vox_size=16, pc_gauss_kernel_size=5), dict(B=2, N=12, sigma=0.8, scale=True, edge=True)),
     "extra_upstream": (dict(vox_size=16, pc_gauss_kernel_size=5), dict(B=2, N=300, sigma=0.8, scale=True, upstream_all=True)),
     "single_point": (dict(vox_size=16, pc_gauss_kernel_size=5), dict(B=1, N=1, sigma=0.8, scale=True)),
+    # 64^3 grid: exercises the shape-specialised FFMA2 kernels (K = 21 and K = 11, max projection,
+    # gradients arriving at voxels / tr_pc / drc_probs / proj_depth as well as at proj)
+    "v64_k11_max": (dict(vox_size=64, pc_gauss_kernel_size=11, ptn_max_projection=True), dict(B=1, N=400, sigma=1.0, scale=True)),
+    "v64_extra_upstream": (dict(vox_size=64, pc_gauss_kernel_size=21), dict(B=1, N=400, sigma=2.0, scale=True, upstream_all=True)),
 }
 
 
@@ -175,7 +179,8 @@ def run_case(ns, name):
 def main():
     ns = run_reference.load()
     total = 0
-    for name in CASES:
+    only = sys.argv[1:]
+    for name in (only or CASES):
         blob = run_case(ns, name)
         path = os.path.join(OUT, name + ".npz")
         total += os.path.getsize(path)
