@@ -16,7 +16,7 @@ class Product:
     pointcloud_project_fast = staticmethod(pcm.pointcloud_project_fast)
 
 
-SMALL = [n for n in cases.golden_names() if n not in ("v64_small", "cfg1_drc_k21_sigma3")]
+SMALL = [n for n in cases.golden_names() if n not in ("cfg1_drc_k21_sigma3",)]
 
 
 @pytest.mark.parametrize("name", SMALL)
