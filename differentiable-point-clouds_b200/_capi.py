@@ -43,6 +43,7 @@ _SIGNATURES = {
     "dpc_error_string": (ctypes.c_char_p, [c_i]),
     "dpc_last_cuda_error": (c_i, []),
     "dpc_is_cuda_build": (c_i, []),
+    "dpc_debug_set": (c_i, [c_i, c_i]),
     "dpc_splat_fwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i,
                             c_p, c_p, c_p, c_p, c_p, c_p]),
     "dpc_splat_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i, c_i,

@@ -16,6 +16,10 @@ static int dpc_check_launch() {
 #define DPC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_last_cuda_error = (int)e__; return DPC_ERR_CUDA; } } while (0)
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
+// Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
+static int g_tune[4] = {4, 4, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
+static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
+
 static bool shape_ok(int B, int Vz, int V) {
   return B >= 1 && B <= 65535 && V >= 1 && V <= DPC_MAX_V && Vz >= 1 && Vz <= DPC_MAX_V;
 }
@@ -23,6 +27,11 @@ static bool shape_ok(int B, int Vz, int V) {
 extern "C" {
 
 int dpc_abi_version(void) { return 1; }
+int dpc_debug_set(int key, int value) {
+  if (key < 0 || key >= 4) return DPC_ERR_ARG;
+  g_tune[key] = value;
+  return DPC_OK;
+}
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
 int dpc_is_cuda_build(void) {
 #ifdef DPC_EMU
@@ -59,8 +68,11 @@ int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float
   a.pose_kind = pose_kind; a.focal_const = focal_const; a.cam_dist = cam_dist;
   a.B = B; a.N = N; a.Vz = Vz; a.V = V;
   a.tr_pc = tr_pc; a.vox = vox; a.vox_rgb = vox_rgb; a.idx_out = idx_out; a.valid_out = valid_out;
-  dim3 grid((N + DPC_SPLAT_THREADS - 1) / DPC_SPLAT_THREADS, B);
-  DPC_LAUNCH(dpc_splat_fwd_kernel, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a);
+  const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
+  dim3 grid((N + tile - 1) / tile, B);
+  if (ppt == 4) { DPC_LAUNCH(dpc_splat_fwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  else if (ppt == 2) { DPC_LAUNCH(dpc_splat_fwd_kernel<2>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  else { DPC_LAUNCH(dpc_splat_fwd_kernel<1>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
   return dpc_check_launch();
 }
 
@@ -82,8 +94,11 @@ int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float
   a.B = B; a.N = N; a.Vz = Vz; a.V = V;
   a.d_vox = d_vox; a.d_vox_rgb = d_vox_rgb; a.d_tr_pc_in = d_tr_pc_in;
   a.d_pc = d_pc; a.d_pose = d_pose; a.d_trans = d_trans; a.d_focal = d_focal; a.d_rgb = d_rgb;
-  dim3 grid((N + DPC_SPLAT_THREADS - 1) / DPC_SPLAT_THREADS, B);
-  DPC_LAUNCH(dpc_splat_bwd_kernel, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a);
+  const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
+  dim3 grid((N + tile - 1) / tile, B);
+  if (ppt == 4) { DPC_LAUNCH(dpc_splat_bwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  else if (ppt == 2) { DPC_LAUNCH(dpc_splat_bwd_kernel<2>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  else { DPC_LAUNCH(dpc_splat_bwd_kernel<1>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
   return dpc_check_launch();
 }
 

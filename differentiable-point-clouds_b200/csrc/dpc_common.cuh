@@ -104,6 +104,14 @@ DPC_DEV void dpc_mbar_wait(uint64_t* bar, unsigned phase) {
 #endif
 }
 
+// Make this thread's generic-proxy writes to shared memory visible to the async proxy (TMA);
+// every writer calls it before the barrier that precedes a bulk store.
+DPC_DEV void dpc_fence_proxy_async() {
+#ifndef DPC_EMU
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
 // bulk async copy shared -> global (TMA store), bulk-group completion.
 DPC_DEV void dpc_bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes) {
 #ifndef DPC_EMU

@@ -10,6 +10,10 @@
 #include "dpc_math.cuh"
 
 #define DPC_SPLAT_THREADS 256
+#define DPC_SPLAT_MAX_PPT 4
+// Points per thread (PPT) is a template parameter: more points per thread = more independent
+// work per warp and fewer CTAs paying the tile-load latency; fewer = more warps per SM.
+// dpc_splat_ppt() picks the instantiation (tunable for experiments, see dpc_debug_set).
 
 struct DpcSplatArgs {
   const float* pc; const float* pose; const float* trans; const float* focal; const float* rgb;
@@ -18,145 +22,173 @@ struct DpcSplatArgs {
   float* tr_pc; float* vox; float* vox_rgb; int32_t* idx_out; uint8_t* valid_out;
 };
 
-// Stage `n` points (3n floats) of sample b starting at point p0 into smem.
-DPC_DEV void dpc_stage_points(float* tile, uint64_t* bar, const float* src, int n) {
+// Stage `n` points (3n floats) into smem: one TMA bulk copy when the 16-byte rules allow it
+// (issued by thread 0, completion on `bar`), else a cooperative copy.  Returns with the tile
+// visible to every thread.  While the copy is in flight thread 32 prepares the sample's camera.
+DPC_DEV void dpc_stage_points(float* tile, uint64_t* bar, const float* src, int n, DpcPose* pose_sm,
+                              const float* pose, int pose_kind, const float* trans, const float* focal,
+                              float focal_const, float cam_dist, int b) {
   const unsigned bytes = (unsigned)n * 12u;
   const bool bulk_ok = ((((uintptr_t)src) & 15u) == 0) && ((bytes & 15u) == 0);
+  if (bulk_ok && threadIdx.x == 0) dpc_mbar_init(bar, 1);
+  __syncthreads();
   if (bulk_ok) {
-    if (threadIdx.x == 0) {
-      dpc_mbar_init(bar, 1);
-    }
-    __syncthreads();
     if (threadIdx.x == 0) dpc_bulk_load(tile, src, bytes, bar);
-    dpc_mbar_wait(bar, 0);
   } else {
     for (int i = threadIdx.x; i < n * 3; i += blockDim.x) tile[i] = src[i];
   }
+  if (threadIdx.x == 32) dpc_pose_load(*pose_sm, pose, pose_kind, trans, focal, focal_const, cam_dist, b);
+  if (bulk_ok) dpc_mbar_wait(bar, 0);
   __syncthreads();
 }
 
+// Write `n` points (3n floats) from smem to global: TMA bulk store when aligned.
+DPC_DEV void dpc_unstage_points(float* dst, const float* tile, int n) {
+  const unsigned bytes = (unsigned)n * 12u;
+  const bool bulk_ok = ((((uintptr_t)dst) & 15u) == 0) && ((bytes & 15u) == 0);
+  if (bulk_ok) {
+    if (threadIdx.x == 0) dpc_bulk_store(dst, tile, bytes);
+  } else {
+    for (int i = threadIdx.x; i < n * 3; i += blockDim.x) dst[i] = tile[i];
+  }
+}
+
+template <int DPC_SPLAT_PPT>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(DPC_SPLAT_THREADS)
 #else
 static void
 #endif
 dpc_splat_fwd_kernel(DpcSplatArgs a) {
-  __shared__ __align__(128) float tile[DPC_SPLAT_THREADS * 3];
+  constexpr int DPC_SPLAT_TILE = DPC_SPLAT_THREADS * DPC_SPLAT_PPT;
+  __shared__ __align__(128) float tile[DPC_SPLAT_TILE * 3];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ DpcPose pose_sm;
   const int b = blockIdx.y;
-  const int p_first = blockIdx.x * DPC_SPLAT_THREADS;
-  const int n = min(DPC_SPLAT_THREADS, a.N - p_first);
+  const int p_first = blockIdx.x * DPC_SPLAT_TILE;
+  const int n = min(DPC_SPLAT_TILE, a.N - p_first);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-
-  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n);
-
-  DpcPose P;
-  dpc_pose_load(P, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
-
-  const bool live = tid < n;
-  float z = 0.f, y = 0.f, x = 0.f;
-  if (live) {
-    DpcCamPoint cam;
-    dpc_transform_point(P, tile[tid * 3 + 0], tile[tid * 3 + 1], tile[tid * 3 + 2], z, y, x, cam);
-  }
-  __syncthreads();  // everyone has read its point
-  if (a.tr_pc) {
-    if (live) { tile[tid * 3 + 0] = z; tile[tid * 3 + 1] = y; tile[tid * 3 + 2] = x; }
-    __syncthreads();
-    float* dst = a.tr_pc + ((size_t)b * a.N + p_first) * 3;
-    for (int i = tid; i < n * 3; i += DPC_SPLAT_THREADS) dst[i] = tile[i];
-  }
-
-  DpcCell c = dpc_cell(z, y, x, a.Vz, a.V);
-  c.valid = c.valid && live;
-  if (live) {
-    const size_t pi = (size_t)b * a.N + p_first + tid;
-    if (a.idx_out) { a.idx_out[pi * 3 + 0] = c.iz; a.idx_out[pi * 3 + 1] = c.iy; a.idx_out[pi * 3 + 2] = c.ix; }
-    if (a.valid_out) a.valid_out[pi] = c.valid ? 1 : 0;
-  }
-  if (!a.vox) return;
-
-  // corner weights, reference association: (rr[k].z * rr[j].y) * rr[i].x  (point_cloud.py:99)
-  const float wz[2] = {__fsub_rn(1.0f, c.rz), c.rz};
-  const float wy[2] = {__fsub_rn(1.0f, c.ry), c.ry};
-  const float wx[2] = {__fsub_rn(1.0f, c.rx), c.rx};
-  float w[8];
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) w[k * 4 + j * 2 + i] = c.valid ? __fmul_rn(__fmul_rn(wz[k], wy[j]), wx[i]) : 0.0f;
-
   const int V = a.V, Vz = a.Vz;
-  const int base = (c.iz * V + c.iy) * V + c.ix;
 
-  if (a.rgb) {
-    // 3-channel grid (point_cloud.py:111-118): plain per-lane reductions (non-default path).
-    if (c.valid) {
-      const float* col = a.rgb + ((size_t)b * a.N + p_first + tid) * 3;
+  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
+                   a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  const DpcPose P = pose_sm;
+
+  float z[DPC_SPLAT_PPT], y[DPC_SPLAT_PPT], x[DPC_SPLAT_PPT];
+#pragma unroll
+  for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
+    const int i = j * DPC_SPLAT_THREADS + tid;
+    z[j] = y[j] = x[j] = 0.0f;
+    if (i < n) {
+      DpcCamPoint cam;
+      dpc_transform_point(P, tile[i * 3 + 0], tile[i * 3 + 1], tile[i * 3 + 2], z[j], y[j], x[j], cam);
+    }
+  }
+  if (a.tr_pc) {
+    __syncthreads();  // everyone has read its points
+#pragma unroll
+    for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
+      const int i = j * DPC_SPLAT_THREADS + tid;
+      if (i < n) { tile[i * 3 + 0] = z[j]; tile[i * 3 + 1] = y[j]; tile[i * 3 + 2] = x[j]; }
+    }
+    dpc_fence_proxy_async();
+    __syncthreads();
+    dpc_unstage_points(a.tr_pc + ((size_t)b * a.N + p_first) * 3, tile, n);
+  }
+
+#pragma unroll
+  for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
+    const int i = j * DPC_SPLAT_THREADS + tid;
+    const bool live = i < n;
+    DpcCell c = dpc_cell(z[j], y[j], x[j], Vz, V);
+    c.valid = c.valid && live;
+    if (live) {
+      const size_t pi = (size_t)b * a.N + p_first + i;
+      if (a.idx_out) { a.idx_out[pi * 3 + 0] = c.iz; a.idx_out[pi * 3 + 1] = c.iy; a.idx_out[pi * 3 + 2] = c.ix; }
+      if (a.valid_out) a.valid_out[pi] = c.valid ? 1 : 0;
+    }
+    if (!a.vox) continue;   // uniform
+
+    // corner weights, reference association: (rr[k].z * rr[j].y) * rr[i].x  (point_cloud.py:99)
+    const float wz[2] = {__fsub_rn(1.0f, c.rz), c.rz};
+    const float wy[2] = {__fsub_rn(1.0f, c.ry), c.ry};
+    const float wx[2] = {__fsub_rn(1.0f, c.rx), c.rx};
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii)
+          w[k * 4 + jj * 2 + ii] = c.valid ? __fmul_rn(__fmul_rn(wz[k], wy[jj]), wx[ii]) : 0.0f;
+
+    const int base = (c.iz * V + c.iy) * V + c.ix;
+
+    if (a.rgb && c.valid) {
+      // 3-channel grid (point_cloud.py:111-118): plain per-lane reductions (non-default path).
+      const float* col = a.rgb + ((size_t)b * a.N + p_first + i) * 3;
       const float cr = col[0], cg = col[1], cb = col[2];
       float* g3 = a.vox_rgb + (size_t)b * Vz * V * V * 3;
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (c.iz + k < Vz && c.iy + j < V && c.ix + i < V) {
-              const float ww = w[k * 4 + j * 2 + i];
-              float* q = g3 + (size_t)(base + (k * V + j) * V + i) * 3;
+          for (int ii = 0; ii < 2; ++ii) {
+            if (c.iz + k < Vz && c.iy + jj < V && c.ix + ii < V) {
+              const float ww = w[k * 4 + jj * 2 + ii];
+              float* q = g3 + (size_t)(base + (k * V + jj) * V + ii) * 3;
               dpc_red_add(q + 0, __fmul_rn(ww, cr));
               dpc_red_add(q + 1, __fmul_rn(ww, cg));
               dpc_red_add(q + 2, __fmul_rn(ww, cb));
             }
           }
     }
-  }
 
-  // ---- warp aggregation: lanes whose points share a base voxel fold their 8 weights into the
-  // lowest lane of the group, so a clustered cloud (decoder init, stddev 0.025) issues one
-  // reduction per corner per group instead of 32 serialised same-address ones.
-  const int key = c.valid ? base : (-1 - lane);
-  const unsigned peers = __match_any_sync(DPC_FULL, key);
-  const int cnt = __popc(peers);
-  const int maxcnt = __reduce_max_sync(DPC_FULL, cnt);
-  if (maxcnt > 1) {
-    float s[8];
+    // ---- warp aggregation: lanes whose points share a base voxel fold their 8 weights into the
+    // lowest lane of the group, so a clustered cloud (decoder init, stddev 0.025) issues one
+    // reduction per corner per group instead of 32 serialised same-address ones.
+    const int key = c.valid ? base : (-1 - lane);
+    const unsigned peers = __match_any_sync(DPC_FULL, key);
+    const int cnt = __popc(peers);
+    const int maxcnt = __reduce_max_sync(DPC_FULL, cnt);
+    if (maxcnt > 1) {
+      float s[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s[q] = w[q];
-    unsigned rem = peers & ~(1u << lane);
-    for (int it = 1; it < maxcnt; ++it) {
-      const int src = rem ? (__ffs(rem) - 1) : lane;
-      rem &= rem - 1;
-      const bool take = it < cnt;
+      for (int q = 0; q < 8; ++q) s[q] = w[q];
+      unsigned rem = peers & ~(1u << lane);
+      for (int it = 1; it < maxcnt; ++it) {
+        const int src = rem ? (__ffs(rem) - 1) : lane;
+        rem &= rem - 1;
+        const bool take = it < cnt;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float v = __shfl_sync(DPC_FULL, w[q], src);
-        if (take) s[q] += v;
+        for (int q = 0; q < 8; ++q) {
+          const float v = __shfl_sync(DPC_FULL, w[q], src);
+          if (take) s[q] += v;
+        }
       }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w[q] = s[q];
     }
+    const bool leader = c.valid && (lane == (__ffs(peers) - 1));
+    if (leader) {
+      float* g = a.vox + (size_t)b * Vz * V * V + base;
+      const bool pair_ok = ((V & 1) == 0) && ((c.ix & 1) == 0) && ((((uintptr_t)a.vox) & 7u) == 0);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) w[q] = s[q];
-  }
-  const bool leader = c.valid && (lane == (__ffs(peers) - 1));
-  if (!leader) return;
-
-  float* g = a.vox + (size_t)b * Vz * V * V + base;
-  const bool pair_ok = ((V & 1) == 0) && ((c.ix & 1) == 0) && ((((uintptr_t)a.vox) & 7u) == 0);
+      for (int k = 0; k < 2; ++k) {
+        if (c.iz + k >= Vz) continue;  // only for a coordinate of exactly +0.5 (weight is 0): TF-GPU drops it
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    if (c.iz + k >= Vz) continue;  // only for a coordinate of exactly +0.5 (weight is 0): TF-GPU drops it
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (c.iy + j >= V) continue;
-      float* row = g + (k * V + j) * V;
-      if (pair_ok) {
-        dpc_red_add2(row, w[k * 4 + j * 2 + 0], w[k * 4 + j * 2 + 1]);
-      } else {
-        dpc_red_add(row, w[k * 4 + j * 2 + 0]);
-        if (c.ix + 1 < V) dpc_red_add(row + 1, w[k * 4 + j * 2 + 1]);
+        for (int jj = 0; jj < 2; ++jj) {
+          if (c.iy + jj >= V) continue;
+          float* row = g + (k * V + jj) * V;
+          if (pair_ok) {
+            dpc_red_add2(row, w[k * 4 + jj * 2 + 0], w[k * 4 + jj * 2 + 1]);
+          } else {
+            dpc_red_add(row, w[k * 4 + jj * 2 + 0]);
+            if (c.ix + 1 < V) dpc_red_add(row + 1, w[k * 4 + jj * 2 + 1]);
+          }
+        }
       }
     }
   }
@@ -171,95 +203,128 @@ struct DpcSplatBwdArgs {
   float* d_pc; float* d_pose; float* d_trans; float* d_focal; float* d_rgb;
 };
 
+template <int DPC_SPLAT_PPT>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(DPC_SPLAT_THREADS)
 #else
 static void
 #endif
 dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
-  __shared__ __align__(128) float tile[DPC_SPLAT_THREADS * 3];
+  constexpr int DPC_SPLAT_TILE = DPC_SPLAT_THREADS * DPC_SPLAT_PPT;
+  __shared__ __align__(128) float tile[DPC_SPLAT_TILE * 3];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ DpcPose pose_sm;
   __shared__ float red[DPC_SPLAT_THREADS / 32][12];
   const int b = blockIdx.y;
-  const int p_first = blockIdx.x * DPC_SPLAT_THREADS;
-  const int n = min(DPC_SPLAT_THREADS, a.N - p_first);
+  const int p_first = blockIdx.x * DPC_SPLAT_TILE;
+  const int n = min(DPC_SPLAT_TILE, a.N - p_first);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int V = a.V, Vz = a.Vz;
 
-  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n);
+  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
+                   a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  const DpcPose P = pose_sm;
 
-  DpcPose P;
-  dpc_pose_load(P, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
-
-  const bool live = tid < n;
   float acc[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
-  float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-  if (live) {
-    const float p0 = tile[tid * 3 + 0], p1 = tile[tid * 3 + 1], p2 = tile[tid * 3 + 2];
-    float z, y, x;
-    DpcCamPoint cam;
-    dpc_transform_point(P, p0, p1, p2, z, y, x, cam);  // same code as forward => same indices
-    const DpcCell c = dpc_cell(z, y, x, Vz, V);
+  for (int q = 0; q < 12; ++q) acc[q] = 0.0f;
+  float p0[DPC_SPLAT_PPT], p1[DPC_SPLAT_PPT], p2[DPC_SPLAT_PPT];
+  DpcCamPoint cam[DPC_SPLAT_PPT];
+  DpcCell cell[DPC_SPLAT_PPT];
+  float dw[DPC_SPLAT_PPT][8];
+  const float* dv = a.d_vox ? a.d_vox + (size_t)b * Vz * V * V : nullptr;
+
+  // pass 1: recompute the transform (same code as forward => same cell) and issue all corner
+  // gathers of all four points before anything consumes them
+#pragma unroll
+  for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
+    const int i = j * DPC_SPLAT_THREADS + tid;
+    p0[j] = p1[j] = p2[j] = 0.0f;
+    float z = 0.f, y = 0.f, x = 0.f;
+    cam[j].xs = cam[j].ys = 0.f; cam[j].zs = 1.f;
+    if (i < n) {
+      p0[j] = tile[i * 3 + 0]; p1[j] = tile[i * 3 + 1]; p2[j] = tile[i * 3 + 2];
+      dpc_transform_point(P, p0[j], p1[j], p2[j], z, y, x, cam[j]);
+    }
+    cell[j] = dpc_cell(z, y, x, Vz, V);
+    cell[j].valid = cell[j].valid && (i < n);
+    const int base = (cell[j].iz * V + cell[j].iy) * V + cell[j].ix;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          const bool inb = cell[j].valid && dv && (cell[j].iz + k < Vz) && (cell[j].iy + jj < V) && (cell[j].ix + ii < V);
+          dw[j][k * 4 + jj * 2 + ii] = inb ? __ldg(dv + base + (k * V + jj) * V + ii) : 0.0f;
+        }
+  }
+  __syncthreads();  // every thread has read its points: the tile can take the results
+
+  // pass 2: weights' derivative, chain rule through the camera
+#pragma unroll
+  for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
+    const int i = j * DPC_SPLAT_THREADS + tid;
+    const bool live = i < n;
+    const DpcCell c = cell[j];
+    const size_t pi = (size_t)b * a.N + p_first + i;
     float gz = 0.f, gy = 0.f, gx = 0.f;
-    const size_t pi = (size_t)b * a.N + p_first + tid;
     if (c.valid && (a.d_vox || a.d_vox_rgb)) {
       const float wz[2] = {1.0f - c.rz, c.rz}, wy[2] = {1.0f - c.ry, c.ry}, wx[2] = {1.0f - c.rx, c.rx};
       const int base = (c.iz * V + c.iy) * V + c.ix;
-      const float* dv = a.d_vox ? a.d_vox + (size_t)b * Vz * V * V : nullptr;
       const float* dv3 = a.d_vox_rgb ? a.d_vox_rgb + (size_t)b * Vz * V * V * 3 : nullptr;
       float cr = 0.f, cg = 0.f, cb = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
       if (dv3) { const float* col = a.rgb + pi * 3; cr = col[0]; cg = col[1]; cb = col[2]; }
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (c.iz + k < Vz && c.iy + j < V && c.ix + i < V) {
-              const int off = base + (k * V + j) * V + i;
-              float dw = dv ? __ldg(dv + off) : 0.0f;  // dL/dw of this corner
+          for (int ii = 0; ii < 2; ++ii) {
+            if (c.iz + k < Vz && c.iy + jj < V && c.ix + ii < V) {
+              float dwc = dw[j][k * 4 + jj * 2 + ii];  // dL/dw of this corner
               if (dv3) {
-                const float e0 = __ldg(dv3 + (size_t)off * 3 + 0), e1 = __ldg(dv3 + (size_t)off * 3 + 1),
-                            e2 = __ldg(dv3 + (size_t)off * 3 + 2);
-                const float ww = (wz[k] * wy[j]) * wx[i];
+                const size_t off = (size_t)(base + (k * V + jj) * V + ii) * 3;
+                const float e0 = __ldg(dv3 + off + 0), e1 = __ldg(dv3 + off + 1), e2 = __ldg(dv3 + off + 2);
+                const float ww = (wz[k] * wy[jj]) * wx[ii];
                 dr += ww * e0; dg += ww * e1; db += ww * e2;
-                if (!a.rgb_stop_grad) dw += e0 * cr + e1 * cg + e2 * cb;
+                if (!a.rgb_stop_grad) dwc += e0 * cr + e1 * cg + e2 * cb;
               }
-              gz += (k ? dw : -dw) * (wy[j] * wx[i]);
-              gy += (j ? dw : -dw) * (wz[k] * wx[i]);
-              gx += (i ? dw : -dw) * (wz[k] * wy[j]);
+              gz += (k ? dwc : -dwc) * (wy[jj] * wx[ii]);
+              gy += (jj ? dwc : -dwc) * (wz[k] * wx[ii]);
+              gx += (ii ? dwc : -dwc) * (wz[k] * wy[jj]);
             }
           }
       gz *= (float)(Vz - 1); gy *= (float)(V - 1); gx *= (float)(V - 1);  // d grid / d coordinate
       if (a.d_rgb) { a.d_rgb[pi * 3 + 0] = dr; a.d_rgb[pi * 3 + 1] = dg; a.d_rgb[pi * 3 + 2] = db; }
-    } else if (a.d_rgb) {
+    } else if (a.d_rgb && live) {
       a.d_rgb[pi * 3 + 0] = 0.f; a.d_rgb[pi * 3 + 1] = 0.f; a.d_rgb[pi * 3 + 2] = 0.f;
     }
-    if (a.d_tr_pc_in) {
-      gz += a.d_tr_pc_in[pi * 3 + 0]; gy += a.d_tr_pc_in[pi * 3 + 1]; gx += a.d_tr_pc_in[pi * 3 + 2];
+    if (live) {
+      if (a.d_tr_pc_in) {
+        gz += a.d_tr_pc_in[pi * 3 + 0]; gy += a.d_tr_pc_in[pi * 3 + 1]; gx += a.d_tr_pc_in[pi * 3 + 2];
+      }
+      // chain rule applied unconditionally: an invalid but finite point gets exact zeros, a NaN
+      // point propagates NaN into the pose gradient exactly as TF's autodiff does (0 * NaN).
+      float d0, d1, d2;
+      dpc_transform_point_bwd(P, p0[j], p1[j], p2[j], cam[j], gz, gy, gx, d0, d1, d2, acc);
+      if (a.d_pc) { tile[i * 3 + 0] = d0; tile[i * 3 + 1] = d1; tile[i * 3 + 2] = d2; }
     }
-    // chain rule applied unconditionally: an invalid but finite point gets exact zeros, a NaN
-    // point propagates NaN into the pose gradient exactly as TF's autodiff does (0 * NaN).
-    dpc_transform_point_bwd(P, p0, p1, p2, cam, gz, gy, gx, d0, d1, d2, acc);
   }
-  __syncthreads();
   if (a.d_pc) {
-    if (live) { tile[tid * 3 + 0] = d0; tile[tid * 3 + 1] = d1; tile[tid * 3 + 2] = d2; }
+    dpc_fence_proxy_async();
     __syncthreads();
-    float* dst = a.d_pc + ((size_t)b * a.N + p_first) * 3;
-    for (int i = tid; i < n * 3; i += DPC_SPLAT_THREADS) dst[i] = tile[i];
+    dpc_unstage_points(a.d_pc + ((size_t)b * a.N + p_first) * 3, tile, n);
   }
   if (a.pose_kind == DPC_POSE_NONE) return;
   const bool want_pose = a.d_pose != nullptr, want_t = a.d_trans != nullptr, want_f = a.d_focal != nullptr;
   if (!(want_pose || want_t || want_f)) return;
   // block reduction of the per-sample pose gradients: warp shuffles, then one atomic per CTA
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    const float v = dpc_warp_sum(acc[i]);
-    if (lane == 0) red[warp][i] = v;
+  for (int q = 0; q < 12; ++q) {
+    const float v = dpc_warp_sum(acc[q]);
+    if (lane == 0) red[warp][q] = v;
   }
   __syncthreads();
   if (tid < 12) {
@@ -273,9 +338,9 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
       if (want_pose) {
         float dq[4];
         dpc_quat_norm_bwd(P, red[0], dq);
-        for (int i = 0; i < 4; ++i) atomicAdd(a.d_pose + b * 4 + i, dq[i]);
+        for (int q = 0; q < 4; ++q) atomicAdd(a.d_pose + b * 4 + q, dq[q]);
       }
-      if (want_t) for (int i = 0; i < 3; ++i) atomicAdd(a.d_trans + b * 3 + i, red[0][4 + i]);
+      if (want_t) for (int q = 0; q < 3; ++q) atomicAdd(a.d_trans + b * 3 + q, red[0][4 + q]);
       if (want_f) atomicAdd(a.d_focal + b, red[0][7]);
     } else if (want_pose) {
       // dL/dE = K^T dL/dM: rows 1,2 scaled by f; row 3 of the extrinsic does not reach the output

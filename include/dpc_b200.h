@@ -52,6 +52,9 @@ extern "C" {
 int dpc_abi_version(void);
 const char* dpc_error_string(int code);
 int dpc_last_cuda_error(void);
+/* Experiment knob for benchmark sweeps (key 0/1: points per thread of the splat forward/backward
+ * kernels, 1|2|4).  Process-wide, not thread-safe, not needed in normal use. */
+int dpc_debug_set(int key, int value);
 /* compiled for sm_100a?  1 = real CUDA build, 0 = the CPU emulation build used by tests/emu */
 int dpc_is_cuda_build(void);
 
