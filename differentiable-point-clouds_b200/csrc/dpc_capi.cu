@@ -142,7 +142,7 @@ int dpc_conv_z_fwd(const float* in, const float* taps_z, int Kz, int pad_lo_z,
   if ((drc_probs || proj_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
   if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo_z < 0 || pad_lo_z >= Kz) return DPC_ERR_ARG;
-  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z)) {
+  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z, drc_probs != nullptr || proj_depth != nullptr)) {
     DPC_TRY(dpc_conv_z_fwd_fast_launch(in, taps_z, Kz, scale, mode, clip_eps, cam_dist, max_depth, flip_y, B, Vz, V,
                                        vox_out, mask2_out, proj, drc_probs, proj_depth, stream));
     return dpc_check_launch();
@@ -171,7 +171,7 @@ int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
   if ((g_probs || g_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
   if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo_z_rev < 0 || pad_lo_z_rev >= Kz) return DPC_ERR_ARG;
-  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z_rev)) {
+  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z_rev, g_probs != nullptr || g_depth != nullptr)) {
     DPC_TRY(dpc_conv_z_bwd_fast_launch(vox, mask2, scale, taps_z_rev, Kz, mode, clip_eps, cam_dist, max_depth, flip_y,
                                        B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, stream));
     return dpc_check_launch();

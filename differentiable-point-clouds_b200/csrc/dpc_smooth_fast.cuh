@@ -145,11 +145,19 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
 }
 
 // ------------------------------------------------------------------------------ conv_z, V = Vz = 64
-#define DPC_ZF_TY 4           // image rows per CTA: tile = 64 z x 4 rows x 64 x fp32 = 64 KiB, 128 threads
+// CTA = 4 image rows x all 64 depth levels (64 KiB tile, TMA bulk loads), 256 threads = 8 warps.
+// Warp w works on image row w>>1 and on depth half w&1 (levels 32h .. 32h+31): the correlation has
+// no carry along depth, and the ray scan is affine in its carry (p_i = u_i T_i with T a running
+// product), so each half scans from T = 1 and the two halves are combined through smem:
+//   proj = S_lo + T_lo * S_hi,   max = max(max_lo, max_hi).
+// That doubles the resident warps per tile (24 per SM) against one warp per row.
+// Not handled here (the generic kernel takes over): drc_probs / proj_depth outputs or gradients.
+#define DPC_ZF_TY 4
+#define DPC_ZF_THREADS 256
 
 template <int K>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(32 * DPC_ZF_TY)
+__global__ void __launch_bounds__(DPC_ZF_THREADS)
 #else
 static void
 #endif
@@ -158,6 +166,7 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
   DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]
   __shared__ __align__(8) uint64_t bar;
   __shared__ float tz[K];
+  __shared__ __align__(8) float comb[TY][V][2];   // (T, S) or (max, -) of the low depth half per ray
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
   if (tid < K) tz[tid] = a.taps[tid];
@@ -182,79 +191,73 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
   dpc_mbar_wait(&bar, 0);
   __syncthreads();
 
-  const int ty = tid >> 5, xp = tid & 31, y = y0 + ty;
+  const int w = tid >> 5, xp = tid & 31;
+  const int ty = w >> 1, h = w & 1, y = y0 + ty;
   float2 tt[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) tt[j] = dpc_f2(tz[j], tz[j]);
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
-  const int yo = a.flip_y ? (V - 1 - y) : y;
-  const size_t ray = ((size_t)b * V + yo) * V + 2 * xp;
-  const size_t plane = (size_t)a.B * V * V;
-  float2 T = dpc_f2(1.f, 1.f), proj = dpc_f2(0.f, 0.f), dep = dpc_f2(0.f, 0.f), mx = dpc_f2(-INFINITY, -INFINITY);
-  uint32_t m0 = 0u, m1 = 0u, m0lo = 0u, m1lo = 0u;   // clip-pass bits of the two rays (current word / low word)
+  float2 T = dpc_f2(1.f, 1.f), S = dpc_f2(0.f, 0.f), mx = dpc_f2(-INFINITY, -INFINITY);
+  uint32_t m0 = 0u, m1 = 0u;   // clip-pass bits of the two rays for this depth half
   float* vout = a.vox_out + ((size_t)b * Vz * V + y) * V + 2 * xp;
   const float* col = tile + ty * V + 2 * xp;
 #pragma unroll 1
-  for (int c = 0; c < Vz / 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
+    const int zc = (4 * h + c) * 8;
     float2 acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-    dpc_col_conv_pairs<K, 8>(col, RW, c * 8, Vz, tt, acc);
+    dpc_col_conv_pairs<K, 8>(col, RW, zc, Vz, tt, acc);
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
-      const int z = c * 8 + o;
       float2 v = acc[o];
       if (has_s) {
         const float t0 = __fmul_rn(v.x, s), t1 = __fmul_rn(v.y, s);
-        if (t0 >= 0.0f && t0 <= 1.0f) m0 |= 1u << (z & 31);
-        if (t1 >= 0.0f && t1 <= 1.0f) m1 |= 1u << (z & 31);
         v = dpc_f2(dpc_clip01(t0), dpc_clip01(t1));
+        // the clip passes the gradient iff 0 <= t <= 1, i.e. iff it left t unchanged
+        if (v.x == t0) m0 |= 1u << (c * 8 + o);
+        if (v.y == t1) m1 |= 1u << (c * 8 + o);
       }
-      *reinterpret_cast<float2*>(vout + (size_t)z * V * V) = v;
+      *reinterpret_cast<float2*>(vout + (size_t)(zc + o) * V * V) = v;
       if (a.mode == DPC_PROJ_MAX) {
         mx = dpc_f2(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y));
       } else if (a.mode != DPC_PROJ_NONE) {
         const float u0 = D.clampu ? fminf(fmaxf(v.x, D.lo), D.hi) : v.x;
         const float u1 = D.clampu ? fminf(fmaxf(v.y, D.lo), D.hi) : v.y;
-        const float c0 = (z == 0) ? D.c0 : 1.0f;
-        const float2 p = dpc_f2(c0 * u0 * T.x, c0 * u1 * T.y);
-        T = dpc_f2(T.x * (1.0f - u0), T.y * (1.0f - u1));
-        proj = dpc_f2(proj.x + p.x, proj.y + p.y);
-        if (a.probs) *reinterpret_cast<float2*>(a.probs + (size_t)z * plane + ray) = p;
-        if (a.depth) { const float ps = dpc_psi(z, Vz, a.cam_dist); dep = dpc_f2(fmaf(p.x, ps, dep.x), fmaf(p.y, ps, dep.y)); }
+        float p0 = u0 * T.x, p1 = u1 * T.y;           // p_i = u_i T_i (local T)
+        T = dpc_f2(T.x - p0, T.y - p1);                // T_{i+1} = T_i (1 - u_i)
+        if (o == 0 && zc == 0) { p0 *= D.c0; p1 *= D.c0; }   // the reference's e^eps on the first event
+        S = dpc_f2(S.x + p0, S.y + p1);
       }
     }
-    if (c == 3) { m0lo = m0; m1lo = m1; m0 = 0u; m1 = 0u; }   // depth levels 0..31 done
   }
-  if (a.mask2_out) {
-    uint4 mw; mw.x = m0lo; mw.y = m0; mw.z = m1lo; mw.w = m1;
-    *reinterpret_cast<uint4*>(a.mask2_out + (((size_t)b * V + y) * V + 2 * xp) * 2) = mw;
+  if (a.mask2_out && has_s) {
+    uint32_t* mp = a.mask2_out + (((size_t)b * V + y) * V + 2 * xp) * 2 + h;
+    mp[0] = m0; mp[2] = m1;
   }
-  if (a.mode == DPC_PROJ_MAX) {
-    *reinterpret_cast<float2*>(a.proj + ray) = mx;
-  } else if (a.mode != DPC_PROJ_NONE) {
-    const float2 pZ = dpc_f2(D.cZ * T.x, D.cZ * T.y);
-    *reinterpret_cast<float2*>(a.proj + ray) = proj;
-    if (a.probs) *reinterpret_cast<float2*>(a.probs + (size_t)Vz * plane + ray) = pZ;
-    if (a.depth) *reinterpret_cast<float2*>(a.depth + ray) = dpc_f2(fmaf(pZ.x, a.max_depth, dep.x), fmaf(pZ.y, a.max_depth, dep.y));
+  if (a.mode == DPC_PROJ_NONE) return;
+  // combine the two depth halves
+  if (h == 0) {
+    *reinterpret_cast<float2*>(&comb[ty][2 * xp][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.x, 0.f) : dpc_f2(T.x, S.x);
+    *reinterpret_cast<float2*>(&comb[ty][2 * xp + 1][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.y, 0.f) : dpc_f2(T.y, S.y);
   }
-}
-
-// one ray of the backward: reverse-sweep step (see dpc_conv_z_bwd_kernel for the derivation)
-DPC_DEV float dpc_drc_bwd_step(const DpcDrc& D, float v, float Tk, float G, int z, float& Q) {
-  const float u = D.clampu ? fminf(fmaxf(v, D.lo), D.hi) : v;
-  const float Gc = G * (z == 0 ? D.c0 : 1.0f);
-  float du = Tk * (Gc - Q);
-  Q = fmaf(1.0f - u, Q, Gc * u);
-  if (D.clampu && !(v >= D.lo && v <= D.hi)) du = 0.0f;
-  return du;
+  __syncthreads();
+  if (h == 1) {
+    const float2 c0v = *reinterpret_cast<const float2*>(&comb[ty][2 * xp][0]);
+    const float2 c1v = *reinterpret_cast<const float2*>(&comb[ty][2 * xp + 1][0]);
+    float2 out;
+    if (a.mode == DPC_PROJ_MAX) out = dpc_f2(fmaxf(c0v.x, mx.x), fmaxf(c1v.x, mx.y));
+    else out = dpc_f2(fmaf(c0v.x, S.x, c0v.y), fmaf(c1v.x, S.y, c1v.y));
+    const int yo = a.flip_y ? (V - 1 - y) : y;
+    *reinterpret_cast<float2*>(a.proj + ((size_t)b * V + yo) * V + 2 * xp) = out;
+  }
 }
 
 template <int K>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(32 * DPC_ZF_TY)
+__global__ void __launch_bounds__(DPC_ZF_THREADS)
 #else
 static void
 #endif
@@ -262,108 +265,92 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
   constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZF_TY, RW = TY * V;
   DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]: T_k, then dL/d(smoothed)
   __shared__ float tz[K];
-  __shared__ float red[DPC_ZF_TY];
+  __shared__ float red[DPC_ZF_THREADS / 32];
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
   if (tid < K) tz[tid] = a.taps[tid];
-  __syncthreads();
-  const int ty = tid >> 5, xp = tid & 31, y = y0 + ty;
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const float inv_s = (s != 0.0f) ? 1.0f / s : 0.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
-  const int yo = a.flip_y ? (V - 1 - y) : y;
-  const size_t ray = ((size_t)b * V + yo) * V + 2 * xp;
-  const size_t plane = (size_t)a.B * V * V;
-  const float* vin = a.vox + ((size_t)b * Vz * V + y) * V + 2 * xp;
-  const float* gv = a.g_vox ? a.g_vox + ((size_t)b * Vz * V + y) * V + 2 * xp : nullptr;
-  float* col = tile + ty * V + 2 * xp;
-  const float2 gp = a.g_proj ? *reinterpret_cast<const float2*>(a.g_proj + ray) : dpc_f2(0.f, 0.f);
-  const float2 gd = a.g_depth ? *reinterpret_cast<const float2*>(a.g_depth + ray) : dpc_f2(0.f, 0.f);
-
-  if (a.mode == DPC_PROJ_MAX) {
-    float2 mx = dpc_f2(-INFINITY, -INFINITY);
-    for (int z = 0; z < Vz; ++z) {
-      const float2 v = *reinterpret_cast<const float2*>(vin + (size_t)z * V * V);
-      mx = dpc_f2(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y));
+  float ds = 0.0f;
+  // ---- phase 1: one thread per ray.  dL/dvoxel from the projection, then back through
+  // clip(. * scale); result (dL/d smoothed) left in the tile.
+  {
+    const int ty = tid >> 6, x = tid & 63, y = y0 + ty;
+    const int yo = a.flip_y ? (V - 1 - y) : y;
+    const float* vin = a.vox + ((size_t)b * Vz * V + y) * V + x;
+    const float* gv = a.g_vox ? a.g_vox + ((size_t)b * Vz * V + y) * V + x : nullptr;
+    float* col = tile + ty * V + x;
+    const float gp = a.g_proj ? a.g_proj[((size_t)b * V + yo) * V + x] : 0.0f;
+    uint32_t mlo = 0xffffffffu, mhi = 0xffffffffu;
+    if (a.mask2 && has_s) {
+      const uint2 mw = *reinterpret_cast<const uint2*>(a.mask2 + (((size_t)b * V + y) * V + x) * 2);
+      mlo = mw.x; mhi = mw.y;
     }
-    int c0 = 0, c1 = 0;
-    for (int z = 0; z < Vz; ++z) {
-      const float2 v = *reinterpret_cast<const float2*>(vin + (size_t)z * V * V);
-      c0 += (v.x == mx.x); c1 += (v.y == mx.y);
-    }
-    const float s0 = gp.x / (float)c0, s1 = gp.y / (float)c1;
-    for (int z = 0; z < Vz; ++z) {
-      const float2 v = *reinterpret_cast<const float2*>(vin + (size_t)z * V * V);
-      *reinterpret_cast<float2*>(col + z * RW) = dpc_f2(v.x == mx.x ? s0 : 0.0f, v.y == mx.y ? s1 : 0.0f);
-    }
-  } else if (a.mode == DPC_PROJ_NONE) {
-    for (int z = 0; z < Vz; ++z) *reinterpret_cast<float2*>(col + z * RW) = dpc_f2(0.f, 0.f);
-  } else {
-    float2 T = dpc_f2(1.f, 1.f);
+    float share = 0.0f, mx = -INFINITY;
+    if (a.mode == DPC_PROJ_MAX) {
+      for (int z = 0; z < Vz; ++z) mx = fmaxf(mx, vin[(size_t)z * V * V]);
+      int cnt = 0;
+      for (int z = 0; z < Vz; ++z) cnt += (vin[(size_t)z * V * V] == mx) ? 1 : 0;
+      share = gp / (float)cnt;     // TF _MaxGrad: ties share the gradient equally
+    } else if (a.mode != DPC_PROJ_NONE) {
+      // prefix products T_k = prod_{j<k} (1-u_j) into the tile
+      float T = 1.0f;
 #pragma unroll 8
-    for (int z = 0; z < Vz; ++z) {
-      const float2 v = *reinterpret_cast<const float2*>(vin + (size_t)z * V * V);
-      const float u0 = D.clampu ? fminf(fmaxf(v.x, D.lo), D.hi) : v.x;
-      const float u1 = D.clampu ? fminf(fmaxf(v.y, D.lo), D.hi) : v.y;
-      *reinterpret_cast<float2*>(col + z * RW) = T;
-      T = dpc_f2(T.x * (1.0f - u0), T.y * (1.0f - u1));
+      for (int z = 0; z < Vz; ++z) {
+        const float v = vin[(size_t)z * V * V];
+        const float u = D.clampu ? fminf(fmaxf(v, D.lo), D.hi) : v;
+        col[z * RW] = T;
+        T = T - u * T;
+      }
     }
-    float2 gZ = dpc_f2(gd.x * a.max_depth, gd.y * a.max_depth);
-    if (a.g_probs) {
-      const float2 t = *reinterpret_cast<const float2*>(a.g_probs + (size_t)Vz * plane + ray);
-      gZ = dpc_f2(gZ.x + t.x, gZ.y + t.y);
-    }
-    float Q0 = gZ.x * D.cZ, Q1 = gZ.y * D.cZ;
+    // reverse sweep.  With only the silhouette gradient g:  dL/du_k = g T_k (c_k - 1 + R_k),
+    // R_k = prod_{j>k} (1-u_j)  (for k > 0 that is g * prod_{j != k} (1-u_j)).
+    float R = 1.0f;
 #pragma unroll 8
     for (int z = Vz - 1; z >= 0; --z) {
-      const float2 v = *reinterpret_cast<const float2*>(vin + (size_t)z * V * V);   // second read: L1/L2 hit
-      const float2 Tk = *reinterpret_cast<const float2*>(col + z * RW);
-      float G0 = gp.x, G1 = gp.y;
-      if (a.g_depth) { const float ps = dpc_psi(z, Vz, a.cam_dist); G0 = fmaf(gd.x, ps, G0); G1 = fmaf(gd.y, ps, G1); }
-      if (a.g_probs) {
-        const float2 t = *reinterpret_cast<const float2*>(a.g_probs + (size_t)z * plane + ray);
-        G0 += t.x; G1 += t.y;
+      const float v = vin[(size_t)z * V * V];      // second read of the column: L1/L2 hit
+      float dv = 0.0f;
+      if (a.mode == DPC_PROJ_MAX) {
+        dv = (v == mx) ? share : 0.0f;
+      } else if (a.mode != DPC_PROJ_NONE) {
+        const float u = D.clampu ? fminf(fmaxf(v, D.lo), D.hi) : v;
+        const float ck = (z == 0) ? (D.c0 - 1.0f) : 0.0f;
+        dv = gp * col[z * RW] * (ck + R);
+        R = R - u * R;
+        if (D.clampu && !(v >= D.lo && v <= D.hi)) dv = 0.0f;   // clip_by_value passes lo <= v <= hi
       }
-      const float d0 = dpc_drc_bwd_step(D, v.x, Tk.x, G0, z, Q0);
-      const float d1 = dpc_drc_bwd_step(D, v.y, Tk.y, G1, z, Q1);
-      *reinterpret_cast<float2*>(col + z * RW) = dpc_f2(d0, d1);
-    }
-  }
-  // + direct gradient on voxels, back through clip(. * scale)
-  float ds = 0.0f;
-  if (gv || has_s) {
-    uint4 mw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    if (a.mask2 && has_s) mw = *reinterpret_cast<const uint4*>(a.mask2 + (((size_t)b * V + y) * V + 2 * xp) * 2);
-#pragma unroll 8
-    for (int z = 0; z < Vz; ++z) {
-      float2 dv = *reinterpret_cast<const float2*>(col + z * RW);
-      if (gv) { const float2 t = *reinterpret_cast<const float2*>(gv + (size_t)z * V * V); dv = dpc_f2(dv.x + t.x, dv.y + t.y); }
+      if (gv) dv += gv[(size_t)z * V * V];
       if (has_s) {
-        const uint32_t w0 = (z < 32) ? mw.x : mw.y, w1 = (z < 32) ? mw.z : mw.w;
-        if (!((w0 >> (z & 31)) & 1u)) dv.x = 0.0f;
-        if (!((w1 >> (z & 31)) & 1u)) dv.y = 0.0f;
-        const float2 v = *reinterpret_cast<const float2*>(vin + (size_t)z * V * V);
-        ds = fmaf(dv.x, v.x * inv_s, ds);
-        ds = fmaf(dv.y, v.y * inv_s, ds);
-        dv = dpc_f2(dv.x * s, dv.y * s);
+        const uint32_t wbits = (z < 32) ? mlo : mhi;
+        if (!((wbits >> (z & 31)) & 1u)) dv = 0.0f;
+        ds = fmaf(dv, v * inv_s, ds);      // smoothed value = voxels / scale where the clip passed
+        dv *= s;
       }
-      *reinterpret_cast<float2*>(col + z * RW) = dv;
+      col[z * RW] = dv;
     }
   }
-  // transposed depth correlation (reversed taps) straight to global
-  float2 tt[K];
+  __syncthreads();
+  // ---- phase 2: transposed depth correlation (reversed taps), warp = (row, depth half)
+  {
+    const int w = tid >> 5, xp = tid & 31;
+    const int ty = w >> 1, h = w & 1, y = y0 + ty;
+    float2 tt[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) tt[j] = dpc_f2(tz[j], tz[j]);
-  float* dout = a.d_in + ((size_t)b * Vz * V + y) * V + 2 * xp;
+    for (int j = 0; j < K; ++j) tt[j] = dpc_f2(tz[j], tz[j]);
+    const float* col = tile + ty * V + 2 * xp;
+    float* dout = a.d_in + ((size_t)b * Vz * V + y) * V + 2 * xp;
 #pragma unroll 1
-  for (int c = 0; c < Vz / 8; ++c) {
-    float2 acc[8];
+    for (int c = 0; c < 4; ++c) {
+      const int zc = (4 * h + c) * 8;
+      float2 acc[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-    dpc_col_conv_pairs<K, 8>(col, RW, c * 8, Vz, tt, acc);
+      for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+      dpc_col_conv_pairs<K, 8>(col, RW, zc, Vz, tt, acc);
 #pragma unroll
-    for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(dout + (size_t)(c * 8 + o) * V * V) = acc[o];
+      for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(dout + (size_t)(zc + o) * V * V) = acc[o];
+    }
   }
   if (a.d_scale) {
     const float v = dpc_warp_sum(ds);
@@ -371,7 +358,7 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
     __syncthreads();
     if (tid == 0) {
       float t = 0.0f;
-      for (int i = 0; i < TY; ++i) t += red[i];
+      for (int i = 0; i < DPC_ZF_THREADS / 32; ++i) t += red[i];
       atomicAdd(a.d_scale + b, t);
     }
   }
@@ -396,8 +383,9 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   return DPC_OK;
 }
 
-static inline bool dpc_conv_z_fast_supported(int V, int Vz, int Kz, int plz) {
-  return V == 64 && Vz == 64 && dpc_fast_k(Kz) && plz == (Kz - 1) / 2;
+// `extras`: drc_probs / proj_depth outputs (forward) or their gradients (backward) requested
+static inline bool dpc_conv_z_fast_supported(int V, int Vz, int Kz, int plz, bool extras) {
+  return V == 64 && Vz == 64 && dpc_fast_k(Kz) && plz == (Kz - 1) / 2 && !extras;
 }
 
 static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_z, int Kz, const float* scale, int mode,
@@ -409,7 +397,7 @@ static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_
   a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = probs; a.depth = depth;
   const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
-  dim3 grid(V / DPC_ZF_TY, B), block(32 * DPC_ZF_TY);
+  dim3 grid(V / DPC_ZF_TY, B), block(DPC_ZF_THREADS);
 #ifndef DPC_EMU
   cudaError_t e = (Kz == 21)
       ? cudaFuncSetAttribute(dpc_conv_z64_fwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -432,7 +420,7 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
   a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;
   a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;
   const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
-  dim3 grid(V / DPC_ZF_TY, B), block(32 * DPC_ZF_TY);
+  dim3 grid(V / DPC_ZF_TY, B), block(DPC_ZF_THREADS);
 #ifndef DPC_EMU
   cudaError_t e = (Kz == 21)
       ? cudaFuncSetAttribute(dpc_conv_z64_bwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)

@@ -16,6 +16,9 @@ timeout 600 python bench.py --steps 50 --warmup 5 > $O/bench.json 2> $O/bench.er
 cat $O/bench.json
 timeout 300 python bench.py --steps 50 --warmup 5 --no-l2-flush --no-cpu-baseline > $O/bench_noflush.json 2>> $O/bench.err; echo "bench-noflush rc=$?" | tee -a $O/status.txt
 cat $O/bench_noflush.json
+echo "== tune" | tee -a $O/status.txt
+timeout 300 python scripts/tune.py > $O/tune.log 2>&1; echo "tune rc=$?" | tee -a $O/status.txt
+cat $O/tune.log | tail -8
 if [ "$1" != "quick" ]; then
 echo "== ncu launch list" | tee -a $O/status.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Experiment sweep on the GPU box: per-stage device times for each tuning-knob setting."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    pipe = bench.Pipeline(dev, 0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {}
+    for clustered in (False, True):
+        if clustered:
+            pc = bench.make_inputs(bench.B, 0, clustered=True)[0]
+            pipe.pc.copy_(pc.to(dev))
+        for ppt in (4, 2, 1):
+            pipe.L.dpc_debug_set(0, ppt)
+            pipe.L.dpc_debug_set(1, ppt)
+            for _ in range(3):
+                pipe.step()
+            st = pipe.stage_times(20, flush)
+            key = "%s_ppt%d" % ("clustered" if clustered else "spread", ppt)
+            out[key] = {k: round(v * 1000, 2) for k, v in st.items()}
+            print(key, out[key], flush=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
