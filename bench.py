@@ -181,9 +181,12 @@ class Pipeline:
         self.p = _capi.ProjectParams(B=B, N=N, Vz=V, V=V, pose_kind=_capi.POSE_QUAT, mode=_capi.PROJ_DRC, K=K, Kz=K,
                                      focal_const=float(self.cfg.focal_length), cam_dist=float(self.cfg.camera_distance),
                                      clip_eps=float(self.cfg.drc_logsum_clip_val), max_depth=float(self.cfg.max_depth))
-        self.ws_bytes = self.L.dpc_project_fast_workspace_bytes(ctypes.byref(self.p))
+        self.p.flags = _capi.FLAG_SCRATCH_RAW_ZERO      # scratch is zeroed once, the kernels keep it clean
+        self.scratch_bytes = self.L.dpc_project_fast_scratch_bytes(ctypes.byref(self.p))
+        self.saved_bytes = self.L.dpc_project_fast_saved_bytes(ctypes.byref(self.p))
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
-        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.scratch = torch.zeros(self.scratch_bytes, dtype=torch.uint8, device=dev)
+        self.saved = torch.empty(self.saved_bytes, dtype=torch.uint8, device=dev)
         self.tr_pc, self.vox, self.proj, self.g_proj = f(B, N, 3), f(B, V, V, V), f(B, V, V), f(B, V, V)
         self.d_pc, self.d_q, self.d_sc = f(B, N, 3), f(B, 4), f(B)
         self.stream = torch.cuda.current_stream(dev).cuda_stream
@@ -192,78 +195,40 @@ class Pipeline:
         L, p, c = self.L, self.p, self.capi.check
         c(L.dpc_project_fast_fwd(ctypes.byref(p), self.pc.data_ptr(), self.q.data_ptr(), None, None, self.sc1.data_ptr(),
                                  self.taps.data_ptr(), self.taps.data_ptr(), self.tr_pc.data_ptr(), self.vox.data_ptr(),
-                                 self.proj.data_ptr(), None, None, self.ws.data_ptr(), self.ws_bytes, self.stream))
+                                 self.proj.data_ptr(), None, None, self.scratch.data_ptr(), self.scratch_bytes,
+                                 self.saved.data_ptr(), self.saved_bytes, self.stream))
         # dL/dproj of sum((gt-proj)^2)/2/B  (model_pc.py:414-415) -- loss side, plain torch
         torch.sub(self.proj, self.gt3, out=self.g_proj)
         self.g_proj.mul_(1.0 / B)
         c(L.dpc_project_fast_bwd(ctypes.byref(p), self.pc.data_ptr(), self.q.data_ptr(), None, None, self.sc1.data_ptr(),
                                  self.taps.data_ptr(), self.taps.data_ptr(), self.vox.data_ptr(), self.g_proj.data_ptr(),
                                  None, None, None, None, self.d_pc.data_ptr(), self.d_q.data_ptr(), None, None,
-                                 self.d_sc.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self.stream))
+                                 self.d_sc.data_ptr(), self.scratch.data_ptr(), self.scratch_bytes,
+                                 self.saved.data_ptr(), self.saved_bytes, self.stream))
 
-    LAUNCHES_PER_STEP = 7  # prepare_taps, splat_fwd, conv_xy, conv_z_fwd, conv_z_bwd, conv_xy, splat_bwd
+    LAUNCHES_PER_STEP = 6  # splat_fwd, conv_xy, conv_z_fwd, conv_z_bwd, conv_xy, splat_bwd
+
+    STAGES = ("splat_fwd", "conv_xy_fwd", "conv_z_fwd", "conv_z_bwd", "conv_xy_bwd", "splat_bwd")
 
     def stage_times(self, steps, flush):
-        """Per-stage device time (CUDA events on the launch stream), same kernels as step()."""
-        L, c, cp = self.L, self.capi.check, self.capi
-        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.dev)  # noqa: E731
-        raw, tmp = f(B, V, V, V), f(B, V, V, V)
-        m1 = torch.empty(B * V * V * V // 32 + 1, dtype=torch.int32, device=self.dev)
-        m2 = torch.empty(B * V * V * 2, dtype=torch.int32, device=self.dev)
-        taps, rev = self.taps, self.taps.flip(0).contiguous()
-        st = self.stream
-        cfg = self.cfg
-        fo, cd, eps, md = float(cfg.focal_length), float(cfg.camera_distance), float(cfg.drc_logsum_clip_val), float(cfg.max_depth)
-        pl = (K - 1) // 2
-
-        def s_splat_fwd():
-            raw.zero_()
-            c(L.dpc_splat_fwd(self.pc.data_ptr(), self.q.data_ptr(), cp.POSE_QUAT, None, None, fo, cd, None, B, N, V, V,
-                              self.tr_pc.data_ptr(), raw.data_ptr(), None, None, None, st))
-
-        def s_conv_xy_fwd():
-            c(L.dpc_conv_xy(raw.data_ptr(), tmp.data_ptr(), taps.data_ptr(), K, pl, taps.data_ptr(), K, pl, B, V, V, 1,
-                            m1.data_ptr(), None, st))
-
-        def s_conv_z_fwd():
-            c(L.dpc_conv_z_fwd(tmp.data_ptr(), taps.data_ptr(), K, pl, self.sc1.data_ptr(), cp.PROJ_DRC, eps, cd, md, 1,
-                               B, V, V, self.vox.data_ptr(), m2.data_ptr(), self.proj.data_ptr(), None, None, st))
-
-        def s_conv_z_bwd():
-            self.d_sc.zero_()
-            c(L.dpc_conv_z_bwd(self.vox.data_ptr(), m2.data_ptr(), self.sc1.data_ptr(), rev.data_ptr(), K, K - 1 - pl,
-                               cp.PROJ_DRC, eps, cd, md, 1, B, V, V, self.g_proj.data_ptr(), None, None, None,
-                               tmp.data_ptr(), self.d_sc.data_ptr(), st))
-
-        def s_conv_xy_bwd():
-            c(L.dpc_conv_xy(tmp.data_ptr(), raw.data_ptr(), rev.data_ptr(), K, K - 1 - pl, rev.data_ptr(), K, K - 1 - pl,
-                            B, V, V, 0, None, m1.data_ptr(), st))
-
-        def s_splat_bwd():
-            self.d_q.zero_()
-            c(L.dpc_splat_bwd(self.pc.data_ptr(), self.q.data_ptr(), cp.POSE_QUAT, None, None, fo, cd, None, 0, B, N, V, V,
-                              raw.data_ptr(), None, None, self.d_pc.data_ptr(), self.d_q.data_ptr(), None, None, None, st))
-
-        stages = [("splat_fwd", s_splat_fwd), ("conv_xy_fwd", s_conv_xy_fwd), ("conv_z_fwd", s_conv_z_fwd),
-                  ("conv_z_bwd", s_conv_z_bwd), ("conv_xy_bwd", s_conv_xy_bwd), ("splat_bwd", s_splat_bwd)]
-        tot = {k: 0.0 for k, _ in stages}
-        for it in range(steps + 2):
-            if flush is not None:
-                flush.fill_(it)
-            evs = []
-            for name, fn in stages:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                fn()
-                if name == "conv_z_fwd":
-                    torch.sub(self.proj, self.gt3, out=self.g_proj)
-                e1.record()
-                evs.append((name, e0, e1))
-            torch.cuda.synchronize()
-            if it >= 2:
-                for name, e0, e1 in evs:
-                    tot[name] += e0.elapsed_time(e1)
-        return {k: v / steps for k, v in tot.items()}
+        """Per-stage device time of the SAME fused entry points step() calls: the library records
+        CUDA events on the launch stream around every stage (dpc_debug_set(3, 1))."""
+        L = self.L
+        tot = [0.0] * 6
+        buf = (ctypes.c_float * 6)()
+        L.dpc_debug_set(3, 1)
+        try:
+            for it in range(steps + 2):
+                if flush is not None:
+                    flush.fill_(it & 0xff)
+                self.step()
+                self.capi.check(L.dpc_debug_stage_ms(ctypes.cast(buf, ctypes.c_void_p)))
+                if it >= 2:
+                    for i in range(6):
+                        tot[i] += buf[i]
+        finally:
+            L.dpc_debug_set(3, 0)
+        return {k: tot[i] / steps for i, k in enumerate(self.STAGES)}
 
     def e2e_step(self):
         """Through the public API with host buffers: H2D inputs, forward, loss, backward, D2H results."""
@@ -340,7 +305,7 @@ def run_ours(args, rank, local_rank, world):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         stages = pipe.stage_times(min(args.steps, 20), flush)
-        dom = max(stages, key=stages.get)
+        dom = max((k for k in stages if k in STAGE_BYTES), key=stages.get)
         achieved = STAGE_BYTES[dom] * B / (stages[dom] * 1e-3) / 1e9
         step_gbs = FULL_PATH_BYTES * B / ((ms_total / args.steps) * 1e-3) / 1e9 if world == 1 else None
         line = {

@@ -29,7 +29,10 @@ c_i64 = ctypes.c_int64
 class ProjectParams(ctypes.Structure):
     _fields_ = [("B", c_i), ("N", c_i), ("Vz", c_i), ("V", c_i), ("pose_kind", c_i), ("mode", c_i),
                 ("K", c_i), ("Kz", c_i), ("focal_const", c_f), ("cam_dist", c_f), ("clip_eps", c_f),
-                ("max_depth", c_f)]
+                ("max_depth", c_f), ("flags", c_i)]
+
+
+FLAG_SCRATCH_RAW_ZERO = 1
 
 
 POSE_NONE, POSE_QUAT, POSE_MATRIX = -1, 0, 1
@@ -44,6 +47,7 @@ _SIGNATURES = {
     "dpc_last_cuda_error": (c_i, []),
     "dpc_is_cuda_build": (c_i, []),
     "dpc_debug_set": (c_i, [c_i, c_i]),
+    "dpc_debug_stage_ms": (c_i, [c_p]),
     "dpc_splat_fwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i,
                             c_p, c_p, c_p, c_p, c_p, c_p]),
     "dpc_splat_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i, c_i,
@@ -53,11 +57,12 @@ _SIGNATURES = {
                              c_p, c_p, c_p, c_p, c_p, c_p]),
     "dpc_conv_z_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i,
                              c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
-    "dpc_project_fast_workspace_bytes": (c_i64, [_PP]),
+    "dpc_project_fast_scratch_bytes": (c_i64, [_PP]),
+    "dpc_project_fast_saved_bytes": (c_i64, [_PP]),
     "dpc_project_fast_fwd": (c_i, [_PP, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                                   c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
+                                   c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
     "dpc_project_fast_bwd": (c_i, [_PP, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
+                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
     "dpc_gather_points": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "dpc_gather_points_bwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
 }

@@ -20,6 +20,21 @@ static int dpc_check_launch() {
 static int g_tune[4] = {4, 4, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
+// ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are
+// recorded on the caller's stream around every stage so bench.py can attribute the step time to
+// the very kernels the fused entry points launch.  Off by default (no events, no overhead).
+#ifndef DPC_EMU
+static cudaEvent_t g_ev[8];
+static bool g_ev_ready = false;
+static void stage_mark(int i, void* stream) {
+  if (!g_tune[3]) return;
+  if (!g_ev_ready) { for (int k = 0; k < 8; ++k) cudaEventCreate(&g_ev[k]); g_ev_ready = true; }
+  cudaEventRecord(g_ev[i], (cudaStream_t)stream);
+}
+#else
+static void stage_mark(int, void*) {}
+#endif
+
 static bool shape_ok(int B, int Vz, int V) {
   return B >= 1 && B <= 65535 && V >= 1 && V <= DPC_MAX_V && Vz >= 1 && Vz <= DPC_MAX_V;
 }
@@ -27,9 +42,26 @@ static bool shape_ok(int B, int Vz, int V) {
 extern "C" {
 
 int dpc_abi_version(void) { return 1; }
+/* ms between the stage marks of the last instrumented forward+backward (synchronises):
+ * out[0..5] = splat_fwd(+memset), conv_xy_fwd, conv_z_fwd, conv_z_bwd(+memsets), conv_xy_bwd, splat_bwd */
+int dpc_debug_stage_ms(float* out6) {
+#ifndef DPC_EMU
+  if (!out6 || !g_ev_ready) return DPC_ERR_ARG;
+  if (cudaEventSynchronize(g_ev[7]) != cudaSuccess) return DPC_ERR_CUDA;
+  const int pairs[6][2] = {{0, 1}, {1, 2}, {2, 3}, {4, 5}, {5, 6}, {6, 7}};
+  for (int i = 0; i < 6; ++i)
+    if (cudaEventElapsedTime(&out6[i], g_ev[pairs[i][0]], g_ev[pairs[i][1]]) != cudaSuccess) return DPC_ERR_CUDA;
+  return DPC_OK;
+#else
+  (void)out6;
+  return DPC_ERR_ARG;
+#endif
+}
+
 int dpc_debug_set(int key, int value) {
   if (key < 0 || key >= 4) return DPC_ERR_ARG;
   g_tune[key] = value;
+  if (key == 2) dpc_xy_grid_cap = value;
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
@@ -102,22 +134,30 @@ int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float
   return dpc_check_launch();
 }
 
-int dpc_conv_xy(const float* in, float* out, const float* taps_x, int Kx, int pad_lo_x,
-                const float* taps_y, int Ky, int pad_lo_y, int B, int Vz, int V,
-                int clip_in, uint32_t* mask_bits_out, const uint32_t* mask_bits_in, void* stream) {
-  if (!in || !out || !taps_x || !taps_y) return DPC_ERR_NULL;
+}  // extern "C" (internal launchers below have C++ linkage)
+
+// ---- internal launchers: like the public entry points plus `rev` (read the taps back to front:
+// the transposed correlation, so the backward needs no reversed copy of the taps), NULL taps =
+// identity filter, and `zero_in` (conv_xy hands its input back all-zero once it has been read).
+static int launch_conv_xy(const float* in, float* out, const float* taps_x, int Kx, int pad_lo_x,
+                          const float* taps_y, int Ky, int pad_lo_y, int B, int Vz, int V,
+                          int clip_in, uint32_t* mask_bits_out, const uint32_t* mask_bits_in,
+                          int rev, int zero_in, void* stream) {
+  if (!in || !out) return DPC_ERR_NULL;
   if (!shape_ok(B, Vz, V) || Kx < 1 || Ky < 1 || Kx > DPC_MAX_TAPS || Ky > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo_x < 0 || pad_lo_x >= Kx || pad_lo_y < 0 || pad_lo_y >= Ky) return DPC_ERR_ARG;
   if ((mask_bits_out || mask_bits_in) && ((V * V) % 32 != 0)) return DPC_ERR_SHAPE;
   if ((int64_t)B * Vz > 2147483647LL) return DPC_ERR_SHAPE;
-  if (dpc_conv_xy_fast_supported(V, Kx, pad_lo_x, Ky, pad_lo_y)) {
-    DPC_TRY(dpc_conv_xy_fast_launch(in, out, taps_x, taps_y, Kx, B, Vz, V, clip_in, mask_bits_out, mask_bits_in, stream));
+  float* zero_ptr = zero_in ? const_cast<float*>(in) : nullptr;
+  if (taps_x && taps_y && dpc_conv_xy_fast_supported(V, Kx, pad_lo_x, Ky, pad_lo_y)) {
+    DPC_TRY(dpc_conv_xy_fast_launch(in, out, taps_x, taps_y, Kx, B, Vz, V, clip_in, mask_bits_out, mask_bits_in,
+                                    rev, zero_ptr, stream));
     return dpc_check_launch();
   }
   DpcConvXYArgs a;
   a.in = in; a.out = out; a.taps_x = taps_x; a.Kx = Kx; a.plx = pad_lo_x;
   a.taps_y = taps_y; a.Ky = Ky; a.ply = pad_lo_y; a.B = B; a.Vz = Vz; a.V = V; a.clip_in = clip_in;
-  a.mask_out = mask_bits_out; a.mask_in = mask_bits_in;
+  a.mask_out = mask_bits_out; a.mask_in = mask_bits_in; a.rev = rev; a.zero_ptr = zero_ptr;
   const size_t smem = (size_t)(2 * V * V + 2 * (DPC_MAX_TAPS + 1)) * sizeof(float);
 #ifndef DPC_EMU
   if (smem > 48 * 1024) DPC_CUDA(cudaFuncSetAttribute(dpc_conv_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -131,24 +171,24 @@ static int conv_z_ty(int V) {
   return ty < 1 ? 1 : ty;
 }
 
-int dpc_conv_z_fwd(const float* in, const float* taps_z, int Kz, int pad_lo_z,
-                   const float* scale, int mode, float clip_eps, float cam_dist, float max_depth,
-                   int flip_y, int B, int Vz, int V,
-                   float* vox_out, uint32_t* mask2_out, float* proj, float* drc_probs,
-                   float* proj_depth, void* stream) {
-  if (!in || !taps_z || !vox_out) return DPC_ERR_NULL;
+static int launch_conv_z_fwd(const float* in, const float* taps_z, int Kz, int pad_lo_z,
+                             const float* scale, int mode, float clip_eps, float cam_dist, float max_depth,
+                             int flip_y, int B, int Vz, int V,
+                             float* vox_out, uint32_t* mask2_out, float* proj, float* drc_probs,
+                             float* proj_depth, void* stream) {
+  if (!in || !vox_out) return DPC_ERR_NULL;
   if (mode < DPC_PROJ_NONE || mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
   if (mode != DPC_PROJ_NONE && !proj) return DPC_ERR_NULL;
   if ((drc_probs || proj_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
   if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo_z < 0 || pad_lo_z >= Kz) return DPC_ERR_ARG;
-  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z, drc_probs != nullptr || proj_depth != nullptr)) {
+  if (taps_z && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z, drc_probs != nullptr || proj_depth != nullptr)) {
     DPC_TRY(dpc_conv_z_fwd_fast_launch(in, taps_z, Kz, scale, mode, clip_eps, cam_dist, max_depth, flip_y, B, Vz, V,
                                        vox_out, mask2_out, proj, drc_probs, proj_depth, stream));
     return dpc_check_launch();
   }
   DpcConvZArgs a;
-  a.in = in; a.taps = taps_z; a.K = Kz; a.pl = pad_lo_z; a.scale = scale; a.mode = mode; a.eps = clip_eps;
+  a.in = in; a.taps = taps_z; a.K = Kz; a.pl = pad_lo_z; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = clip_eps;
   a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = conv_z_ty(V);
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = drc_probs; a.depth = proj_depth;
   const size_t smem = ((size_t)Vz * a.TY * V + DPC_MAX_TAPS + 1) * sizeof(float);
@@ -160,24 +200,24 @@ int dpc_conv_z_fwd(const float* in, const float* taps_z, int Kz, int pad_lo_z,
   return dpc_check_launch();
 }
 
-int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
-                   const float* taps_z_rev, int Kz, int pad_lo_z_rev,
-                   int mode, float clip_eps, float cam_dist, float max_depth, int flip_y,
-                   int B, int Vz, int V,
-                   const float* g_proj, const float* g_vox, const float* g_probs, const float* g_depth,
-                   float* d_in, float* d_scale, void* stream) {
-  if (!vox || !taps_z_rev || !d_in) return DPC_ERR_NULL;
+static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
+                             const float* taps, int Kz, int pad_lo, int rev,
+                             int mode, float clip_eps, float cam_dist, float max_depth, int flip_y,
+                             int B, int Vz, int V,
+                             const float* g_proj, const float* g_vox, const float* g_probs, const float* g_depth,
+                             float* d_in, float* d_scale, void* stream) {
+  if (!vox || !d_in) return DPC_ERR_NULL;
   if (mode < DPC_PROJ_NONE || mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
   if ((g_probs || g_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
   if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
-  if (pad_lo_z_rev < 0 || pad_lo_z_rev >= Kz) return DPC_ERR_ARG;
-  if (dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z_rev, g_probs != nullptr || g_depth != nullptr)) {
-    DPC_TRY(dpc_conv_z_bwd_fast_launch(vox, mask2, scale, taps_z_rev, Kz, mode, clip_eps, cam_dist, max_depth, flip_y,
-                                       B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, stream));
+  if (pad_lo < 0 || pad_lo >= Kz) return DPC_ERR_ARG;
+  if (taps && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo, g_probs != nullptr || g_depth != nullptr)) {
+    DPC_TRY(dpc_conv_z_bwd_fast_launch(vox, mask2, scale, taps, Kz, mode, clip_eps, cam_dist, max_depth, flip_y,
+                                       B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, rev, stream));
     return dpc_check_launch();
   }
   DpcConvZBwdArgs a;
-  a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps_z_rev; a.K = Kz; a.pl = pad_lo_z_rev;
+  a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps; a.K = Kz; a.pl = pad_lo; a.rev = rev;
   a.mode = mode; a.eps = clip_eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
   a.B = B; a.Vz = Vz; a.V = V; a.TY = conv_z_ty(V);
   a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;
@@ -190,23 +230,62 @@ int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
   return dpc_check_launch();
 }
 
+extern "C" {
+
+int dpc_conv_xy(const float* in, float* out, const float* taps_x, int Kx, int pad_lo_x,
+                const float* taps_y, int Ky, int pad_lo_y, int B, int Vz, int V,
+                int clip_in, uint32_t* mask_bits_out, const uint32_t* mask_bits_in, void* stream) {
+  if (!taps_x || !taps_y) return DPC_ERR_NULL;
+  return launch_conv_xy(in, out, taps_x, Kx, pad_lo_x, taps_y, Ky, pad_lo_y, B, Vz, V, clip_in, mask_bits_out,
+                        mask_bits_in, 0, 0, stream);
+}
+
+int dpc_conv_z_fwd(const float* in, const float* taps_z, int Kz, int pad_lo_z,
+                   const float* scale, int mode, float clip_eps, float cam_dist, float max_depth,
+                   int flip_y, int B, int Vz, int V,
+                   float* vox_out, uint32_t* mask2_out, float* proj, float* drc_probs,
+                   float* proj_depth, void* stream) {
+  if (!taps_z) return DPC_ERR_NULL;
+  return launch_conv_z_fwd(in, taps_z, Kz, pad_lo_z, scale, mode, clip_eps, cam_dist, max_depth, flip_y, B, Vz, V,
+                           vox_out, mask2_out, proj, drc_probs, proj_depth, stream);
+}
+
+int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
+                   const float* taps_z_rev, int Kz, int pad_lo_z_rev,
+                   int mode, float clip_eps, float cam_dist, float max_depth, int flip_y,
+                   int B, int Vz, int V,
+                   const float* g_proj, const float* g_vox, const float* g_probs, const float* g_depth,
+                   float* d_in, float* d_scale, void* stream) {
+  if (!taps_z_rev) return DPC_ERR_NULL;
+  return launch_conv_z_bwd(vox, mask2, scale, taps_z_rev, Kz, pad_lo_z_rev, 0, mode, clip_eps, cam_dist, max_depth,
+                           flip_y, B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, stream);
+}
+
 // ------------------------------------------------------------------------------------ fused path
 static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-struct DpcWs { float* raw; float* tmp; uint32_t* mask1; uint32_t* mask2; float* taps_rev; int64_t total; };
+struct DpcScratch { float* raw; float* tmp; int64_t total; };
+struct DpcSaved { uint32_t* mask1; uint32_t* mask2; int64_t total; };
 
-static DpcWs ws_layout(const dpc_project_params* p, void* base) {
+static DpcScratch scratch_layout(const dpc_project_params* p, void* base) {
+  const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
+  DpcScratch w;
+  char* c = (char*)base;
+  w.raw = (float*)c;
+  w.tmp = (float*)(c + align256(g * 4));
+  w.total = 2 * align256(g * 4);
+  return w;
+}
+
+static DpcSaved saved_layout(const dpc_project_params* p, void* base) {
   const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
   const int64_t nw = (p->Vz + 31) / 32;
-  int64_t off = 0;
-  DpcWs w;
+  DpcSaved w;
   char* c = (char*)base;
-  w.raw = (float*)(c + off); off += align256(g * 4);
-  w.tmp = (float*)(c + off); off += align256(g * 4);
-  w.mask1 = (uint32_t*)(c + off); off += align256((g / 32 + 1) * 4);
-  w.mask2 = (uint32_t*)(c + off); off += align256((int64_t)p->B * p->V * p->V * nw * 4);
-  w.taps_rev = (float*)(c + off); off += align256(4 * (DPC_MAX_TAPS + 1) * 4);
-  w.total = off;
+  w.mask1 = (uint32_t*)c;
+  const int64_t m1 = align256((g / 32 + 1) * 4);
+  w.mask2 = (uint32_t*)(c + m1);
+  w.total = m1 + align256((int64_t)p->B * p->V * p->V * nw * 4);
   return w;
 }
 
@@ -221,52 +300,47 @@ static int params_ok(const dpc_project_params* p) {
   return DPC_OK;
 }
 
-int64_t dpc_project_fast_workspace_bytes(const dpc_project_params* p) {
+int64_t dpc_project_fast_scratch_bytes(const dpc_project_params* p) {
   if (params_ok(p) != DPC_OK) return -1;
-  return ws_layout(p, nullptr).total;
+  return scratch_layout(p, nullptr).total;
 }
 
-// identity tap used when the caller passes no smoothing kernel (kernel=None in the reference):
-// 1.0 * x + exact zeros is exact, so the same kernels serve both cases.
-#ifndef DPC_EMU
-__global__ void
-#else
-static void
-#endif
-dpc_prepare_taps_kernel(const float* taps_xy, int K, const float* taps_z, int Kz, float* out) {
-  // out: [0..63] xy taps, [64..127] z taps, [128..191] reversed xy, [192..255] reversed z
-  const int t = threadIdx.x;
-  const int S = DPC_MAX_TAPS + 1;
-  const int k = K > 0 ? K : 1, kz = Kz > 0 ? Kz : 1;
-  if (t < k) { const float v = K > 0 ? taps_xy[t] : 1.0f; out[t] = v; out[2 * S + (k - 1 - t)] = v; }
-  if (t < kz) { const float v = Kz > 0 ? taps_z[t] : 1.0f; out[S + t] = v; out[3 * S + (kz - 1 - t)] = v; }
+int64_t dpc_project_fast_saved_bytes(const dpc_project_params* p) {
+  if (params_ok(p) != DPC_OK) return -1;
+  return saved_layout(p, nullptr).total;
 }
 
 int dpc_project_fast_fwd(const dpc_project_params* p,
                          const float* pc, const float* pose, const float* trans, const float* focal,
                          const float* scale, const float* taps_xy, const float* taps_z,
                          float* tr_pc, float* voxels, float* proj, float* drc_probs, float* proj_depth,
-                         void* workspace, int64_t workspace_bytes, void* stream) {
+                         void* scratch, int64_t scratch_bytes, void* saved, int64_t saved_bytes, void* stream) {
   DPC_TRY(params_ok(p));
-  if (!pc || !voxels || !proj || !workspace) return DPC_ERR_NULL;
+  if (!pc || !voxels || !proj || !scratch || !saved) return DPC_ERR_NULL;
   if (p->K > 0 && (!taps_xy || !taps_z)) return DPC_ERR_NULL;
-  if (((uintptr_t)workspace & 15) != 0) return DPC_ERR_WORKSPACE;
-  DpcWs w = ws_layout(p, workspace);
-  if (workspace_bytes < w.total) return DPC_ERR_WORKSPACE;
-  const int S = DPC_MAX_TAPS + 1;
+  if ((((uintptr_t)scratch) & 15) != 0 || (((uintptr_t)saved) & 15) != 0) return DPC_ERR_WORKSPACE;
+  DpcScratch w = scratch_layout(p, scratch);
+  DpcSaved sv = saved_layout(p, saved);
+  if (scratch_bytes < w.total || saved_bytes < sv.total) return DPC_ERR_WORKSPACE;
   const int K = p->K > 0 ? p->K : 1, Kz = p->Kz > 0 ? p->Kz : 1;
+  const float* tx = p->K > 0 ? taps_xy : nullptr;   // NULL taps = identity filter (kernel=None)
+  const float* tz = p->Kz > 0 ? taps_z : nullptr;
   const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
-  DPC_LAUNCH(dpc_prepare_taps_kernel, dim3(1), dim3(64), 0, stream, taps_xy, p->K, taps_z, p->Kz, w.taps_rev);
-  DPC_TRY(dpc_check_launch());
-  DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
+  stage_mark(0, stream);
+  if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO))
+    DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
   DPC_TRY(dpc_splat_fwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
                         p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, stream));
-  DPC_TRY(dpc_conv_xy(w.raw, w.tmp, w.taps_rev, K, (K - 1) / 2, w.taps_rev, K, (K - 1) / 2,
-                      p->B, p->Vz, p->V, /*clip_in=*/1, w.mask1, nullptr, stream));
+  stage_mark(1, stream);
+  // clip + x/y smoothing; the pass also returns the raw grid to all-zero (next splat target)
+  DPC_TRY(launch_conv_xy(w.raw, w.tmp, tx, K, (K - 1) / 2, tx, K, (K - 1) / 2,
+                         p->B, p->Vz, p->V, /*clip_in=*/1, sv.mask1, nullptr, /*rev=*/0, /*zero_in=*/1, stream));
+  stage_mark(2, stream);
   const bool want_probs = (p->mode != DPC_PROJ_MAX);
-  DPC_TRY(dpc_conv_z_fwd(w.tmp, w.taps_rev + S, Kz, (Kz - 1) / 2, scale, p->mode, p->clip_eps, p->cam_dist,
-                         p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V, voxels, scale ? w.mask2 : nullptr, proj,
-                         want_probs ? drc_probs : nullptr, want_probs ? proj_depth : nullptr, stream));
+  DPC_TRY(launch_conv_z_fwd(w.tmp, tz, Kz, (Kz - 1) / 2, scale, p->mode, p->clip_eps, p->cam_dist,
+                            p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V, voxels, scale ? sv.mask2 : nullptr, proj,
+                            want_probs ? drc_probs : nullptr, want_probs ? proj_depth : nullptr, stream));
+  stage_mark(3, stream);
   return DPC_OK;
 }
 
@@ -277,15 +351,17 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                          const float* g_proj, const float* g_voxels, const float* g_tr_pc,
                          const float* g_probs, const float* g_depth,
                          float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_scale,
-                         void* workspace, int64_t workspace_bytes, void* stream) {
+                         void* scratch, int64_t scratch_bytes, const void* saved, int64_t saved_bytes, void* stream) {
   DPC_TRY(params_ok(p));
-  if (!pc || !voxels || !workspace) return DPC_ERR_NULL;
-  (void)taps_xy; (void)taps_z;  // the forward left both tap sets (and their reversals) in the workspace
-  if (((uintptr_t)workspace & 15) != 0) return DPC_ERR_WORKSPACE;
-  DpcWs w = ws_layout(p, workspace);
-  if (workspace_bytes < w.total) return DPC_ERR_WORKSPACE;
-  const int S = DPC_MAX_TAPS + 1;
+  if (!pc || !voxels || !scratch || !saved) return DPC_ERR_NULL;
+  if (p->K > 0 && (!taps_xy || !taps_z)) return DPC_ERR_NULL;
+  if ((((uintptr_t)scratch) & 15) != 0 || (((uintptr_t)saved) & 15) != 0) return DPC_ERR_WORKSPACE;
+  DpcScratch w = scratch_layout(p, scratch);
+  DpcSaved sv = saved_layout(p, const_cast<void*>(saved));
+  if (scratch_bytes < w.total || saved_bytes < sv.total) return DPC_ERR_WORKSPACE;
   const int K = p->K > 0 ? p->K : 1, Kz = p->Kz > 0 ? p->Kz : 1;
+  const float* tx = p->K > 0 ? taps_xy : nullptr;
+  const float* tz = p->Kz > 0 ? taps_z : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (d_pose) DPC_CUDA(cudaMemsetAsync(d_pose, 0, (size_t)p->B * (p->pose_kind == DPC_POSE_MATRIX ? 16 : 4) * 4, st));
   if (d_trans) DPC_CUDA(cudaMemsetAsync(d_trans, 0, (size_t)p->B * 3 * 4, st));
@@ -293,17 +369,22 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   if (d_scale) DPC_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->B * 4, st));
   const bool any_grid_grad = g_proj || g_voxels || g_probs || g_depth;
   const float* d_raw = nullptr;
+  stage_mark(4, stream);
   if (any_grid_grad) {
-    // voxels/proj -> d(xy-smoothed) in tmp -> d(raw) in raw (the clip mask saved by the forward applied)
-    DPC_TRY(dpc_conv_z_bwd(voxels, scale ? w.mask2 : nullptr, scale, w.taps_rev + 3 * S, Kz, Kz - 1 - (Kz - 1) / 2,
-                           p->mode, p->clip_eps, p->cam_dist, p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V,
-                           g_proj, g_voxels, g_probs, g_depth, w.tmp, d_scale, stream));
-    DPC_TRY(dpc_conv_xy(w.tmp, w.raw, w.taps_rev + 2 * S, K, K - 1 - (K - 1) / 2, w.taps_rev + 2 * S, K,
-                        K - 1 - (K - 1) / 2, p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, w.mask1, stream));
-    d_raw = w.raw;
+    // voxels/proj -> dL/d(xy-smoothed) in tmp -> dL/d(raw) in tmp again (per-slice in place; the saved
+    // clip mask applied).  `raw` is not touched: it stays all-zero for the next forward.
+    DPC_TRY(launch_conv_z_bwd(voxels, scale ? sv.mask2 : nullptr, scale, tz, Kz, Kz - 1 - (Kz - 1) / 2, /*rev=*/1,
+                              p->mode, p->clip_eps, p->cam_dist, p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V,
+                              g_proj, g_voxels, g_probs, g_depth, w.tmp, d_scale, stream));
+    stage_mark(5, stream);
+    DPC_TRY(launch_conv_xy(w.tmp, w.tmp, tx, K, K - 1 - (K - 1) / 2, tx, K, K - 1 - (K - 1) / 2,
+                           p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, sv.mask1, /*rev=*/1, /*zero_in=*/0, stream));
+    d_raw = w.tmp;
   }
+  stage_mark(6, stream);
   DPC_TRY(dpc_splat_bwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
                         p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr, stream));
+  stage_mark(7, stream);
   return DPC_OK;
 }
 

@@ -83,7 +83,7 @@ DPC_DEV void dpc_bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes,
                ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
 #else
   memcpy(smem_dst, gmem_src, bytes);
-  *bar = 1;
+  dpc_emu::mbar_complete(bar);
 #endif
 }
 
@@ -100,7 +100,7 @@ DPC_DEV void dpc_mbar_wait(uint64_t* bar, unsigned phase) {
       "DONE_%=:\n"
       "}\n" ::"r"(a), "r"(phase) : "memory");
 #else
-  (void)bar; (void)phase;
+  dpc_emu::mbar_wait(bar, phase);
 #endif
 }
 

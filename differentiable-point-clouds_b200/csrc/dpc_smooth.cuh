@@ -13,12 +13,20 @@
 
 #define DPC_CONV_THREADS 256
 
+// tap j of a K-tap filter: NULL taps = the identity filter (K = 1, used when the caller passes no
+// smoothing kernel); rev = read the taps back to front (the transposed correlation of the backward).
+DPC_DEV float dpc_tap(const float* taps, int K, int j, int rev) {
+  return taps ? taps[rev ? (K - 1 - j) : j] : 1.0f;
+}
+
 struct DpcConvXYArgs {
   const float* in; float* out;
   const float* taps_x; int Kx; int plx;
   const float* taps_y; int Ky; int ply;
   int B, Vz, V; int clip_in;
   uint32_t* mask_out; const uint32_t* mask_in;
+  int rev;            // taps are read back to front
+  float* zero_ptr;    // == in when the input is to be overwritten with zeros once it has been read
 };
 
 #ifndef DPC_EMU
@@ -35,8 +43,8 @@ dpc_conv_xy_kernel(DpcConvXYArgs a) {
   float* ty = tx + DPC_MAX_TAPS + 1;
   const int tid = threadIdx.x;
   const size_t slice = (size_t)blockIdx.x * VV;
-  if (tid < a.Kx) tx[tid] = a.taps_x[tid];
-  if (tid < a.Ky) ty[tid] = a.taps_y[tid];
+  if (tid < a.Kx) tx[tid] = dpc_tap(a.taps_x, a.Kx, tid, a.rev);
+  if (tid < a.Ky) ty[tid] = dpc_tap(a.taps_y, a.Ky, tid, a.rev);
   const int rounds = (VV + DPC_CONV_THREADS - 1) / DPC_CONV_THREADS;
   for (int r = 0; r < rounds; ++r) {
     const int i = r * DPC_CONV_THREADS + tid;
@@ -47,6 +55,7 @@ dpc_conv_xy_kernel(DpcConvXYArgs a) {
     }
     if (a.clip_in) v = dpc_clip01(v);
     if (i < VV) A[i] = v;
+    if (a.zero_ptr && i < VV) a.zero_ptr[slice + i] = 0.0f;
   }
   __syncthreads();
   for (int i = tid; i < VV; i += DPC_CONV_THREADS) {
@@ -78,7 +87,7 @@ dpc_conv_xy_kernel(DpcConvXYArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 struct DpcConvZArgs {
-  const float* in; const float* taps; int K; int pl;
+  const float* in; const float* taps; int K; int pl; int rev;
   const float* scale; int mode; float eps; float cam_dist; float max_depth; int flip_y;
   int B, Vz, V, TY;
   float* vox_out; uint32_t* mask2_out; float* proj; float* probs; float* depth;
@@ -118,7 +127,7 @@ dpc_conv_z_fwd_kernel(DpcConvZArgs a) {
   float* tile = sm;                   // [Vz][TY*V]
   float* taps = sm + (size_t)Vz * RW;
   const int tid = threadIdx.x;
-  if (tid < a.K) taps[tid] = a.taps[tid];
+  if (tid < a.K) taps[tid] = dpc_tap(a.taps, a.K, tid, a.rev);
   const float* src = a.in + ((size_t)b * Vz * V + y0) * V;
   const int rowlen = rows * V;
   for (int z = 0; z < Vz; ++z)
@@ -175,7 +184,7 @@ dpc_conv_z_fwd_kernel(DpcConvZArgs a) {
 
 struct DpcConvZBwdArgs {
   const float* vox; const uint32_t* mask2; const float* scale;
-  const float* taps; int K; int pl;        // reversed taps / pad
+  const float* taps; int K; int pl; int rev;   // taps of the TRANSPOSED correlation (rev: given forward taps)
   int mode; float eps; float cam_dist; float max_depth; int flip_y;
   int B, Vz, V, TY;
   const float* g_proj; const float* g_vox; const float* g_probs; const float* g_depth;
@@ -198,7 +207,7 @@ dpc_conv_z_bwd_kernel(DpcConvZBwdArgs a) {
   float* tileD = sm + (size_t)Vz * RW;       // T_k, then dL/d(smoothed)
   float* taps = tileD + (size_t)Vz * RW;
   const int tid = threadIdx.x;
-  if (tid < a.K) taps[tid] = a.taps[tid];
+  if (tid < a.K) taps[tid] = dpc_tap(a.taps, a.K, tid, a.rev);
   const float* src = a.vox + ((size_t)b * Vz * V + y0) * V;
   const int rowlen = rows * V;
   for (int z = 0; z < Vz; ++z)

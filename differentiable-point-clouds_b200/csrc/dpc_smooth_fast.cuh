@@ -37,14 +37,45 @@ DPC_DEV void dpc_col_conv_pairs(const float* base, int stride, int r0, int nrows
 }
 
 // ------------------------------------------------------------------------------ conv_xy, V = 64
+// Persistent CTAs (3 per SM) walk the depth slices round-robin.  The next slice is prefetched by
+// the TMA engine (64 bulk copies of one 256-byte row each, into a padded smem image) while the
+// current one is being correlated, so no warp ever waits on a global load in steady state; the
+// clip to [0,1] and the clip-pass bits are computed when the x pass reads its window.
 struct DpcConvXY64Args {
   const float* in; float* out; const float* taps_x; const float* taps_y;
-  int clip_in; uint32_t* mask_out; const uint32_t* mask_in;
+  int clip_in; uint32_t* mask_out; const uint32_t* mask_in; int nslices;
+  int rev; float* zero_ptr;
 };
+
+#define DPC_XY_SMEM_FLOATS (3 * DPC_F64_V * DPC_F64_S)          // A[2] + M
+#define DPC_XY_SMEM_BYTES (DPC_XY_SMEM_FLOATS * 4 + 512)
+
+// Rows of `nrows` x `row_bytes` from global (row pitch src_pitch floats) into smem (row pitch
+// dst_pitch floats) through the TMA engine, completion on `bar`.  Called by ALL lanes of warp 0:
+// lane 0 posts the expected byte count, then every lane issues its share of the bulk copies.
+DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, size_t src_pitch, int nrows,
+                                unsigned row_bytes, uint64_t* bar) {
+  const int lane = threadIdx.x & 31;
+#ifndef DPC_EMU
+  const unsigned bb = (unsigned)__cvta_generic_to_shared(bar);
+  if (lane == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"((unsigned)nrows * row_bytes) : "memory");
+  __syncwarp();
+  for (int r = lane; r < nrows; r += 32) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (size_t)r * dst_pitch);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src + (size_t)r * src_pitch), "r"(row_bytes), "r"(bb) : "memory");
+  }
+#else
+  for (int r = lane; r < nrows; r += 32) memcpy(dst + (size_t)r * dst_pitch, src + (size_t)r * src_pitch, row_bytes);
+  __syncwarp();
+  if (lane == 0) dpc_emu::mbar_complete(bar);
+#endif
+}
 
 template <int K>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 #else
 static void
 #endif
@@ -53,94 +84,114 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
   constexpr int WL = ((PL + 3) / 4) * 4;            // window starts WL floats left of the first output
   constexpr int NW4 = (WL + 16 + WL) / 4;           // float4 groups in the x window
   static_assert((K & 1) == 1 && K <= 21, "odd K <= 21");
-  __shared__ __align__(16) float A[V * S];
-  __shared__ __align__(16) float M[V * S];
-  __shared__ float tx[K + 3], ty[K + 3];
+  DPC_DYN_SMEM(float, sm);
+  float* Abuf = sm;                                  // [2][V*S]
+  float* M = sm + 2 * V * S;                         // [V*S]
+  float* txe = sm + 3 * V * S;                       // E[i] = t[i-1], i = 0..K+1 (zero outside), padded to 24
+  float* txo = txe + 24;                             // O[i] = E[i+1]
+  float2* tyd = reinterpret_cast<float2*>(txo + 24);  // y taps, each duplicated into a float2 (FFMA2 operand)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(txo + 24 + 48);   // 2 mbarriers (8-byte aligned offset)
   const int tid = threadIdx.x;
-  const size_t slice = (size_t)blockIdx.x * (V * V);
-  if (tid < K) { tx[tid + 1] = a.taps_x[tid]; ty[tid] = a.taps_y[tid]; }
-  if (tid == 0) { tx[0] = 0.0f; tx[K + 1] = 0.0f; }
-
-  // ---- phase 0: slice -> smem (float4, coalesced), clip, clip-mask bits
-  {
-    const float4* src = reinterpret_cast<const float4*>(a.in + slice);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = tid + 256 * k;            // float4 index in the slice: row = i/16, col4 = i%16
-      float4 v = src[i];
-      if (a.mask_out) {
-        unsigned nib = ((v.x >= 0.0f && v.x <= 1.0f) ? 1u : 0u) | ((v.y >= 0.0f && v.y <= 1.0f) ? 2u : 0u) |
-                       ((v.z >= 0.0f && v.z <= 1.0f) ? 4u : 0u) | ((v.w >= 0.0f && v.w <= 1.0f) ? 8u : 0u);
-        unsigned word = nib << (4 * (tid & 7));
-        word |= __shfl_xor_sync(DPC_FULL, word, 1);
-        word |= __shfl_xor_sync(DPC_FULL, word, 2);
-        word |= __shfl_xor_sync(DPC_FULL, word, 4);
-        if ((tid & 7) == 0) a.mask_out[(slice >> 5) + (i >> 3)] = word;
-      }
-      if (a.clip_in) { v.x = dpc_clip01(v.x); v.y = dpc_clip01(v.y); v.z = dpc_clip01(v.z); v.w = dpc_clip01(v.w); }
-      *reinterpret_cast<float4*>(&A[(i >> 4) * S + (i & 15) * 4]) = v;
-    }
+  if (tid < 24) {
+    const int a_e = tid - 1, a_o = tid;              // tap indices behind E[tid], O[tid]
+    txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
+    txo[tid] = (a_o >= 0 && a_o < K) ? dpc_tap(a.taps_x, K, a_o, a.rev) : 0.0f;
+    const float tyv = (tid < K) ? dpc_tap(a.taps_y, K, tid, a.rev) : 0.0f;
+    tyd[tid] = dpc_f2(tyv, tyv);
   }
+  if (tid == 0) { dpc_mbar_init(&bars[0], 1); dpc_mbar_init(&bars[1], 1); }
   __syncthreads();
+  int slice = blockIdx.x;
+  if (slice >= a.nslices) return;
+  if (tid < 32) dpc_warp_bulk_rows(Abuf, S, a.in + (size_t)slice * (V * V), V, V, V * 4, &bars[0]);
 
-  // ---- phase 1: x correlation.  Thread = (row y, run r of 16 outputs); a warp = 32 rows, one r.
-  {
-    const int y = tid & 63, r = tid >> 6;
-    const int x0 = r * 16;
-    float2 tp[K + 1];                      // tp[a+1] = (t[a], t[a+1]), a = -1..K-1, zero outside
+  for (int it = 0; slice < a.nslices; ++it, slice += gridDim.x) {
+    const int cb = it & 1;
+    float* A = Abuf + cb * (V * S);
+    const int next = slice + gridDim.x;
+    // the other buffer was last read by the x pass of the previous iteration, which every thread
+    // left before the barrier that follows it
+    if (tid < 32 && next < a.nslices)
+      dpc_warp_bulk_rows(Abuf + (cb ^ 1) * (V * S), S, a.in + (size_t)next * (V * V), V, V, V * 4, &bars[cb ^ 1]);
+    dpc_mbar_wait(&bars[cb], (it >> 1) & 1);
+    const size_t sl = (size_t)slice * (V * V);
+    if (a.zero_ptr) {   // the slice lives in smem now: hand the global copy back all-zero (next forward's splat target)
+      float4* zp = reinterpret_cast<float4*>(a.zero_ptr + sl);
 #pragma unroll
-    for (int q = 0; q < K + 1; ++q) tp[q] = dpc_f2(tx[q], tx[q + 1]);
-    float2 acc[16];
+      for (int k = 0; k < 4; ++k) zp[tid + 256 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // ---- x correlation.  Thread = (row y, run r of 16 outputs); a warp = 32 rows, one r.
+    {
+      const int y = tid & 63, r = tid >> 6;
+      const int x0 = r * 16;
+      float2 acc[16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-    const float* rowp = A + y * S;
+      for (int o = 0; o < 16; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+      const float* rowp = A + y * S;
+      unsigned mbits = 0u;
 #pragma unroll
-    for (int g = 0; g < NW4; ++g) {
-      const int xs = x0 - WL + 4 * g;       // warp-uniform: whole float4 in or out of the row
-      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (xs >= 0 && xs < V) w4 = *reinterpret_cast<const float4*>(rowp + xs);
+      for (int g = 0; g < NW4; ++g) {
+        const int xs = x0 - WL + 4 * g;       // warp-uniform: whole float4 in or out of the row
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xs >= 0 && xs < V) w4 = *reinterpret_cast<const float4*>(rowp + xs);
+        if (a.clip_in) {
+          if (g >= WL / 4 && g < WL / 4 + 4) {   // the thread's own 16 voxels: clip-pass bits
+            const int sh = 4 * (g - WL / 4);
+            mbits |= ((w4.x >= 0.0f && w4.x <= 1.0f) ? 1u : 0u) << sh;
+            mbits |= ((w4.y >= 0.0f && w4.y <= 1.0f) ? 2u : 0u) << sh;
+            mbits |= ((w4.z >= 0.0f && w4.z <= 1.0f) ? 4u : 0u) << sh;
+            mbits |= ((w4.w >= 0.0f && w4.w <= 1.0f) ? 8u : 0u) << sh;
+          }
+          w4.x = dpc_clip01(w4.x); w4.y = dpc_clip01(w4.y); w4.z = dpc_clip01(w4.z); w4.w = dpc_clip01(w4.w);
+        }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float2 w = h ? dpc_f2(w4.z, w4.w) : dpc_f2(w4.x, w4.y);
-        // window pair index i = 4g + 2h; for output o the first tap of the pair is a = i - o - WL + PL
+        for (int h = 0; h < 2; ++h) {
+          const float2 w = h ? dpc_f2(w4.z, w4.w) : dpc_f2(w4.x, w4.y);
+          // window pair index i = 4g + 2h; for output o the first tap of the pair is a = i - o - WL + PL,
+          // the tap pair (t[a], t[a+1]) = (E[a+1], E[a+2]): aligned in E for odd a, in O for even a
 #pragma unroll
-        for (int o = 0; o < 16; ++o) {
-          if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1)
-            acc[o] = dpc_ffma2(w, tp[4 * g + 2 * h - o - WL + PL + 1], acc[o]);
+          for (int o = 0; o < 16; ++o) {
+            if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1) {
+              const int q = 4 * g + 2 * h - o - WL + PL + 1;   // 0..K
+              const float2 tp = (q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1))
+                                        : *reinterpret_cast<const float2*>(txe + q);
+              acc[o] = dpc_ffma2(w, tp, acc[o]);
+            }
+          }
         }
       }
-    }
-    float* dst = M + y * S + x0;
+      if (a.mask_out) reinterpret_cast<uint16_t*>(a.mask_out)[(sl + (size_t)y * V + x0) >> 4] = (uint16_t)mbits;
+      float* dst = M + y * S + x0;
 #pragma unroll
-    for (int o = 0; o < 16; o += 4) {
-      *reinterpret_cast<float4*>(dst + o) = make_float4(acc[o].x + acc[o].y, acc[o + 1].x + acc[o + 1].y,
-                                                         acc[o + 2].x + acc[o + 2].y, acc[o + 3].x + acc[o + 3].y);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: y correlation.  Thread = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
-  {
-    const int xp = tid & 31, y0 = (tid >> 5) * 8;
-    float2 tt[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) tt[j] = dpc_f2(ty[j], ty[j]);
-    float2 acc[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-    dpc_col_conv_pairs<K, 8>(M + 2 * xp, S, y0, V, tt, acc);
-    float* dst = a.out + slice + (size_t)y0 * V + 2 * xp;
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      float2 v = acc[o];
-      if (a.mask_in) {
-        const size_t e = slice + (size_t)(y0 + o) * V + 2 * xp;
-        const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
-        if (!(wbits & 1u)) v.x = 0.0f;
-        if (!(wbits & 2u)) v.y = 0.0f;
+      for (int o = 0; o < 16; o += 4) {
+        *reinterpret_cast<float4*>(dst + o) = make_float4(acc[o].x + acc[o].y, acc[o + 1].x + acc[o + 1].y,
+                                                           acc[o + 2].x + acc[o + 2].y, acc[o + 3].x + acc[o + 3].y);
       }
-      *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
     }
+    __syncthreads();
+
+    // ---- y correlation.  Thread = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
+    {
+      const int xp = tid & 31, y0 = (tid >> 5) * 8;
+      float2 acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+      dpc_col_conv_pairs<K, 8>(M + 2 * xp, S, y0, V, tyd, acc);
+      float* dst = a.out + sl + (size_t)y0 * V + 2 * xp;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        float2 v = acc[o];
+        if (a.mask_in) {
+          const size_t e = sl + (size_t)(y0 + o) * V + 2 * xp;
+          const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
+          if (!(wbits & 1u)) v.x = 0.0f;
+          if (!(wbits & 2u)) v.y = 0.0f;
+        }
+        *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
+      }
+    }
+    __syncthreads();   // M is free for the next slice
   }
 }
 
@@ -165,37 +216,23 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
   constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZF_TY, RW = TY * V;
   DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]
   __shared__ __align__(8) uint64_t bar;
-  __shared__ float tz[K];
+  __shared__ __align__(8) float2 tzd[K];          // taps, each duplicated into a float2 (FFMA2 operand)
   __shared__ __align__(8) float comb[TY][V][2];   // (T, S) or (max, -) of the low depth half per ray
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
-  if (tid < K) tz[tid] = a.taps[tid];
+  if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
   // ---- tile load: 64 bulk copies (one per depth level, TY*V*4 = 1 KiB each) through the TMA
-  // engine, completion on one mbarrier; no register staging.
+  // engine, two per lane of warp 0, completion on one mbarrier; no register staging.
   const float* src = a.in + ((size_t)b * Vz * V + y0) * V;
   if (tid == 0) dpc_mbar_init(&bar, 1);
   __syncthreads();
-  if (tid == 0) {
-#ifndef DPC_EMU
-    unsigned bb = (unsigned)__cvta_generic_to_shared(&bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"((unsigned)(Vz * RW * 4)) : "memory");
-    for (int z = 0; z < Vz; ++z) {
-      unsigned d = (unsigned)__cvta_generic_to_shared(tile + z * RW);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(d), "l"(src + (size_t)z * V * V), "r"((unsigned)(RW * 4)), "r"(bb) : "memory");
-    }
-#else
-    for (int z = 0; z < Vz; ++z) memcpy(tile + z * RW, src + (size_t)z * V * V, RW * 4);
-#endif
-  }
+  if (tid < 32) dpc_warp_bulk_rows(tile, RW, src, (size_t)V * V, Vz, RW * 4, &bar);
   dpc_mbar_wait(&bar, 0);
   __syncthreads();
 
   const int w = tid >> 5, xp = tid & 31;
   const int ty = w >> 1, h = w & 1, y = y0 + ty;
-  float2 tt[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) tt[j] = dpc_f2(tz[j], tz[j]);
+  const float2* tt = tzd;
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
@@ -263,23 +300,31 @@ static void
 #endif
 dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
   constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZF_TY, RW = TY * V;
-  DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]: T_k, then dL/d(smoothed)
-  __shared__ float tz[K];
+  DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]: forward voxels, overwritten by dL/d(smoothed)
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) float2 tzd[K];
   __shared__ float red[DPC_ZF_THREADS / 32];
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
-  if (tid < K) tz[tid] = a.taps[tid];
+  if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
+  // the forward's voxels of these 4 image rows, all depth levels: TMA bulk copies into the tile
+  if (tid == 0) dpc_mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid < 32) dpc_warp_bulk_rows(tile, RW, a.vox + ((size_t)b * Vz * V + y0) * V, (size_t)V * V, Vz, RW * 4, &bar);
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const float inv_s = (s != 0.0f) ? 1.0f / s : 0.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
   float ds = 0.0f;
-  // ---- phase 1: one thread per ray.  dL/dvoxel from the projection, then back through
-  // clip(. * scale); result (dL/d smoothed) left in the tile.
+  dpc_mbar_wait(&bar, 0);
+  // ---- phase 1: one thread per ray, in place in the tile (a thread touches only its own column).
+  // Silhouette gradient g:  dL/du_k = g * prod_{j != k} (1-u_j) = g * T_Z / (1-u_k)  for k > 0 and
+  // g * (c_0 - 1 + T_Z / (1-u_0)) for k = 0, T_Z = prod_j (1-u_j).  1-u >= eps (the clip), and where
+  // T_Z underflows the true value is below 1e-35, so the quotient form is exact to ~1e-7 relative
+  // or negligible in absolute terms; no second scan, no carried state.
   {
     const int ty = tid >> 6, x = tid & 63, y = y0 + ty;
     const int yo = a.flip_y ? (V - 1 - y) : y;
-    const float* vin = a.vox + ((size_t)b * Vz * V + y) * V + x;
     const float* gv = a.g_vox ? a.g_vox + ((size_t)b * Vz * V + y) * V + x : nullptr;
     float* col = tile + ty * V + x;
     const float gp = a.g_proj ? a.g_proj[((size_t)b * V + yo) * V + x] : 0.0f;
@@ -288,38 +333,37 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
       const uint2 mw = *reinterpret_cast<const uint2*>(a.mask2 + (((size_t)b * V + y) * V + x) * 2);
       mlo = mw.x; mhi = mw.y;
     }
-    float share = 0.0f, mx = -INFINITY;
+    float share = 0.0f, mx = -INFINITY, gT = 0.0f;
     if (a.mode == DPC_PROJ_MAX) {
-      for (int z = 0; z < Vz; ++z) mx = fmaxf(mx, vin[(size_t)z * V * V]);
+#pragma unroll 8
+      for (int z = 0; z < Vz; ++z) mx = fmaxf(mx, col[z * RW]);
       int cnt = 0;
-      for (int z = 0; z < Vz; ++z) cnt += (vin[(size_t)z * V * V] == mx) ? 1 : 0;
+#pragma unroll 8
+      for (int z = 0; z < Vz; ++z) cnt += (col[z * RW] == mx) ? 1 : 0;
       share = gp / (float)cnt;     // TF _MaxGrad: ties share the gradient equally
     } else if (a.mode != DPC_PROJ_NONE) {
-      // prefix products T_k = prod_{j<k} (1-u_j) into the tile
-      float T = 1.0f;
-#pragma unroll 8
-      for (int z = 0; z < Vz; ++z) {
-        const float v = vin[(size_t)z * V * V];
-        const float u = D.clampu ? fminf(fmaxf(v, D.lo), D.hi) : v;
-        col[z * RW] = T;
-        T = T - u * T;
+      float T0 = 1.0f, T1 = 1.0f, T2 = 1.0f, T3 = 1.0f;   // four partial products: shorter dependency chains
+#pragma unroll 4
+      for (int z = 0; z < Vz; z += 4) {
+        const float v0 = col[(z + 0) * RW], v1 = col[(z + 1) * RW], v2 = col[(z + 2) * RW], v3 = col[(z + 3) * RW];
+        T0 *= 1.0f - (D.clampu ? fminf(fmaxf(v0, D.lo), D.hi) : v0);
+        T1 *= 1.0f - (D.clampu ? fminf(fmaxf(v1, D.lo), D.hi) : v1);
+        T2 *= 1.0f - (D.clampu ? fminf(fmaxf(v2, D.lo), D.hi) : v2);
+        T3 *= 1.0f - (D.clampu ? fminf(fmaxf(v3, D.lo), D.hi) : v3);
       }
+      gT = gp * ((T0 * T1) * (T2 * T3));
     }
-    // reverse sweep.  With only the silhouette gradient g:  dL/du_k = g T_k (c_k - 1 + R_k),
-    // R_k = prod_{j>k} (1-u_j)  (for k > 0 that is g * prod_{j != k} (1-u_j)).
-    float R = 1.0f;
 #pragma unroll 8
-    for (int z = Vz - 1; z >= 0; --z) {
-      const float v = vin[(size_t)z * V * V];      // second read of the column: L1/L2 hit
+    for (int z = 0; z < Vz; ++z) {
+      const float v = col[z * RW];
       float dv = 0.0f;
       if (a.mode == DPC_PROJ_MAX) {
         dv = (v == mx) ? share : 0.0f;
       } else if (a.mode != DPC_PROJ_NONE) {
         const float u = D.clampu ? fminf(fmaxf(v, D.lo), D.hi) : v;
-        const float ck = (z == 0) ? (D.c0 - 1.0f) : 0.0f;
-        dv = gp * col[z * RW] * (ck + R);
-        R = R - u * R;
-        if (D.clampu && !(v >= D.lo && v <= D.hi)) dv = 0.0f;   // clip_by_value passes lo <= v <= hi
+        dv = __fdividef(gT, 1.0f - u);
+        if (z == 0) dv += gp * (D.c0 - 1.0f);
+        if (u != v) dv = 0.0f;                       // clip_by_value passes lo <= v <= hi only
       }
       if (gv) dv += gv[(size_t)z * V * V];
       if (has_s) {
@@ -336,9 +380,6 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
   {
     const int w = tid >> 5, xp = tid & 31;
     const int ty = w >> 1, h = w & 1, y = y0 + ty;
-    float2 tt[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) tt[j] = dpc_f2(tz[j], tz[j]);
     const float* col = tile + ty * V + 2 * xp;
     float* dout = a.d_in + ((size_t)b * Vz * V + y) * V + 2 * xp;
 #pragma unroll 1
@@ -347,7 +388,7 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
       float2 acc[8];
 #pragma unroll
       for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      dpc_col_conv_pairs<K, 8>(col, RW, zc, Vz, tt, acc);
+      dpc_col_conv_pairs<K, 8>(col, RW, zc, Vz, tzd, acc);
 #pragma unroll
       for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(dout + (size_t)(zc + o) * V * V) = acc[o];
     }
@@ -365,6 +406,8 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
+static int dpc_xy_grid_cap = 0;   // experiment/test knob (dpc_debug_set key 2); 0 = default
+
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
 
 static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, int ply) {
@@ -373,13 +416,22 @@ static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, in
 
 static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const float* taps_x, const float* taps_y, int K,
                                           int B, int Vz, int V, int clip_in, uint32_t* mask_out, const uint32_t* mask_in,
-                                          void* stream) {
+                                          int rev, float* zero_ptr, void* stream) {
   (void)V;
   if ((((uintptr_t)in) & 15u) || (((uintptr_t)out) & 7u)) return DPC_ERR_ARG;
   DpcConvXY64Args a;
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
-  if (K == 21) { DPC_LAUNCH(dpc_conv_xy64_kernel<21>, dim3(B * Vz), dim3(256), 0, stream, a); }
-  else { DPC_LAUNCH(dpc_conv_xy64_kernel<11>, dim3(B * Vz), dim3(256), 0, stream, a); }
+  a.nslices = B * Vz; a.rev = rev; a.zero_ptr = zero_ptr;
+  const int cap = dpc_xy_grid_cap > 0 ? dpc_xy_grid_cap : 3 * 148;   // 3 resident CTAs on each of the 148 SMs
+  const int grid = a.nslices < cap ? a.nslices : cap;
+#ifndef DPC_EMU
+  cudaError_t e = (K == 21)
+      ? cudaFuncSetAttribute(dpc_conv_xy64_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XY_SMEM_BYTES)
+      : cudaFuncSetAttribute(dpc_conv_xy64_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XY_SMEM_BYTES);
+  if (e != cudaSuccess) return DPC_ERR_CUDA;
+#endif
+  if (K == 21) { DPC_LAUNCH(dpc_conv_xy64_kernel<21>, dim3(grid), dim3(256), DPC_XY_SMEM_BYTES, stream, a); }
+  else { DPC_LAUNCH(dpc_conv_xy64_kernel<11>, dim3(grid), dim3(256), DPC_XY_SMEM_BYTES, stream, a); }
   return DPC_OK;
 }
 
@@ -393,7 +445,7 @@ static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_
                                              float* vox_out, uint32_t* mask2_out, float* proj, float* probs, float* depth,
                                              void* stream) {
   DpcConvZArgs a;
-  a.in = in; a.taps = taps_z; a.K = Kz; a.pl = (Kz - 1) / 2; a.scale = scale; a.mode = mode; a.eps = eps;
+  a.in = in; a.taps = taps_z; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = eps;
   a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = probs; a.depth = depth;
   const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
@@ -413,9 +465,9 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
                                              const float* taps_rev, int Kz, int mode, float eps, float cam_dist,
                                              float max_depth, int flip_y, int B, int Vz, int V, const float* g_proj,
                                              const float* g_vox, const float* g_probs, const float* g_depth, float* d_in,
-                                             float* d_scale, void* stream) {
+                                             float* d_scale, int rev, void* stream) {
   DpcConvZBwdArgs a;
-  a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps_rev; a.K = Kz; a.pl = (Kz - 1) / 2;
+  a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps_rev; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = rev;
   a.mode = mode; a.eps = eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
   a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;
   a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;

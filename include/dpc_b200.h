@@ -53,8 +53,12 @@ int dpc_abi_version(void);
 const char* dpc_error_string(int code);
 int dpc_last_cuda_error(void);
 /* Experiment knob for benchmark sweeps (key 0/1: points per thread of the splat forward/backward
- * kernels, 1|2|4).  Process-wide, not thread-safe, not needed in normal use. */
+ * kernels, 1|2|4; key 2: cap on the persistent grid of the 64^3 xy-smoothing kernel, 0 = default).
+ * Process-wide, not thread-safe, not needed in normal use. */
 int dpc_debug_set(int key, int value);
+/* key 3 = 1: record CUDA events around every stage of the fused forward/backward; this returns the
+ * six stage durations (ms) of the last instrumented step (synchronises on the last event). */
+int dpc_debug_stage_ms(float* out6);
 /* compiled for sm_100a?  1 = real CUDA build, 0 = the CPU emulation build used by tests/emu */
 int dpc_is_cuda_build(void);
 
@@ -120,24 +124,35 @@ int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
                    float* d_in, float* d_scale, void* stream);
 
 /* ---- the fused pipeline of pointcloud_project_fast (no rgb) -------------------------------
- * Workspace (device, caller-owned, 16-byte aligned): dpc_project_fast_workspace_bytes().
- * Forward keeps in the workspace what the backward needs (clip masks); pass the SAME workspace,
- * untouched, to the backward.  taps: fp32 device arrays (NULL taps with K = 0 mean "no kernel"). */
+ * Two caller-owned device buffers (16-byte aligned):
+ *   scratch (dpc_project_fast_scratch_bytes): raw grid + one intermediate grid.  Carries NO state
+ *     between calls and may be shared by any number of forward/backward calls on one stream.  If
+ *     DPC_FLAG_SCRATCH_RAW_ZERO is set the caller guarantees the first half (the raw grid) is
+ *     all-zero on entry and the forward skips its memset; every forward leaves it all-zero again
+ *     (the smoothing pass zeroes each slice as it consumes it) and the backward never writes it.
+ *   saved (dpc_project_fast_saved_bytes): the two clip masks as bit planes; written by the forward,
+ *     read by the backward of the same call -- keep it until then.
+ * taps: fp32 device arrays of K / Kz taps (K = Kz = 0: no smoothing kernel, taps ignored); the
+ * backward takes the SAME taps (it reads them back to front). */
+#define DPC_FLAG_SCRATCH_RAW_ZERO 1
+
 typedef struct {
   int B, N, Vz, V;
   int pose_kind;        /* DPC_POSE_* */
   int mode;             /* DPC_PROJ_DRC | DPC_PROJ_MAX | DPC_PROJ_DRC_PROD */
   int K, Kz;            /* tap counts along x/y and along depth; 0 = no smoothing */
   float focal_const, cam_dist, clip_eps, max_depth;
+  int flags;            /* DPC_FLAG_* */
 } dpc_project_params;
 
-int64_t dpc_project_fast_workspace_bytes(const dpc_project_params* p);
+int64_t dpc_project_fast_scratch_bytes(const dpc_project_params* p);
+int64_t dpc_project_fast_saved_bytes(const dpc_project_params* p);
 
 int dpc_project_fast_fwd(const dpc_project_params* p,
                          const float* pc, const float* pose, const float* trans, const float* focal,
                          const float* scale, const float* taps_xy, const float* taps_z,
                          float* tr_pc, float* voxels, float* proj, float* drc_probs, float* proj_depth,
-                         void* workspace, int64_t workspace_bytes, void* stream);
+                         void* scratch, int64_t scratch_bytes, void* saved, int64_t saved_bytes, void* stream);
 
 int dpc_project_fast_bwd(const dpc_project_params* p,
                          const float* pc, const float* pose, const float* trans, const float* focal,
@@ -146,7 +161,7 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                          const float* g_proj, const float* g_voxels, const float* g_tr_pc,
                          const float* g_probs, const float* g_depth,
                          float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_scale,
-                         void* workspace, int64_t workspace_bytes, void* stream);
+                         void* scratch, int64_t scratch_bytes, const void* saved, int64_t saved_bytes, void* stream);
 
 /* ---- f-2: point dropout gather (point_cloud.py:312-318): out[b,i,:] = in[b, sel[b,i], :] and its
  * backward (scatter-add).  sel int64 [B,n_keep]. */

@@ -55,6 +55,12 @@ unsigned char* dyn_smem();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 uint32_t exchange(uint32_t v, int src);          // value of lane `src`
 void gather(uint32_t v, uint32_t* all32);         // all lanes' values
+// mbarrier model: the word counts completed phases; wait(parity P) passes once the phase of
+// parity P has completed, i.e. while (count & 1) == P it blocks.
+static inline void mbar_complete(uint64_t* bar) { std::atomic_ref<uint64_t>(*bar).fetch_add(1, std::memory_order_release); }
+static inline void mbar_wait(uint64_t* bar, unsigned parity) {
+  while ((std::atomic_ref<uint64_t>(*bar).load(std::memory_order_acquire) & 1u) == parity) std::this_thread::yield();
+}
 }  // namespace dpc_emu
 
 #define threadIdx dpc_emu::t_threadIdx
@@ -110,5 +116,6 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __fdividef(float a, float b) { return a / b; }
 using std::max;
 using std::min;

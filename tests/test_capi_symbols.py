@@ -43,9 +43,10 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.dpc_splat_fwd(None, None, 0, None, None, 1.0, 2.0, None, 1, 1, 8, 8, None, None, None, None, None, None) == -1
     p = _capi.ProjectParams(B=1, N=10, Vz=200, V=64, pose_kind=0, mode=0, K=21, Kz=21)
     import ctypes
-    assert lib.dpc_project_fast_workspace_bytes(ctypes.byref(p)) == -1
+    assert lib.dpc_project_fast_scratch_bytes(ctypes.byref(p)) == -1
     p.Vz = 64
-    assert lib.dpc_project_fast_workspace_bytes(ctypes.byref(p)) > 2 * 64 ** 3 * 4
+    assert lib.dpc_project_fast_scratch_bytes(ctypes.byref(p)) == 2 * 64 ** 3 * 4
+    assert lib.dpc_project_fast_saved_bytes(ctypes.byref(p)) >= 2 * 64 ** 3 // 8
 
 
 def test_product_refuses_cpu_tensors():

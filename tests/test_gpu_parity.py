@@ -238,4 +238,4 @@ def test_error_conventions():
     p = _capi.ProjectParams(B=1, N=4, Vz=16, V=16, pose_kind=0, mode=0, K=0, Kz=0, focal_const=1.875,
                             cam_dist=2.0, clip_eps=1e-5, max_depth=10.0)
     assert L.dpc_project_fast_fwd(ctypes.byref(p), None, None, None, None, None, None, None, None, None, None, None,
-                                  None, None, 0, None) == -1
+                                  None, None, 0, None, 0, None) == -1
