@@ -241,9 +241,13 @@ class Pipeline:
         out = pcm.pointcloud_project_fast(self.cfg, pc, q, None, None, self.kernel, sc)
         loss = ((gt - out["proj"]) ** 2).sum() / 2 / B
         loss.backward()
-        res = [loss.detach(), out["proj"].detach(), pc.grad, q.grad, sc.grad]
-        host = [t.to("cpu", non_blocking=True) for t in res]
+        res = [loss.detach().reshape(1), out["proj"].detach(), pc.grad, q.grad, sc.grad]
+        if not hasattr(self, "host_out"):
+            self.host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
+        for h, t in zip(self.host_out, res):
+            h.copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        host = self.host_out
         h2d = sum(t.numel() * t.element_size() for t in (hp, hq, hs, hg))
         d2h = sum(t.numel() * t.element_size() for t in res)
         return float(host[0]), h2d, d2h
