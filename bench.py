@@ -181,7 +181,7 @@ class Pipeline:
         self.p = _capi.ProjectParams(B=B, N=N, Vz=V, V=V, pose_kind=_capi.POSE_QUAT, mode=_capi.PROJ_DRC, K=K, Kz=K,
                                      focal_const=float(self.cfg.focal_length), cam_dist=float(self.cfg.camera_distance),
                                      clip_eps=float(self.cfg.drc_logsum_clip_val), max_depth=float(self.cfg.max_depth))
-        self.p.flags = _capi.FLAG_SCRATCH_RAW_ZERO      # scratch is zeroed once, the kernels keep it clean
+        self.p.flags = 0
         self.scratch_bytes = self.L.dpc_project_fast_scratch_bytes(ctypes.byref(self.p))
         self.saved_bytes = self.L.dpc_project_fast_saved_bytes(ctypes.byref(self.p))
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731

@@ -61,7 +61,6 @@ int dpc_debug_stage_ms(float* out6) {
 int dpc_debug_set(int key, int value) {
   if (key < 0 || key >= 4) return DPC_ERR_ARG;
   g_tune[key] = value;
-  if (key == 2) dpc_xy_grid_cap = value;
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
@@ -332,9 +331,13 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   DPC_TRY(dpc_splat_fwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
                         p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, stream));
   stage_mark(1, stream);
-  // clip + x/y smoothing; the pass also returns the raw grid to all-zero (next splat target)
+  // clip + x/y smoothing.  With DPC_FLAG_SCRATCH_RAW_ZERO the pass also hands the raw grid back
+  // all-zero (so the next forward needs no memset).  Measured on B200 (profiles/r01_d): not a win --
+  // the memset doubles as an L2 warm-up for the splat's reductions, which otherwise miss to HBM --
+  // so the default path keeps the memset and leaves the flag to callers that want it.
   DPC_TRY(launch_conv_xy(w.raw, w.tmp, tx, K, (K - 1) / 2, tx, K, (K - 1) / 2,
-                         p->B, p->Vz, p->V, /*clip_in=*/1, sv.mask1, nullptr, /*rev=*/0, /*zero_in=*/1, stream));
+                         p->B, p->Vz, p->V, /*clip_in=*/1, sv.mask1, nullptr, /*rev=*/0,
+                         /*zero_in=*/(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) ? 1 : 0, stream));
   stage_mark(2, stream);
   const bool want_probs = (p->mode != DPC_PROJ_MAX);
   DPC_TRY(launch_conv_z_fwd(w.tmp, tz, Kz, (Kz - 1) / 2, scale, p->mode, p->clip_eps, p->cam_dist,

@@ -37,18 +37,125 @@ DPC_DEV void dpc_col_conv_pairs(const float* base, int stride, int r0, int nrows
 }
 
 // ------------------------------------------------------------------------------ conv_xy, V = 64
-// Persistent CTAs (3 per SM) walk the depth slices round-robin.  The next slice is prefetched by
-// the TMA engine (64 bulk copies of one 256-byte row each, into a padded smem image) while the
-// current one is being correlated, so no warp ever waits on a global load in steady state; the
-// clip to [0,1] and the clip-pass bits are computed when the x pass reads its window.
+// One CTA per depth slice (2048 CTAs at B=32, three resident per SM, so the load phase of one
+// overlaps the arithmetic of the others).  A persistent, TMA-prefetching variant was measured and
+// was SLOWER (barrier stalls; profiles/r01_d_*), so the plain form stays.
 struct DpcConvXY64Args {
   const float* in; float* out; const float* taps_x; const float* taps_y;
   int clip_in; uint32_t* mask_out; const uint32_t* mask_in; int nslices;
   int rev; float* zero_ptr;
 };
 
-#define DPC_XY_SMEM_FLOATS (3 * DPC_F64_V * DPC_F64_S)          // A[2] + M
-#define DPC_XY_SMEM_BYTES (DPC_XY_SMEM_FLOATS * 4 + 512)
+template <int K>
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(256, 3)
+#else
+static void
+#endif
+dpc_conv_xy64_kernel(DpcConvXY64Args a) {
+  constexpr int V = DPC_F64_V, S = DPC_F64_S, PL = (K - 1) / 2;
+  constexpr int WL = ((PL + 3) / 4) * 4;            // window starts WL floats left of the first output
+  constexpr int NW4 = (WL + 16 + WL) / 4;           // float4 groups in the x window
+  static_assert((K & 1) == 1 && K <= 21, "odd K <= 21");
+  __shared__ __align__(16) float A[V * S];
+  __shared__ __align__(16) float M[V * S];
+  __shared__ __align__(8) float txe[24];            // E[i] = t[i-1], i = 0..K+1 (zero outside)
+  __shared__ __align__(8) float txo[24];            // O[i] = E[i+1]
+  __shared__ __align__(8) float2 tyd[24];           // y taps, each duplicated into a float2 (FFMA2 operand)
+  const int tid = threadIdx.x;
+  const size_t slice = (size_t)blockIdx.x * (V * V);
+  if (tid < 24) {
+    const int a_e = tid - 1, a_o = tid;              // tap indices behind E[tid], O[tid]
+    txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
+    txo[tid] = (a_o >= 0 && a_o < K) ? dpc_tap(a.taps_x, K, a_o, a.rev) : 0.0f;
+    const float tyv = (tid < K) ? dpc_tap(a.taps_y, K, tid, a.rev) : 0.0f;
+    tyd[tid] = dpc_f2(tyv, tyv);
+  }
+
+  // ---- phase 0: slice -> smem (float4, coalesced), clip, clip-mask bits
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.in + slice);
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = src[tid + 256 * k];        // all four loads in flight
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = tid + 256 * k;            // float4 index in the slice: row = i/16, col4 = i%16
+      if (a.mask_out) {
+        unsigned nib = ((v[k].x >= 0.0f && v[k].x <= 1.0f) ? 1u : 0u) | ((v[k].y >= 0.0f && v[k].y <= 1.0f) ? 2u : 0u) |
+                       ((v[k].z >= 0.0f && v[k].z <= 1.0f) ? 4u : 0u) | ((v[k].w >= 0.0f && v[k].w <= 1.0f) ? 8u : 0u);
+        unsigned word = nib << (4 * (tid & 7));
+        word |= __shfl_xor_sync(DPC_FULL, word, 1);
+        word |= __shfl_xor_sync(DPC_FULL, word, 2);
+        word |= __shfl_xor_sync(DPC_FULL, word, 4);
+        if ((tid & 7) == 0) a.mask_out[(slice >> 5) + (i >> 3)] = word;
+      }
+      if (a.clip_in) { v[k].x = dpc_clip01(v[k].x); v[k].y = dpc_clip01(v[k].y); v[k].z = dpc_clip01(v[k].z); v[k].w = dpc_clip01(v[k].w); }
+      *reinterpret_cast<float4*>(&A[(i >> 4) * S + (i & 15) * 4]) = v[k];
+      if (a.zero_ptr) reinterpret_cast<float4*>(a.zero_ptr + slice)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: x correlation.  Thread = (row y, run r of 16 outputs); a warp = 32 rows, one r.
+  {
+    const int y = tid & 63, r = tid >> 6;
+    const int x0 = r * 16;
+    // tap pairs (t[a], t[a+1]), a = -1..K-1, index q = a+1: aligned float2 in E for even q, in O for odd q
+    float2 tp[K + 1];
+#pragma unroll
+    for (int q = 0; q < K + 1; ++q)
+      tp[q] = (q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1)) : *reinterpret_cast<const float2*>(txe + q);
+    float2 acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+    const float* rowp = A + y * S;
+#pragma unroll
+    for (int g = 0; g < NW4; ++g) {
+      const int xs = x0 - WL + 4 * g;       // warp-uniform: whole float4 in or out of the row
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (xs >= 0 && xs < V) w4 = *reinterpret_cast<const float4*>(rowp + xs);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 w = h ? dpc_f2(w4.z, w4.w) : dpc_f2(w4.x, w4.y);
+        // window pair index i = 4g + 2h; for output o the first tap of the pair is a = i - o - WL + PL
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1)
+            acc[o] = dpc_ffma2(w, tp[4 * g + 2 * h - o - WL + PL + 1], acc[o]);
+        }
+      }
+    }
+    float* dst = M + y * S + x0;
+#pragma unroll
+    for (int o = 0; o < 16; o += 4) {
+      *reinterpret_cast<float4*>(dst + o) = make_float4(acc[o].x + acc[o].y, acc[o + 1].x + acc[o + 1].y,
+                                                         acc[o + 2].x + acc[o + 2].y, acc[o + 3].x + acc[o + 3].y);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: y correlation.  Thread = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
+  {
+    const int xp = tid & 31, y0 = (tid >> 5) * 8;
+    float2 acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+    dpc_col_conv_pairs<K, 8>(M + 2 * xp, S, y0, V, tyd, acc);
+    float* dst = a.out + slice + (size_t)y0 * V + 2 * xp;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float2 v = acc[o];
+      if (a.mask_in) {
+        const size_t e = slice + (size_t)(y0 + o) * V + 2 * xp;
+        const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
+        if (!(wbits & 1u)) v.x = 0.0f;
+        if (!(wbits & 2u)) v.y = 0.0f;
+      }
+      *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
+    }
+  }
+}
 
 // Rows of `nrows` x `row_bytes` from global (row pitch src_pitch floats) into smem (row pitch
 // dst_pitch floats) through the TMA engine, completion on `bar`.  Called by ALL lanes of warp 0:
@@ -71,128 +178,6 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
   __syncwarp();
   if (lane == 0) dpc_emu::mbar_complete(bar);
 #endif
-}
-
-template <int K>
-#ifndef DPC_EMU
-__global__ void __launch_bounds__(256, 3)
-#else
-static void
-#endif
-dpc_conv_xy64_kernel(DpcConvXY64Args a) {
-  constexpr int V = DPC_F64_V, S = DPC_F64_S, PL = (K - 1) / 2;
-  constexpr int WL = ((PL + 3) / 4) * 4;            // window starts WL floats left of the first output
-  constexpr int NW4 = (WL + 16 + WL) / 4;           // float4 groups in the x window
-  static_assert((K & 1) == 1 && K <= 21, "odd K <= 21");
-  DPC_DYN_SMEM(float, sm);
-  float* Abuf = sm;                                  // [2][V*S]
-  float* M = sm + 2 * V * S;                         // [V*S]
-  float* txe = sm + 3 * V * S;                       // E[i] = t[i-1], i = 0..K+1 (zero outside), padded to 24
-  float* txo = txe + 24;                             // O[i] = E[i+1]
-  float2* tyd = reinterpret_cast<float2*>(txo + 24);  // y taps, each duplicated into a float2 (FFMA2 operand)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(txo + 24 + 48);   // 2 mbarriers (8-byte aligned offset)
-  const int tid = threadIdx.x;
-  if (tid < 24) {
-    const int a_e = tid - 1, a_o = tid;              // tap indices behind E[tid], O[tid]
-    txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
-    txo[tid] = (a_o >= 0 && a_o < K) ? dpc_tap(a.taps_x, K, a_o, a.rev) : 0.0f;
-    const float tyv = (tid < K) ? dpc_tap(a.taps_y, K, tid, a.rev) : 0.0f;
-    tyd[tid] = dpc_f2(tyv, tyv);
-  }
-  if (tid == 0) { dpc_mbar_init(&bars[0], 1); dpc_mbar_init(&bars[1], 1); }
-  __syncthreads();
-  int slice = blockIdx.x;
-  if (slice >= a.nslices) return;
-  if (tid < 32) dpc_warp_bulk_rows(Abuf, S, a.in + (size_t)slice * (V * V), V, V, V * 4, &bars[0]);
-
-  for (int it = 0; slice < a.nslices; ++it, slice += gridDim.x) {
-    const int cb = it & 1;
-    float* A = Abuf + cb * (V * S);
-    const int next = slice + gridDim.x;
-    // the other buffer was last read by the x pass of the previous iteration, which every thread
-    // left before the barrier that follows it
-    if (tid < 32 && next < a.nslices)
-      dpc_warp_bulk_rows(Abuf + (cb ^ 1) * (V * S), S, a.in + (size_t)next * (V * V), V, V, V * 4, &bars[cb ^ 1]);
-    dpc_mbar_wait(&bars[cb], (it >> 1) & 1);
-    const size_t sl = (size_t)slice * (V * V);
-    if (a.zero_ptr) {   // the slice lives in smem now: hand the global copy back all-zero (next forward's splat target)
-      float4* zp = reinterpret_cast<float4*>(a.zero_ptr + sl);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) zp[tid + 256 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    // ---- x correlation.  Thread = (row y, run r of 16 outputs); a warp = 32 rows, one r.
-    {
-      const int y = tid & 63, r = tid >> 6;
-      const int x0 = r * 16;
-      float2 acc[16];
-#pragma unroll
-      for (int o = 0; o < 16; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      const float* rowp = A + y * S;
-      unsigned mbits = 0u;
-#pragma unroll
-      for (int g = 0; g < NW4; ++g) {
-        const int xs = x0 - WL + 4 * g;       // warp-uniform: whole float4 in or out of the row
-        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xs >= 0 && xs < V) w4 = *reinterpret_cast<const float4*>(rowp + xs);
-        if (a.clip_in) {
-          if (g >= WL / 4 && g < WL / 4 + 4) {   // the thread's own 16 voxels: clip-pass bits
-            const int sh = 4 * (g - WL / 4);
-            mbits |= ((w4.x >= 0.0f && w4.x <= 1.0f) ? 1u : 0u) << sh;
-            mbits |= ((w4.y >= 0.0f && w4.y <= 1.0f) ? 2u : 0u) << sh;
-            mbits |= ((w4.z >= 0.0f && w4.z <= 1.0f) ? 4u : 0u) << sh;
-            mbits |= ((w4.w >= 0.0f && w4.w <= 1.0f) ? 8u : 0u) << sh;
-          }
-          w4.x = dpc_clip01(w4.x); w4.y = dpc_clip01(w4.y); w4.z = dpc_clip01(w4.z); w4.w = dpc_clip01(w4.w);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 w = h ? dpc_f2(w4.z, w4.w) : dpc_f2(w4.x, w4.y);
-          // window pair index i = 4g + 2h; for output o the first tap of the pair is a = i - o - WL + PL,
-          // the tap pair (t[a], t[a+1]) = (E[a+1], E[a+2]): aligned in E for odd a, in O for even a
-#pragma unroll
-          for (int o = 0; o < 16; ++o) {
-            if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1) {
-              const int q = 4 * g + 2 * h - o - WL + PL + 1;   // 0..K
-              const float2 tp = (q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1))
-                                        : *reinterpret_cast<const float2*>(txe + q);
-              acc[o] = dpc_ffma2(w, tp, acc[o]);
-            }
-          }
-        }
-      }
-      if (a.mask_out) reinterpret_cast<uint16_t*>(a.mask_out)[(sl + (size_t)y * V + x0) >> 4] = (uint16_t)mbits;
-      float* dst = M + y * S + x0;
-#pragma unroll
-      for (int o = 0; o < 16; o += 4) {
-        *reinterpret_cast<float4*>(dst + o) = make_float4(acc[o].x + acc[o].y, acc[o + 1].x + acc[o + 1].y,
-                                                           acc[o + 2].x + acc[o + 2].y, acc[o + 3].x + acc[o + 3].y);
-      }
-    }
-    __syncthreads();
-
-    // ---- y correlation.  Thread = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
-    {
-      const int xp = tid & 31, y0 = (tid >> 5) * 8;
-      float2 acc[8];
-#pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      dpc_col_conv_pairs<K, 8>(M + 2 * xp, S, y0, V, tyd, acc);
-      float* dst = a.out + sl + (size_t)y0 * V + 2 * xp;
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        float2 v = acc[o];
-        if (a.mask_in) {
-          const size_t e = sl + (size_t)(y0 + o) * V + 2 * xp;
-          const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
-          if (!(wbits & 1u)) v.x = 0.0f;
-          if (!(wbits & 2u)) v.y = 0.0f;
-        }
-        *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
-      }
-    }
-    __syncthreads();   // M is free for the next slice
-  }
 }
 
 // ------------------------------------------------------------------------------ conv_z, V = Vz = 64
@@ -292,9 +277,11 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
   }
 }
 
-template <int K>
+// LEAN = the training configuration (DRC projection, occupancy scale present, no gradient arriving
+// directly at `voxels`): phase 1 is compiled without any of the per-level mode / option tests.
+template <int K, bool LEAN>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(DPC_ZF_THREADS)
+__global__ void __launch_bounds__(DPC_ZF_THREADS, 3)
 #else
 static void
 #endif
@@ -322,7 +309,40 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
   // g * (c_0 - 1 + T_Z / (1-u_0)) for k = 0, T_Z = prod_j (1-u_j).  1-u >= eps (the clip), and where
   // T_Z underflows the true value is below 1e-35, so the quotient form is exact to ~1e-7 relative
   // or negligible in absolute terms; no second scan, no carried state.
-  {
+  if (LEAN) {
+    const int ty = tid >> 6, x = tid & 63, y = y0 + ty;
+    const int yo = a.flip_y ? (V - 1 - y) : y;
+    float* col = tile + ty * V + x;
+    const float gp = a.g_proj[((size_t)b * V + yo) * V + x];
+    const uint2 mw = *reinterpret_cast<const uint2*>(a.mask2 + (((size_t)b * V + y) * V + x) * 2);
+    float T0 = 1.0f, T1 = 1.0f, T2 = 1.0f, T3 = 1.0f;   // four partial products: shorter dependency chains
+#pragma unroll 4
+    for (int z = 0; z < Vz; z += 4) {
+      T0 *= 1.0f - fminf(fmaxf(col[(z + 0) * RW], D.lo), D.hi);
+      T1 *= 1.0f - fminf(fmaxf(col[(z + 1) * RW], D.lo), D.hi);
+      T2 *= 1.0f - fminf(fmaxf(col[(z + 2) * RW], D.lo), D.hi);
+      T3 *= 1.0f - fminf(fmaxf(col[(z + 3) * RW], D.lo), D.hi);
+    }
+    const float gT = gp * ((T0 * T1) * (T2 * T3));
+    float dsv = 0.0f;    // sum of dv * voxel; the 1/scale factor is applied once at the end
+#pragma unroll
+    for (int hw = 0; hw < 2; ++hw) {
+      uint32_t wbits = hw ? mw.y : mw.x;
+#pragma unroll 8
+      for (int zz = 0; zz < 32; ++zz) {
+        const int z = hw * 32 + zz;
+        const float v = col[z * RW];
+        const float u = fminf(fmaxf(v, D.lo), D.hi);
+        float dv = __fdividef(gT, 1.0f - u);
+        if (z == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
+        if ((u != v) || !(wbits & 1u)) dv = 0.0f;
+        wbits >>= 1;
+        dsv = fmaf(dv, v, dsv);
+        col[z * RW] = dv * s;
+      }
+    }
+    ds = dsv * inv_s;
+  } else {
     const int ty = tid >> 6, x = tid & 63, y = y0 + ty;
     const int yo = a.flip_y ? (V - 1 - y) : y;
     const float* gv = a.g_vox ? a.g_vox + ((size_t)b * Vz * V + y) * V + x : nullptr;
@@ -406,8 +426,6 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
-static int dpc_xy_grid_cap = 0;   // experiment/test knob (dpc_debug_set key 2); 0 = default
-
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
 
 static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, int ply) {
@@ -422,16 +440,8 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   DpcConvXY64Args a;
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
   a.nslices = B * Vz; a.rev = rev; a.zero_ptr = zero_ptr;
-  const int cap = dpc_xy_grid_cap > 0 ? dpc_xy_grid_cap : 3 * 148;   // 3 resident CTAs on each of the 148 SMs
-  const int grid = a.nslices < cap ? a.nslices : cap;
-#ifndef DPC_EMU
-  cudaError_t e = (K == 21)
-      ? cudaFuncSetAttribute(dpc_conv_xy64_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XY_SMEM_BYTES)
-      : cudaFuncSetAttribute(dpc_conv_xy64_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XY_SMEM_BYTES);
-  if (e != cudaSuccess) return DPC_ERR_CUDA;
-#endif
-  if (K == 21) { DPC_LAUNCH(dpc_conv_xy64_kernel<21>, dim3(grid), dim3(256), DPC_XY_SMEM_BYTES, stream, a); }
-  else { DPC_LAUNCH(dpc_conv_xy64_kernel<11>, dim3(grid), dim3(256), DPC_XY_SMEM_BYTES, stream, a); }
+  if (K == 21) { DPC_LAUNCH(dpc_conv_xy64_kernel<21>, dim3(a.nslices), dim3(256), 0, stream, a); }
+  else { DPC_LAUNCH(dpc_conv_xy64_kernel<11>, dim3(a.nslices), dim3(256), 0, stream, a); }
   return DPC_OK;
 }
 
@@ -473,13 +483,16 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
   a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;
   const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
   dim3 grid(V / DPC_ZF_TY, B), block(DPC_ZF_THREADS);
+  const bool lean = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
 #ifndef DPC_EMU
-  cudaError_t e = (Kz == 21)
-      ? cudaFuncSetAttribute(dpc_conv_z64_bwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-      : cudaFuncSetAttribute(dpc_conv_z64_bwd_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return DPC_ERR_CUDA;
+#define DPC_ZB_LAUNCH(KK, LL) do { \
+    if (cudaFuncSetAttribute(dpc_conv_z64_bwd_kernel<KK, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DPC_ERR_CUDA; \
+    DPC_LAUNCH((dpc_conv_z64_bwd_kernel<KK, LL>), grid, block, smem, stream, a); } while (0)
+#else
+#define DPC_ZB_LAUNCH(KK, LL) do { DPC_LAUNCH((dpc_conv_z64_bwd_kernel<KK, LL>), grid, block, smem, stream, a); } while (0)
 #endif
-  if (Kz == 21) { DPC_LAUNCH(dpc_conv_z64_bwd_kernel<21>, grid, block, smem, stream, a); }
-  else { DPC_LAUNCH(dpc_conv_z64_bwd_kernel<11>, grid, block, smem, stream, a); }
+  if (Kz == 21) { if (lean) DPC_ZB_LAUNCH(21, true); else DPC_ZB_LAUNCH(21, false); }
+  else { if (lean) DPC_ZB_LAUNCH(11, true); else DPC_ZB_LAUNCH(11, false); }
+#undef DPC_ZB_LAUNCH
   return DPC_OK;
 }

@@ -273,9 +273,8 @@ class _ProjectFn(torch.autograd.Function):
 
 # --------------------------------------------------------------------------- the fused pipeline
 # Scratch grids of the fused path (raw + one intermediate, 2 x B*Vz*V*V*4 bytes) carry no state
-# between calls, so one buffer per (device, stream, size) is kept and reused: the kernels hand the
-# raw half back all-zero after every forward, which saves the 32 MiB memset per step at the
-# benchmark shape.  Stream-ordered reuse is safe; a different stream gets its own buffer.
+# between calls, so one buffer per (device, stream, size) is kept and reused instead of being
+# allocated per call.  Stream-ordered reuse is safe; a different stream gets its own buffer.
 _SCRATCH = {}
 
 
@@ -285,7 +284,7 @@ def _scratch_for(device, stream, nbytes):
     if buf is None:
         if len(_SCRATCH) >= 8:
             _SCRATCH.clear()
-        buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
     return key, buf
 
@@ -314,7 +313,7 @@ class _ProjectFastFn(torch.autograd.Function):
                              % (b, n, vz, v, params.K))
         stream = stream_of(pc)
         key, scratch = _scratch_for(dev, stream, scratch_bytes)
-        params.flags = _capi.FLAG_SCRATCH_RAW_ZERO
+        params.flags = 0   # the forward zeroes the raw grid itself (the memset also warms L2 for the splat)
         saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
         tr_pc = torch.empty_like(pc)
         voxels = torch.empty(b, vz, v, v, dtype=torch.float32, device=dev)
@@ -327,7 +326,7 @@ class _ProjectFastFn(torch.autograd.Function):
                                          ptr(taps_xy), ptr(taps_z), ptr(tr_pc), ptr(voxels), ptr(proj), None,
                                          None, ptr(scratch), scratch_bytes, ptr(saved), saved_bytes, stream))
         except Exception:
-            _SCRATCH.pop(key, None)   # the all-zero invariant of the raw half can no longer be trusted
+            _SCRATCH.pop(key, None)
             raise
         ctx.save_for_backward(pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved)
         ctx.params = params

@@ -28,7 +28,7 @@ def run(n, v, steps=20):
     gt = (torch.rand(B, v, v, generator=g) > 0.5).float().to(dev)
     taps = gk.smoothing_kernel(cfg, torch.tensor(3.0, device=dev)).taps_xy
     p = _capi.ProjectParams(B=B, N=n, Vz=v, V=v, pose_kind=0, mode=0, K=K, Kz=K, focal_const=1.875, cam_dist=2.0,
-                            clip_eps=1e-5, max_depth=10.0, flags=_capi.FLAG_SCRATCH_RAW_ZERO)
+                            clip_eps=1e-5, max_depth=10.0, flags=0)
     sb, vb = L.dpc_project_fast_scratch_bytes(ctypes.byref(p)), L.dpc_project_fast_saved_bytes(ctypes.byref(p))
     scratch = torch.zeros(sb, dtype=torch.uint8, device=dev)
     saved = torch.empty(vb, dtype=torch.uint8, device=dev)

@@ -26,18 +26,6 @@ def test_emulated_kernels_match_golden(emu, name):  # noqa: F811
     cases.assert_parity(fx, outs, grads)
 
 
-def test_persistent_xy_kernel_loops_over_slices(emu):  # noqa: F811
-    """64 depth slices on 5 persistent CTAs: 13 iterations each through the double-buffered
-    TMA prefetch (mbarrier phase parity flips every second iteration)."""
-    emu.dpc_debug_set(2, 5)
-    try:
-        fx = cases.load_golden("v64_small")
-        outs, grads = cases.run_impl(Product, fx)
-        cases.assert_parity(fx, outs, grads)
-    finally:
-        emu.dpc_debug_set(2, 0)
-
-
 @pytest.mark.parametrize("ppt", [1, 2])
 def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
     emu.dpc_debug_set(0, ppt)
