@@ -1,0 +1,195 @@
+"""Model assembly and losses (reference: dpc/models/model_pc.py:130-445, dpc/util/losses.py:6-20,
+dpc/util/train.py:17-23) rebuilt in PyTorch: encoder -> point decoder (+ occupancy scale, pose
+ensemble) -> replicate per view / per pose candidate -> the B200 projection path -> losses.
+
+Everything here is library kernels (cuDNN/cuBLAS through torch) EXCEPT `compute_projection`, which
+calls the hand-written renderer through the reference-shaped API.  The renderer stays fp32; the
+CNN runs under bf16 autocast when the caller enables it (BASELINE config 3).
+"""
+import torch
+import torch.nn as nn
+
+from ..nets.img_encoder import ImgEncoder, _fc
+from ..nets.pc_decoder import PcDecoder, _trunc_fc
+from ..nets.pose_net import PoseNet
+from ..util import gauss_kernel, point_cloud
+from ..util.quaternion import quaternion_conjugate, quaternion_multiply, quaternion_normalise
+
+
+def tf_repeat_0(t, num):
+    """[a,b,..] -> [a,a,..,b,b,..] along axis 0 (model_pc.py:23-32)."""
+    return t.repeat_interleave(num, dim=0)
+
+
+def get_smooth_sigma(cfg, global_step):
+    """Linear schedule pc_relative_sigma -> pc_relative_sigma_end over training (model_pc.py:35-40)."""
+    diff = cfg.pc_relative_sigma_end - cfg.pc_relative_sigma
+    return float(cfg.pc_relative_sigma + global_step / cfg.max_number_of_steps * diff)
+
+
+def get_dropout_prob(cfg, global_step):
+    """Keep-probability schedule of the point dropout (model_pc.py:43-64), linear variant."""
+    if not cfg.pc_point_dropout_scheduled:
+        return float(cfg.pc_point_dropout)
+    start, end = cfg.pc_point_dropout, 1.0
+    k = (end - start) / (cfg.pc_point_dropout_end_step - cfg.pc_point_dropout_start_step)
+    b = start - k * cfg.pc_point_dropout_start_step
+    x = global_step / cfg.max_number_of_steps
+    if cfg.pc_point_dropout_exponential_schedule:
+        import math
+        keep = start * math.exp(math.log(end / start) * x)
+    else:
+        keep = k * x + b
+    return float(min(max(keep, start), end))
+
+
+def get_learning_rate(cfg, global_step):
+    return cfg.learning_rate if global_step < cfg.learning_rate_step * cfg.max_number_of_steps else cfg.learning_rate_2
+
+
+def pool_single_view(cfg, tensor, view_idx):
+    """Every step_size-th row starting at view_idx (model_base.py:7-18)."""
+    return tensor[view_idx::cfg.step_size]
+
+
+class ModelPointCloud(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.encoder = ImgEncoder(cfg)
+        self.decoder = PcDecoder(cfg)
+        self.scale_fc = _trunc_fc(cfg.z_dim, 1, 0.025) if cfg.pc_learn_occupancy_scaling else None
+        self.posenet = PoseNet(cfg) if cfg.predict_pose else None
+
+    # ------------------------------------------------------------------ prediction
+    def model_predict(self, images):
+        cfg = self.cfg
+        enc = self.encoder(images)
+        out = {"conv_features": enc["conv_features"], "ids": enc["ids"], "z_latent": enc["z_latent"]}
+        ids = enc["ids"]
+        if ids.shape[0] != cfg.batch_size:      # all views were encoded: keep the first view's identity
+            ids = pool_single_view(cfg, ids, 0)
+        out["ids_1"] = ids
+        dec = self.decoder(ids)
+        out["points_1"], out["rgb_1"] = dec["xyz"], dec["rgb"]
+        out["scaling_factor"] = (torch.sigmoid(self.scale_fc(ids)) * cfg.pc_occupancy_scaling_maximum
+                                 if self.scale_fc is not None else None)
+        out["focal_length"] = None
+        if self.posenet is not None:
+            out.update(self.posenet(enc["poses"]))
+        return out
+
+    def compute_projection(self, inputs, outputs, global_step, is_training=True):
+        """model_pc.py:220-259."""
+        cfg = self.cfg
+        all_points, all_rgb = outputs["all_points"], outputs["all_rgb"]
+        camera_pose = outputs["poses"] if cfg.predict_pose else (
+            inputs["camera_quaternion"] if cfg.pose_quaternion else inputs["matrices"])
+        if is_training and cfg.pc_point_dropout != 1:
+            keep = get_dropout_prob(cfg, global_step)
+            all_points, all_rgb = point_cloud.pc_point_dropout(all_points, all_rgb, keep)
+        sigma = torch.tensor(get_smooth_sigma(cfg, global_step), dtype=torch.float32, device=all_points.device)
+        kernel = gauss_kernel.smoothing_kernel(cfg, sigma)
+        trans = outputs.get("predicted_translation") if cfg.predict_translation else None
+        with torch.autocast(device_type=all_points.device.type, enabled=False):   # the renderer is fp32
+            proj_out = point_cloud.pointcloud_project_fast(
+                cfg, all_points.float(), camera_pose.float(), trans, all_rgb, kernel,
+                scaling_factor=None if outputs["all_scaling_factors"] is None else outputs["all_scaling_factors"].float(),
+                focal_length=outputs["all_focal_length"])
+        outputs["projs"] = proj_out["proj"]
+        outputs["projs_rgb"] = proj_out["proj_rgb"]
+        outputs["proj_out"] = proj_out      # drc_probs / proj_depth stay lazy until a loss asks for them
+        outputs["projs_1"] = proj_out["proj"][0:outputs["points_1"].shape[0]]
+        return outputs
+
+    def forward(self, inputs, global_step=0, is_training=True, run_projection=True):
+        """model_pc.py:266-306 (get_model_fn)."""
+        cfg = self.cfg
+        outputs = self.model_predict(inputs["images"] if cfg.predict_pose else inputs["images_1"])
+        if not run_projection:
+            return outputs
+        k = int(cfg.pose_predict_num_candidates)
+        all_points = tf_repeat_0(outputs["points_1"], cfg.step_size)
+        if k > 1:
+            all_points = tf_repeat_0(all_points, k)
+            if cfg.predict_translation:
+                outputs["predicted_translation"] = tf_repeat_0(outputs["predicted_translation"], k)
+        outputs["all_focal_length"] = None
+        outputs["all_points"] = all_points
+        sc = outputs["scaling_factor"]
+        if sc is not None:
+            sc = tf_repeat_0(sc, cfg.step_size)
+            if k > 1:
+                sc = tf_repeat_0(sc, k)
+        outputs["all_scaling_factors"] = sc
+        outputs["all_rgb"] = tf_repeat_0(outputs["rgb_1"], cfg.step_size) if cfg.pc_rgb else None
+        return self.compute_projection(inputs, outputs, global_step, is_training)
+
+    # ------------------------------------------------------------------ losses
+    def proj_loss_pose_candidates(self, gt, pred):
+        """min over pose candidates (model_pc.py:308-337) -> (loss, winning candidate per view)."""
+        k = int(self.cfg.pose_predict_num_candidates)
+        gt = tf_repeat_0(gt, k)
+        all_loss = ((gt - pred) ** 2).sum(dim=(1, 2, 3)).reshape(-1, k)
+        winner = all_loss.argmin(dim=1)
+        mask = torch.nn.functional.one_hot(winner, k).to(pred.dtype).reshape(-1, 1, 1, 1)
+        loss_tensor = (gt - pred) * mask
+        num_samples = winner.shape[0]
+        return (loss_tensor ** 2).sum() / 2 / num_samples, winner
+
+    def add_student_loss(self, outputs, winner):
+        """model_pc.py:339-381 (quaternion-angle variant)."""
+        cfg = self.cfg
+        k = int(cfg.pose_predict_num_candidates)
+        teachers = outputs["poses"].reshape(-1, k, 4)
+        teachers = teachers[torch.arange(teachers.shape[0], device=teachers.device), winner].detach()
+        q_diff = quaternion_normalise(quaternion_multiply(teachers, quaternion_conjugate(outputs["pose_student"])))
+        loss = (1.0 - q_diff[:, 0] ** 2).sum() / winner.shape[0]
+        return loss * cfg.pose_predictor_student_loss_weight
+
+    def add_proj_loss(self, inputs, outputs):
+        """model_pc.py:383-423.  TF1's bilinear resize without half-pixel centres is exact [::2,::2]
+        subsampling for 128 -> 64."""
+        cfg = self.cfg
+        gt, pred = inputs["masks"], outputs["projs"]
+        gs, ps = gt.shape[1], pred.shape[1]
+        assert gs >= ps, "GT size should not be higher than prediction size"
+        if gs > ps:
+            assert gs % ps == 0
+            gt = gt[:, ::gs // ps, ::gs // ps, :]
+        total = pred.new_zeros(())
+        if int(cfg.pose_predict_num_candidates) > 1:
+            proj_loss, winner = self.proj_loss_pose_candidates(gt, pred)
+            if cfg.pose_predictor_student:
+                total = total + self.add_student_loss(outputs, winner)
+        else:
+            proj_loss = ((gt - pred) ** 2).sum() / 2 / pred.shape[0]
+        return (total + proj_loss) * cfg.proj_weight
+
+    def get_loss(self, inputs, outputs):
+        """model_pc.py:425-445 (projection loss; drc / depth terms when their weights are non-zero)."""
+        cfg = self.cfg
+        loss = outputs["projs"].new_zeros(())
+        if cfg.proj_weight:
+            loss = loss + self.add_proj_loss(inputs, outputs)
+        if cfg.drc_weight:
+            gt = inputs["masks"]
+            pred = outputs["proj_out"]["drc_probs"]
+            if gt.shape[1] != pred.shape[2]:
+                gt = gt[:, ::gt.shape[1] // pred.shape[2], ::gt.shape[1] // pred.shape[2], :]
+            psi = torch.cat([(1 - gt).unsqueeze(0).expand(cfg.vox_size, -1, -1, -1, -1), gt.unsqueeze(0)], 0)
+            loss = loss + (pred * psi).sum() / gt.shape[0] * cfg.drc_weight
+        return loss
+
+    def regularization_loss(self):
+        """weight_decay * sum l2_loss(W) over encoder/decoder weights (util/losses.py:6-20)."""
+        if self.cfg.weight_decay <= 0:
+            return 0.0
+        reg = 0.0
+        for mod in (self.encoder, self.decoder, self.scale_fc, self.posenet):
+            if mod is None:
+                continue
+            for name, p in mod.named_parameters():
+                if name.endswith("weight"):
+                    reg = reg + (p.float() ** 2).sum() / 2
+        return reg * self.cfg.weight_decay

@@ -11,6 +11,29 @@ YAML is read with `yaml.safe_load` (the reference's bare `yaml.load` fails on Py
 import copy
 
 _DEFAULTS = {
+    # networks (default_config.yaml:10-26,37-47)
+    "image_size": 128,
+    "z_dim": 1024,
+    "f_dim": 16,
+    "fc_dim": 1024,
+    "pc_decoder_init_stddev": 0.025,
+    "pc_unit_cube": True,
+    "pose_candidates_num_layers": 3,
+    "pose_predictor_student": True,
+    "pose_predictor_student_loss_weight": 1.0,
+    "pose_student_align_loss": False,
+    "predict_translation_scaling_factor": 0.15,
+    "predict_translation_tanh": True,
+    "predict_translation_init_stddev": 0.05,
+    # loss / optimisation (default_config.yaml:92-122)
+    "proj_weight": 1.0,
+    "drc_weight": 0.0,
+    "proj_depth_weight": 0.0,
+    "learning_rate": 0.0001,
+    "learning_rate_step": 1.0,
+    "learning_rate_2": 0.00001,
+    "weight_decay": 0.001,
+    "variable_num_views": False,
     # shapes set by the caller (default_config.yaml:25-31,107-108,37)
     "pc_num_points": 8000,
     "pc_point_dropout": 1.0,
@@ -109,7 +132,8 @@ def experiment_config(name):
     if name == "chair_camera_supervision":
         return default_config(**common)
     if name == "chair_unsupervised":
-        return default_config(predict_pose=True, pose_predict_num_candidates=4, **common)
+        return default_config(predict_pose=True, pose_predict_num_candidates=4,
+                              pose_predictor_student_loss_weight=20.0, **common)
     raise KeyError(name)
 
 
