@@ -20,8 +20,22 @@
 
 #ifndef DPC_EMU
 #define DPC_DEV __device__ __forceinline__
+// Every kernel is launched with Programmatic Dependent Launch allowed: its CTAs may be scheduled
+// while the previous kernel of the stream is still draining, run their prologue (taps into smem,
+// mbarrier init), and block in dpc_grid_dep_sync() until the previous grid has completed and its
+// memory is visible.  That hides launch latency and the tail of each kernel behind the next one.
+template <typename... KArgs, typename... Args>
+static inline void dpc_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #define DPC_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+  dpc_launch_pdl(kernel, (grid), (block), (smem), (stream), __VA_ARGS__)
 #define DPC_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; \
   type* name = reinterpret_cast<type*>(name##_raw)
 #else
@@ -30,6 +44,18 @@
   dpc_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define DPC_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dpc_emu::dyn_smem())
 #endif
+
+// Block until the kernel(s) this launch depends on have completed (no-op without PDL).  Must
+// precede the first access to anything a previous kernel wrote, and the first global write.
+// It first signals that this grid's own dependents may be scheduled: that takes effect once EVERY
+// CTA of this grid has started (i.e. during its last wave), so the next kernel's CTAs fill the SM
+// slots freed by this kernel's tail and wait here for its completion.
+DPC_DEV void dpc_grid_dep_sync() {
+#ifndef DPC_EMU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 
 // ------------------------------------------------------------------ small PTX wrappers
 // red.global.add.f32: fire-and-forget fp32 add at L2 (SASS REDG.E.ADD.F32).

@@ -45,6 +45,7 @@ dpc_conv_xy_kernel(DpcConvXYArgs a) {
   const size_t slice = (size_t)blockIdx.x * VV;
   if (tid < a.Kx) tx[tid] = dpc_tap(a.taps_x, a.Kx, tid, a.rev);
   if (tid < a.Ky) ty[tid] = dpc_tap(a.taps_y, a.Ky, tid, a.rev);
+  dpc_grid_dep_sync();
   const int rounds = (VV + DPC_CONV_THREADS - 1) / DPC_CONV_THREADS;
   for (int r = 0; r < rounds; ++r) {
     const int i = r * DPC_CONV_THREADS + tid;
@@ -128,6 +129,7 @@ dpc_conv_z_fwd_kernel(DpcConvZArgs a) {
   float* taps = sm + (size_t)Vz * RW;
   const int tid = threadIdx.x;
   if (tid < a.K) taps[tid] = dpc_tap(a.taps, a.K, tid, a.rev);
+  dpc_grid_dep_sync();
   const float* src = a.in + ((size_t)b * Vz * V + y0) * V;
   const int rowlen = rows * V;
   for (int z = 0; z < Vz; ++z)
@@ -208,6 +210,7 @@ dpc_conv_z_bwd_kernel(DpcConvZBwdArgs a) {
   float* taps = tileD + (size_t)Vz * RW;
   const int tid = threadIdx.x;
   if (tid < a.K) taps[tid] = dpc_tap(a.taps, a.K, tid, a.rev);
+  dpc_grid_dep_sync();
   const float* src = a.vox + ((size_t)b * Vz * V + y0) * V;
   const int rowlen = rows * V;
   for (int z = 0; z < Vz; ++z)

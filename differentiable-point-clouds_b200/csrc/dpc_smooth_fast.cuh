@@ -71,6 +71,7 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
     const float tyv = (tid < K) ? dpc_tap(a.taps_y, K, tid, a.rev) : 0.0f;
     tyd[tid] = dpc_f2(tyv, tyv);
   }
+  dpc_grid_dep_sync();
 
   // ---- phase 0: slice -> smem (float4, coalesced), clip, clip-mask bits
   {
@@ -210,6 +211,7 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
   // engine, two per lane of warp 0, completion on one mbarrier; no register staging.
   const float* src = a.in + ((size_t)b * Vz * V + y0) * V;
   if (tid == 0) dpc_mbar_init(&bar, 1);
+  dpc_grid_dep_sync();
   __syncthreads();
   if (tid < 32) dpc_warp_bulk_rows(tile, RW, src, (size_t)V * V, Vz, RW * 4, &bar);
   dpc_mbar_wait(&bar, 0);
@@ -296,6 +298,7 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
   if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
   // the forward's voxels of these 4 image rows, all depth levels: TMA bulk copies into the tile
   if (tid == 0) dpc_mbar_init(&bar, 1);
+  dpc_grid_dep_sync();
   __syncthreads();
   if (tid < 32) dpc_warp_bulk_rows(tile, RW, a.vox + ((size_t)b * Vz * V + y0) * V, (size_t)V * V, Vz, RW * 4, &bar);
   const bool has_s = a.scale != nullptr;

@@ -71,6 +71,7 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
   const int lane = tid & 31;
   const int V = a.V, Vz = a.Vz;
 
+  dpc_grid_dep_sync();
   dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
                    a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
@@ -222,6 +223,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   const int lane = tid & 31, warp = tid >> 5;
   const int V = a.V, Vz = a.Vz;
 
+  dpc_grid_dep_sync();
   dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
                    a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
@@ -362,6 +364,7 @@ static void
 dpc_gather_kernel(const float* in, const int64_t* sel, int N, int n_keep, int C, float* out) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  dpc_grid_dep_sync();
   if (i >= n_keep * C) return;
   const int r = i / C, ch = i - r * C;
   const int64_t s = sel[(size_t)b * n_keep + r];
@@ -376,6 +379,7 @@ static void
 dpc_gather_bwd_kernel(const float* g_out, const int64_t* sel, int N, int n_keep, int C, float* g_in) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  dpc_grid_dep_sync();
   if (i >= n_keep * C) return;
   const int r = i / C, ch = i - r * C;
   const int64_t s = sel[(size_t)b * n_keep + r];
