@@ -61,6 +61,7 @@ int dpc_debug_stage_ms(float* out6) {
 int dpc_debug_set(int key, int value) {
   if (key < 0 || key >= 4) return DPC_ERR_ARG;
   g_tune[key] = value;
+  if (key == 2) dpc_xy_threads = (value == 128) ? 128 : 256;
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
@@ -326,8 +327,13 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   const float* tz = p->Kz > 0 ? taps_z : nullptr;
   const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
   stage_mark(0, stream);
-  if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO))
-    DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
+  if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO)) {
+    const size_t n4 = (size_t)g / 4;
+    const int blocks = (int)((n4 + 256 * 8 - 1) / (256 * 8));
+    DPC_LAUNCH(dpc_zero_kernel, dim3(blocks < 1 ? 1 : blocks), dim3(256), 0, stream, (float4*)w.raw, n4,
+               w.raw + n4 * 4, (int)(g - (int64_t)n4 * 4));
+    DPC_TRY(dpc_check_launch());
+  }
   DPC_TRY(dpc_splat_fwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
                         p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, stream));
   stage_mark(1, stream);

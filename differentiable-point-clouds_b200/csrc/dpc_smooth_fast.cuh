@@ -46,9 +46,11 @@ struct DpcConvXY64Args {
   int rev; float* zero_ptr;
 };
 
-template <int K>
+// NT = threads per CTA: 256 (one task per thread and phase) or 128 (two tasks per thread and
+// phase, twice as many independent CTAs resident per SM to overlap load / barrier bubbles).
+template <int K, int NT>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(NT, 768 / NT)
 #else
 static void
 #endif
@@ -76,12 +78,13 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
   // ---- phase 0: slice -> smem (float4, coalesced), clip, clip-mask bits
   {
     const float4* src = reinterpret_cast<const float4*>(a.in + slice);
-    float4 v[4];
+    constexpr int NL = 1024 / NT;
+    float4 v[NL];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = src[tid + 256 * k];        // all four loads in flight
+    for (int k = 0; k < NL; ++k) v[k] = src[tid + NT * k];        // all loads in flight
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = tid + 256 * k;            // float4 index in the slice: row = i/16, col4 = i%16
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + NT * k;             // float4 index in the slice: row = i/16, col4 = i%16
       if (a.mask_out) {
         unsigned nib = ((v[k].x >= 0.0f && v[k].x <= 1.0f) ? 1u : 0u) | ((v[k].y >= 0.0f && v[k].y <= 1.0f) ? 2u : 0u) |
                        ((v[k].z >= 0.0f && v[k].z <= 1.0f) ? 4u : 0u) | ((v[k].w >= 0.0f && v[k].w <= 1.0f) ? 8u : 0u);
@@ -98,9 +101,10 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
   }
   __syncthreads();
 
-  // ---- phase 1: x correlation.  Thread = (row y, run r of 16 outputs); a warp = 32 rows, one r.
-  {
-    const int y = tid & 63, r = tid >> 6;
+  // ---- phase 1: x correlation.  Task = (row y, run r of 16 outputs); a warp = 32 rows, one r.
+#pragma unroll 1
+  for (int task = tid; task < 256; task += NT) {
+    const int y = task & 63, r = task >> 6;
     const int x0 = r * 16;
     // tap pairs (t[a], t[a+1]), a = -1..K-1, index q = a+1: aligned float2 in E for even q, in O for odd q
     float2 tp[K + 1];
@@ -136,9 +140,10 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
   }
   __syncthreads();
 
-  // ---- phase 2: y correlation.  Thread = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
-  {
-    const int xp = tid & 31, y0 = (tid >> 5) * 8;
+  // ---- phase 2: y correlation.  Task = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
+#pragma unroll 1
+  for (int task = tid; task < 256; task += NT) {
+    const int xp = task & 31, y0 = (task >> 5) * 8;
     float2 acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
@@ -429,6 +434,8 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
+static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256 | 128 threads per conv_xy CTA
+
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
 
 static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, int ply) {
@@ -443,8 +450,14 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   DpcConvXY64Args a;
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
   a.nslices = B * Vz; a.rev = rev; a.zero_ptr = zero_ptr;
-  if (K == 21) { DPC_LAUNCH(dpc_conv_xy64_kernel<21>, dim3(a.nslices), dim3(256), 0, stream, a); }
-  else { DPC_LAUNCH(dpc_conv_xy64_kernel<11>, dim3(a.nslices), dim3(256), 0, stream, a); }
+  const bool small = dpc_xy_threads == 128;
+  if (K == 21) {
+    if (small) { DPC_LAUNCH((dpc_conv_xy64_kernel<21, 128>), dim3(a.nslices), dim3(128), 0, stream, a); }
+    else { DPC_LAUNCH((dpc_conv_xy64_kernel<21, 256>), dim3(a.nslices), dim3(256), 0, stream, a); }
+  } else {
+    if (small) { DPC_LAUNCH((dpc_conv_xy64_kernel<11, 128>), dim3(a.nslices), dim3(128), 0, stream, a); }
+    else { DPC_LAUNCH((dpc_conv_xy64_kernel<11, 256>), dim3(a.nslices), dim3(256), 0, stream, a); }
+  }
   return DPC_OK;
 }
 

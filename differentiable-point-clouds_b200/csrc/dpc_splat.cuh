@@ -355,6 +355,22 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------ grid zeroing
+// Zeroes the raw grid ahead of the splat.  Besides initialising the accumulation target this
+// leaves the grid resident (dirty) in L2, so the splat's reductions hit L2 instead of fetching
+// 32-byte sectors from HBM at random (measured: the splat kernel takes ~10 us longer on a cold grid).
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(256)
+#else
+static void
+#endif
+dpc_zero_kernel(float4* dst, size_t n4, float* tail, int ntail) {
+  dpc_grid_dep_sync();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.0f;
+}
+
 // ------------------------------------------------------------------------------ f-2: dropout gather
 #ifndef DPC_EMU
 __global__ void

@@ -53,7 +53,7 @@ int dpc_abi_version(void);
 const char* dpc_error_string(int code);
 int dpc_last_cuda_error(void);
 /* Experiment knob for benchmark sweeps (key 0/1: points per thread of the splat forward/backward
- * kernels, 1|2|4).
+ * kernels, 1|2|4; key 2: threads per CTA of the 64^3 xy-smoothing kernel, 256|128).
  * Process-wide, not thread-safe, not needed in normal use. */
 int dpc_debug_set(int key, int value);
 /* key 3 = 1: record CUDA events around every stage of the fused forward/backward; this returns the

@@ -21,15 +21,23 @@ def main():
         if clustered:
             pc = bench.make_inputs(bench.B, 0, clustered=True)[0]
             pipe.pc.copy_(pc.to(dev))
-        for ppt in (4, 2, 1):
-            pipe.L.dpc_debug_set(0, ppt)
-            pipe.L.dpc_debug_set(1, ppt)
+        for xy_threads in (256, 128):
+            pipe.L.dpc_debug_set(2, xy_threads)
             for _ in range(3):
                 pipe.step()
             st = pipe.stage_times(20, flush)
-            key = "%s_ppt%d" % ("clustered" if clustered else "spread", ppt)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                pipe.step()
+            e1.record()
+            torch.cuda.synchronize()
+            key = "%s_xy%d" % ("clustered" if clustered else "spread", xy_threads)
             out[key] = {k: round(v * 1000, 2) for k, v in st.items()}
+            out[key]["step_us"] = round(e0.elapsed_time(e1) / 20 * 1000, 2)
             print(key, out[key], flush=True)
+    pipe.L.dpc_debug_set(2, 256)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune.json"), "w"), indent=1)
 
 

@@ -38,3 +38,14 @@ def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
     finally:
         emu.dpc_debug_set(0, 4)
         emu.dpc_debug_set(1, 4)
+
+
+def test_conv_xy_128_thread_variant(emu):  # noqa: F811
+    emu.dpc_debug_set(2, 128)
+    try:
+        for name in ("v64_small", "v64_k11_max"):
+            fx = cases.load_golden(name)
+            outs, grads = cases.run_impl(Product, fx)
+            cases.assert_parity(fx, outs, grads)
+    finally:
+        emu.dpc_debug_set(2, 256)
