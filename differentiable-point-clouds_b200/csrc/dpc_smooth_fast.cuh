@@ -197,22 +197,28 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
 #define DPC_ZF_TY 4
 #define DPC_ZF_THREADS 256
 
+// Forward: CTA = 2 image rows x all 64 depth levels (32 KiB tile), 256 threads = 8 warps; warp w
+// works on row w>>2 and depth quarter w&3 (levels 16q .. 16q+15, two 8-output register chunks).
+// 1024 CTAs of this size fill the 148 SMs far more evenly than 512 four-row CTAs (whose second
+// wave was 15% full), and four of them are resident per SM.
+#define DPC_ZFW_TY 2
+
 template <int K>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(DPC_ZF_THREADS)
+__global__ void __launch_bounds__(DPC_ZF_THREADS, 4)
 #else
 static void
 #endif
 dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
-  constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZF_TY, RW = TY * V;
+  constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZFW_TY, RW = TY * V;
   DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(8) float2 tzd[K];          // taps, each duplicated into a float2 (FFMA2 operand)
-  __shared__ __align__(8) float comb[TY][V][2];   // (T, S) or (max, -) of the low depth half per ray
+  __shared__ __align__(8) float comb[4][TY][V][2];   // per depth quarter and ray: (T, S) or (max, -)
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
   if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
-  // ---- tile load: 64 bulk copies (one per depth level, TY*V*4 = 1 KiB each) through the TMA
+  // ---- tile load: 64 bulk copies (one per depth level, TY*V*4 = 512 B each) through the TMA
   // engine, two per lane of warp 0, completion on one mbarrier; no register staging.
   const float* src = a.in + ((size_t)b * Vz * V + y0) * V;
   if (tid == 0) dpc_mbar_init(&bar, 1);
@@ -223,18 +229,18 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
   __syncthreads();
 
   const int w = tid >> 5, xp = tid & 31;
-  const int ty = w >> 1, h = w & 1, y = y0 + ty;
+  const int ty = w >> 2, qd = w & 3, y = y0 + ty;
   const float2* tt = tzd;
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
   float2 T = dpc_f2(1.f, 1.f), S = dpc_f2(0.f, 0.f), mx = dpc_f2(-INFINITY, -INFINITY);
-  uint32_t m0 = 0u, m1 = 0u;   // clip-pass bits of the two rays for this depth half
+  uint32_t m0 = 0u, m1 = 0u;   // clip-pass bits of the two rays for this depth quarter (16 bits each)
   float* vout = a.vox_out + ((size_t)b * Vz * V + y) * V + 2 * xp;
   const float* col = tile + ty * V + 2 * xp;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const int zc = (4 * h + c) * 8;
+  for (int c = 0; c < 2; ++c) {
+    const int zc = (2 * qd + c) * 8;
     float2 acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
@@ -263,22 +269,33 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
     }
   }
   if (a.mask2_out && has_s) {
-    uint32_t* mp = a.mask2_out + (((size_t)b * V + y) * V + 2 * xp) * 2 + h;
-    mp[0] = m0; mp[2] = m1;
+    // per ray two 32-bit words (depth 0..31, 32..63); this warp owns 16 bits of one of them
+    uint16_t* mp = reinterpret_cast<uint16_t*>(a.mask2_out + (((size_t)b * V + y) * V + 2 * xp) * 2) + qd;
+    mp[0] = (uint16_t)m0; mp[4] = (uint16_t)m1;
   }
   if (a.mode == DPC_PROJ_NONE) return;
-  // combine the two depth halves
-  if (h == 0) {
-    *reinterpret_cast<float2*>(&comb[ty][2 * xp][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.x, 0.f) : dpc_f2(T.x, S.x);
-    *reinterpret_cast<float2*>(&comb[ty][2 * xp + 1][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.y, 0.f) : dpc_f2(T.y, S.y);
-  }
+  // combine the four depth quarters:  proj = S0 + T0 (S1 + T1 (S2 + T2 S3)),  max = max of maxima
+  *reinterpret_cast<float2*>(&comb[qd][ty][2 * xp][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.x, 0.f) : dpc_f2(T.x, S.x);
+  *reinterpret_cast<float2*>(&comb[qd][ty][2 * xp + 1][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.y, 0.f) : dpc_f2(T.y, S.y);
   __syncthreads();
-  if (h == 1) {
-    const float2 c0v = *reinterpret_cast<const float2*>(&comb[ty][2 * xp][0]);
-    const float2 c1v = *reinterpret_cast<const float2*>(&comb[ty][2 * xp + 1][0]);
+  if (qd == 0) {
     float2 out;
-    if (a.mode == DPC_PROJ_MAX) out = dpc_f2(fmaxf(c0v.x, mx.x), fmaxf(c1v.x, mx.y));
-    else out = dpc_f2(fmaf(c0v.x, S.x, c0v.y), fmaf(c1v.x, S.y, c1v.y));
+    if (a.mode == DPC_PROJ_MAX) {
+      out = mx;
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        out.x = fmaxf(out.x, comb[q][ty][2 * xp][0]);
+        out.y = fmaxf(out.y, comb[q][ty][2 * xp + 1][0]);
+      }
+    } else {
+      float r0 = comb[3][ty][2 * xp][1], r1 = comb[3][ty][2 * xp + 1][1];
+#pragma unroll
+      for (int q = 2; q >= 0; --q) {
+        r0 = fmaf(comb[q][ty][2 * xp][0], r0, comb[q][ty][2 * xp][1]);
+        r1 = fmaf(comb[q][ty][2 * xp + 1][0], r1, comb[q][ty][2 * xp + 1][1]);
+      }
+      out = dpc_f2(r0, r1);
+    }
     const int yo = a.flip_y ? (V - 1 - y) : y;
     *reinterpret_cast<float2*>(a.proj + ((size_t)b * V + yo) * V + 2 * xp) = out;
   }
@@ -433,6 +450,96 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
   }
 }
 
+// Lean backward (training configuration: DRC silhouette gradient only, occupancy scale present):
+// 2-row tiles like the forward.  Thread = (depth half, row, x): the product over a ray is split in
+// two 32-level halves exchanged through smem, after which every level's gradient is independent
+// (quotient form, see dpc_conv_z64_bwd_kernel).  Then warp = (row, depth quarter) for the
+// transposed correlation.
+template <int K>
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(DPC_ZF_THREADS, 4)
+#else
+static void
+#endif
+dpc_conv_z64_bwd_lean_kernel(DpcConvZBwdArgs a) {
+  constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZFW_TY, RW = TY * V;
+  DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]: forward voxels, overwritten by dL/d(smoothed)
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) float2 tzd[K];
+  __shared__ float pp[2][TY * V];
+  __shared__ float red[DPC_ZF_THREADS / 32];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, y0 = blockIdx.x * TY;
+  if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
+  if (tid == 0) dpc_mbar_init(&bar, 1);
+  dpc_grid_dep_sync();
+  __syncthreads();
+  if (tid < 32) dpc_warp_bulk_rows(tile, RW, a.vox + ((size_t)b * Vz * V + y0) * V, (size_t)V * V, Vz, RW * 4, &bar);
+  const float s = a.scale[b];
+  const float inv_s = (s != 0.0f) ? 1.0f / s : 0.0f;
+  const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
+  const int h = tid >> 7, rx = tid & 127;            // depth half, (row, x) within the tile
+  const int ty = rx >> 6, x = rx & 63, y = y0 + ty;
+  const int yo = a.flip_y ? (V - 1 - y) : y;
+  const float gp = a.g_proj[((size_t)b * V + yo) * V + x];
+  uint32_t wbits = a.mask2[(((size_t)b * V + y) * V + x) * 2 + h];
+  float* col = tile + (size_t)(32 * h) * RW + rx;
+  dpc_mbar_wait(&bar, 0);
+  {
+    float T0 = 1.0f, T1 = 1.0f, T2 = 1.0f, T3 = 1.0f;
+#pragma unroll 4
+    for (int z = 0; z < 32; z += 4) {
+      T0 *= 1.0f - fminf(fmaxf(col[(z + 0) * RW], D.lo), D.hi);
+      T1 *= 1.0f - fminf(fmaxf(col[(z + 1) * RW], D.lo), D.hi);
+      T2 *= 1.0f - fminf(fmaxf(col[(z + 2) * RW], D.lo), D.hi);
+      T3 *= 1.0f - fminf(fmaxf(col[(z + 3) * RW], D.lo), D.hi);
+    }
+    pp[h][rx] = (T0 * T1) * (T2 * T3);
+  }
+  __syncthreads();
+  const float gT = gp * (pp[0][rx] * pp[1][rx]);
+  float dsv = 0.0f;
+#pragma unroll 8
+  for (int zz = 0; zz < 32; ++zz) {
+    const float v = col[zz * RW];
+    const float u = fminf(fmaxf(v, D.lo), D.hi);
+    float dv = __fdividef(gT, 1.0f - u);
+    if (zz == 0 && h == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
+    if ((u != v) || !(wbits & 1u)) dv = 0.0f;
+    wbits >>= 1;
+    dsv = fmaf(dv, v, dsv);
+    col[zz * RW] = dv * s;
+  }
+  const float ds = dsv * inv_s;
+  __syncthreads();
+  {
+    const int w = tid >> 5, xp = tid & 31;
+    const int wy = w >> 2, qd = w & 3, yy = y0 + wy;
+    const float* c2 = tile + wy * V + 2 * xp;
+    float* dout = a.d_in + ((size_t)b * Vz * V + yy) * V + 2 * xp;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int zc = (2 * qd + c) * 8;
+      float2 acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+      dpc_col_conv_pairs<K, 8>(c2, RW, zc, Vz, tzd, acc);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(dout + (size_t)(zc + o) * V * V) = acc[o];
+    }
+  }
+  if (a.d_scale) {
+    const float v = dpc_warp_sum(ds);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.0f;
+      for (int i = 0; i < DPC_ZF_THREADS / 32; ++i) t += red[i];
+      atomicAdd(a.d_scale + b, t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ dispatch
 static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256 | 128 threads per conv_xy CTA
 
@@ -472,10 +579,10 @@ static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_
                                              void* stream) {
   DpcConvZArgs a;
   a.in = in; a.taps = taps_z; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = eps;
-  a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;
+  a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZFW_TY;
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = probs; a.depth = depth;
-  const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
-  dim3 grid(V / DPC_ZF_TY, B), block(DPC_ZF_THREADS);
+  const size_t smem = (size_t)Vz * DPC_ZFW_TY * V * sizeof(float);
+  dim3 grid(V / DPC_ZFW_TY, B), block(DPC_ZF_THREADS);
 #ifndef DPC_EMU
   cudaError_t e = (Kz == 21)
       ? cudaFuncSetAttribute(dpc_conv_z64_fwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -500,6 +607,13 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
   const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
   dim3 grid(V / DPC_ZF_TY, B), block(DPC_ZF_THREADS);
   const bool lean = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
+  if (lean) {
+    const size_t smem2 = (size_t)Vz * DPC_ZFW_TY * V * sizeof(float);
+    dim3 grid2(V / DPC_ZFW_TY, B);
+    if (Kz == 21) { DPC_LAUNCH(dpc_conv_z64_bwd_lean_kernel<21>, grid2, block, smem2, stream, a); }
+    else { DPC_LAUNCH(dpc_conv_z64_bwd_lean_kernel<11>, grid2, block, smem2, stream, a); }
+    return DPC_OK;
+  }
 #ifndef DPC_EMU
 #define DPC_ZB_LAUNCH(KK, LL) do { \
     if (cudaFuncSetAttribute(dpc_conv_z64_bwd_kernel<KK, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DPC_ERR_CUDA; \
@@ -507,8 +621,7 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
 #else
 #define DPC_ZB_LAUNCH(KK, LL) do { DPC_LAUNCH((dpc_conv_z64_bwd_kernel<KK, LL>), grid, block, smem, stream, a); } while (0)
 #endif
-  if (Kz == 21) { if (lean) DPC_ZB_LAUNCH(21, true); else DPC_ZB_LAUNCH(21, false); }
-  else { if (lean) DPC_ZB_LAUNCH(11, true); else DPC_ZB_LAUNCH(11, false); }
+  if (Kz == 21) DPC_ZB_LAUNCH(21, false); else DPC_ZB_LAUNCH(11, false);
 #undef DPC_ZB_LAUNCH
   return DPC_OK;
 }

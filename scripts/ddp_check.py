@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""torchrun --nproc-per-node W scripts/ddp_check.py : data-parallel train step over NCCL (SURVEY.md 4.4,
+8e).  Objects are sharded over ranks (a rank keeps all views/candidates of its objects), the renderer
+runs locally with no collective, DDP all-reduces the CNN gradients once; the averaged gradients must
+equal the single-process gradients on the concatenated batch."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dpc_b200 import distributed as D  # noqa: E402
+from dpc_b200.train import Trainer, synthetic_batch  # noqa: E402
+from dpc_b200.util.config import experiment_config  # noqa: E402
+
+
+def main():
+    rank, local_rank, world = D.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    name = sys.argv[1] if len(sys.argv) > 1 else "chair_camera_supervision"
+    per_rank = 2
+    cfg = experiment_config(name)
+    cfg.batch_size = per_rank
+    cfg.pc_point_dropout = 1.0            # the dropout draw is per process; keep the comparison deterministic
+    full = experiment_config(name)
+    full.batch_size = per_rank * world
+    full.pc_point_dropout = 1.0
+    big = synthetic_batch(full, dev, seed=7)
+    lo, hi = D.shard_range(full.batch_size, rank, world)
+    s = cfg.step_size
+    mine = {k: (v[lo * s:hi * s] if k != "images_1" else v[lo:hi]).contiguous() for k, v in big.items()}
+
+    torch.manual_seed(0)
+    tr = Trainer(cfg, dev, ddp=world > 1, bf16=False)
+    tr.opt.zero_grad(set_to_none=True)
+    out = tr.net(mine, 0, True)
+    loss = tr.model.get_loss(mine, out) + tr.model.regularization_loss()
+    loss.backward()
+    torch.cuda.synchronize()
+    res = {"world": world, "name": name}
+    if rank == 0:
+        torch.manual_seed(0)
+        ref = Trainer(full, dev, ddp=False, bf16=False)
+        ref.model.load_state_dict(tr.model.state_dict())
+        out_r = ref.net(big, 0, True)
+        loss_r = ref.model.get_loss(big, out_r) + ref.model.regularization_loss()
+        loss_r.backward()
+        worst = 0.0
+        for (n, p), (_, q) in zip(tr.model.named_parameters(), ref.model.named_parameters()):
+            if p.grad is None and q.grad is None:
+                continue
+            d = float((p.grad - q.grad).abs().max())
+            sc = max(1e-6, float(q.grad.abs().max()))
+            worst = max(worst, d / sc)
+        res.update(loss_rank0=float(loss), loss_full=float(loss_r), max_rel_grad_diff=worst)
+        print(json.dumps(res))
+        assert worst < 2e-3, worst
+    D.barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
