@@ -230,27 +230,36 @@ class Pipeline:
             L.dpc_debug_set(3, 0)
         return {k: tot[i] / steps for i, k in enumerate(self.STAGES)}
 
-    def e2e_step(self):
-        """Through the public API with host buffers: H2D inputs, forward, loss, backward, D2H results."""
-        from dpc_b200.util import point_cloud as pcm
+    def _e2e_setup(self):
+        """One pinned host blob per direction: inputs (pc|q|scale|gt) and results (loss|proj|d_pc|d_q|d_scale)."""
         hp, hq, hs, hg = self.host
-        pc = hp.to(self.dev, non_blocking=True).requires_grad_(True)
-        q = hq.to(self.dev, non_blocking=True).requires_grad_(True)
-        sc = hs.to(self.dev, non_blocking=True).requires_grad_(True)
-        gt = hg.to(self.dev, non_blocking=True)
+        self.in_sizes = [t.numel() for t in (hp, hq, hs, hg)]
+        self.in_shapes = [t.shape for t in (hp, hq, hs, hg)]
+        self.h_in = torch.cat([t.reshape(-1) for t in (hp, hq, hs, hg)]).pin_memory()
+        self.d_in = torch.empty_like(self.h_in, device=self.dev)
+        self.out_sizes = [1, B * V * V, B * N * 3, B * 4, B]
+        self.d_out = torch.empty(sum(self.out_sizes), dtype=torch.float32, device=self.dev)
+        self.h_out = torch.empty(sum(self.out_sizes), dtype=torch.float32).pin_memory()
+
+    def e2e_step(self):
+        """Through the public API with HOST buffers: one H2D of the step's inputs from pinned memory,
+        forward, loss, backward (autograd), one D2H of loss + silhouettes + gradients."""
+        from dpc_b200.util import point_cloud as pcm
+        if not hasattr(self, "h_in"):
+            self._e2e_setup()
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        parts = torch.split(self.d_in, self.in_sizes)
+        pc, q, sc, gt = [p.reshape(sh) for p, sh in zip(parts, self.in_shapes)]
+        pc, q, sc = pc.requires_grad_(True), q.requires_grad_(True), sc.requires_grad_(True)
         out = pcm.pointcloud_project_fast(self.cfg, pc, q, None, None, self.kernel, sc)
         loss = ((gt - out["proj"]) ** 2).sum() / 2 / B
-        loss.backward()
-        res = [loss.detach().reshape(1), out["proj"].detach(), pc.grad, q.grad, sc.grad]
-        if not hasattr(self, "host_out"):
-            self.host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
-        for h, t in zip(self.host_out, res):
-            h.copy_(t, non_blocking=True)
+        gpc, gq, gsc = torch.autograd.grad(loss, (pc, q, sc))
+        dst = torch.split(self.d_out, self.out_sizes)
+        for d, t in zip(dst, (loss.detach(), out["proj"].detach(), gpc, gq, gsc)):
+            d.copy_(t.reshape(-1))
+        self.h_out.copy_(self.d_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        host = self.host_out
-        h2d = sum(t.numel() * t.element_size() for t in (hp, hq, hs, hg))
-        d2h = sum(t.numel() * t.element_size() for t in res)
-        return float(host[0]), h2d, d2h
+        return float(self.h_out[0]), self.h_in.numel() * 4, self.h_out.numel() * 4
 
 
 def run_ours(args, rank, local_rank, world):

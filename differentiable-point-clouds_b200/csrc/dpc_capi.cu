@@ -327,13 +327,10 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   const float* tz = p->Kz > 0 ? taps_z : nullptr;
   const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
   stage_mark(0, stream);
-  if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO)) {
-    const size_t n4 = (size_t)g / 4;
-    const int blocks = (int)((n4 + 256 * 8 - 1) / (256 * 8));
-    DPC_LAUNCH(dpc_zero_kernel, dim3(blocks < 1 ? 1 : blocks), dim3(256), 0, stream, (float4*)w.raw, n4,
-               w.raw + n4 * 4, (int)(g - (int64_t)n4 * 4));
-    DPC_TRY(dpc_check_launch());
-  }
+  // cudaMemsetAsync beat a hand-written float4 zero kernel here (23.6 vs 28.4 us for memset + splat,
+  // gpurun round 7), so the driver's memset stays.
+  if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO))
+    DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
   DPC_TRY(dpc_splat_fwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
                         p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, stream));
   stage_mark(1, stream);
