@@ -351,8 +351,52 @@ def run_ours(args, rank, local_rank, world):
     D.barrier()
 
 
+def run_train(args, rank, local_rank, world):
+    """BASELINE configs 3/4: the full train step (CNN encoder/decoder under bf16 autocast -> fp32
+    renderer -> losses -> Adam), data parallel over ranks with DDP's gradient all-reduce."""
+    from dpc_b200 import distributed as D
+    from dpc_b200.train import Trainer, synthetic_batch
+    from dpc_b200.util.config import experiment_config
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    name = "chair_camera_supervision" if args.workload == "train_supervised" else "chair_unsupervised"
+    cfg = experiment_config(name)
+    if args.objects_per_rank:
+        cfg.batch_size = args.objects_per_rank
+    torch.manual_seed(0)
+    tr = Trainer(cfg, dev, ddp=world > 1, bf16=True)
+    batch = synthetic_batch(cfg, dev, seed=rank)
+    for _ in range(max(3, args.warmup)):
+        tr.step(batch)
+    torch.cuda.synchronize()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.step(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.reduce_scalar(e0.elapsed_time(e1), "max", dev)
+    views = cfg.batch_size * cfg.step_size
+    if rank == 0:
+        print(json.dumps({
+            "metric": "train step: object-views/sec (%s)" % name, "value": world * views * args.steps / (ms / 1000.0),
+            "unit": "object-views/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (CNN) + f32 (renderer)", "data": "synthetic",
+            "config": {"workload": name, "objects_per_gpu": cfg.batch_size, "views": cfg.step_size,
+                       "pose_candidates": cfg.pose_predict_num_candidates,
+                       "renderer_batch_per_gpu": views * cfg.pose_predict_num_candidates,
+                       "parallelism": "dp%d (DDP, one bucketed NCCL all-reduce of the CNN gradients)" % world},
+            "loss": float(loss)}))
+    D.barrier()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="projection", choices=["projection", "train_supervised", "train_unsupervised"])
+    ap.add_argument("--objects-per-rank", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
@@ -367,7 +411,10 @@ def main():
         run_reference(args, rank)
         return
     rank, local_rank, world = D.init()
-    run_ours(args, rank, local_rank, world)
+    if args.workload != "projection":
+        run_train(args, rank, local_rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
     if world > 1:
         torch.distributed.destroy_process_group()
 

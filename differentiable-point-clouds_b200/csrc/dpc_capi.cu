@@ -17,7 +17,7 @@ static int dpc_check_launch() {
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
 // Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[4] = {4, 4, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
+static int g_tune[8] = {4, 4, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
 // ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are
@@ -59,9 +59,10 @@ int dpc_debug_stage_ms(float* out6) {
 }
 
 int dpc_debug_set(int key, int value) {
-  if (key < 0 || key >= 4) return DPC_ERR_ARG;
+  if (key < 0 || key >= 8) return DPC_ERR_ARG;
   g_tune[key] = value;
   if (key == 2) dpc_xy_threads = (value == 128) ? 128 : 256;
+  if (key == 4) dpc_z_minblocks = (value == 3) ? 3 : 4;
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }

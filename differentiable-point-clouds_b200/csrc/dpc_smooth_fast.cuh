@@ -203,9 +203,9 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
 // wave was 15% full), and four of them are resident per SM.
 #define DPC_ZFW_TY 2
 
-template <int K>
+template <int K, int MINB>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(DPC_ZF_THREADS, 4)
+__global__ void __launch_bounds__(DPC_ZF_THREADS, MINB)
 #else
 static void
 #endif
@@ -230,7 +230,9 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
 
   const int w = tid >> 5, xp = tid & 31;
   const int ty = w >> 2, qd = w & 3, y = y0 + ty;
-  const float2* tt = tzd;
+  float2 tt[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) tt[j] = tzd[j];
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
@@ -455,9 +457,9 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
 // two 32-level halves exchanged through smem, after which every level's gradient is independent
 // (quotient form, see dpc_conv_z64_bwd_kernel).  Then warp = (row, depth quarter) for the
 // transposed correlation.
-template <int K>
+template <int K, int MINB>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(DPC_ZF_THREADS, 4)
+__global__ void __launch_bounds__(DPC_ZF_THREADS, MINB)
 #else
 static void
 #endif
@@ -517,13 +519,16 @@ dpc_conv_z64_bwd_lean_kernel(DpcConvZBwdArgs a) {
     const int wy = w >> 2, qd = w & 3, yy = y0 + wy;
     const float* c2 = tile + wy * V + 2 * xp;
     float* dout = a.d_in + ((size_t)b * Vz * V + yy) * V + 2 * xp;
+    float2 tt[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) tt[j] = tzd[j];
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int zc = (2 * qd + c) * 8;
       float2 acc[8];
 #pragma unroll
       for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      dpc_col_conv_pairs<K, 8>(c2, RW, zc, Vz, tzd, acc);
+      dpc_col_conv_pairs<K, 8>(c2, RW, zc, Vz, tt, acc);
 #pragma unroll
       for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(dout + (size_t)(zc + o) * V * V) = acc[o];
     }
@@ -541,6 +546,7 @@ dpc_conv_z64_bwd_lean_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
+static int dpc_z_minblocks = 4;    // experiment knob (dpc_debug_set key 4): resident CTAs/SM the conv_z kernels are compiled for
 static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256 | 128 threads per conv_xy CTA
 
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
@@ -583,14 +589,14 @@ static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = probs; a.depth = depth;
   const size_t smem = (size_t)Vz * DPC_ZFW_TY * V * sizeof(float);
   dim3 grid(V / DPC_ZFW_TY, B), block(DPC_ZF_THREADS);
-#ifndef DPC_EMU
-  cudaError_t e = (Kz == 21)
-      ? cudaFuncSetAttribute(dpc_conv_z64_fwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-      : cudaFuncSetAttribute(dpc_conv_z64_fwd_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return DPC_ERR_CUDA;
-#endif
-  if (Kz == 21) { DPC_LAUNCH(dpc_conv_z64_fwd_kernel<21>, grid, block, smem, stream, a); }
-  else { DPC_LAUNCH(dpc_conv_z64_fwd_kernel<11>, grid, block, smem, stream, a); }
+  const bool b3 = dpc_z_minblocks == 3;
+  if (Kz == 21) {
+    if (b3) { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<21, 3>), grid, block, smem, stream, a); }
+    else { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<21, 4>), grid, block, smem, stream, a); }
+  } else {
+    if (b3) { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<11, 3>), grid, block, smem, stream, a); }
+    else { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<11, 4>), grid, block, smem, stream, a); }
+  }
   return DPC_OK;
 }
 
@@ -610,8 +616,14 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
   if (lean) {
     const size_t smem2 = (size_t)Vz * DPC_ZFW_TY * V * sizeof(float);
     dim3 grid2(V / DPC_ZFW_TY, B);
-    if (Kz == 21) { DPC_LAUNCH(dpc_conv_z64_bwd_lean_kernel<21>, grid2, block, smem2, stream, a); }
-    else { DPC_LAUNCH(dpc_conv_z64_bwd_lean_kernel<11>, grid2, block, smem2, stream, a); }
+    const bool b3 = dpc_z_minblocks == 3;
+    if (Kz == 21) {
+      if (b3) { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<21, 3>), grid2, block, smem2, stream, a); }
+      else { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<21, 4>), grid2, block, smem2, stream, a); }
+    } else {
+      if (b3) { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<11, 3>), grid2, block, smem2, stream, a); }
+      else { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<11, 4>), grid2, block, smem2, stream, a); }
+    }
     return DPC_OK;
   }
 #ifndef DPC_EMU
