@@ -62,7 +62,6 @@ int dpc_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return DPC_ERR_ARG;
   g_tune[key] = value;
   if (key == 2) dpc_xy_threads = (value == 128) ? 128 : 256;
-  if (key == 4) dpc_z_minblocks = (value == 3) ? 3 : 4;
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
@@ -150,7 +149,7 @@ static int launch_conv_xy(const float* in, float* out, const float* taps_x, int 
   if ((mask_bits_out || mask_bits_in) && ((V * V) % 32 != 0)) return DPC_ERR_SHAPE;
   if ((int64_t)B * Vz > 2147483647LL) return DPC_ERR_SHAPE;
   float* zero_ptr = zero_in ? const_cast<float*>(in) : nullptr;
-  if (taps_x && taps_y && dpc_conv_xy_fast_supported(V, Kx, pad_lo_x, Ky, pad_lo_y)) {
+  if (taps_x && taps_y && dpc_conv_xy_fast_supported(V, Kx, pad_lo_x, Ky, pad_lo_y) && ((int64_t)B * Vz * V * V) % (V == 128 ? 16384 : 4096) == 0) {
     DPC_TRY(dpc_conv_xy_fast_launch(in, out, taps_x, taps_y, Kx, B, Vz, V, clip_in, mask_bits_out, mask_bits_in,
                                     rev, zero_ptr, stream));
     return dpc_check_launch();
@@ -212,7 +211,9 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
   if ((g_probs || g_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
   if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo < 0 || pad_lo >= Kz) return DPC_ERR_ARG;
-  if (taps && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo, g_probs != nullptr || g_depth != nullptr)) {
+  const bool lean_case = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
+  if (taps && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo, g_probs != nullptr || g_depth != nullptr) &&
+      (lean_case || dpc_conv_z_bwd_fast_general_ok(V))) {
     DPC_TRY(dpc_conv_z_bwd_fast_launch(vox, mask2, scale, taps, Kz, mode, clip_eps, cam_dist, max_depth, flip_y,
                                        B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, rev, stream));
     return dpc_check_launch();

@@ -46,26 +46,40 @@ struct DpcConvXY64Args {
   int rev; float* zero_ptr;
 };
 
+// V in {32, 64, 128}: a CTA owns one "unit" of contiguous voxels: four 32x32 slices, one 64x64 slice or
+// one 128x128 slice.  The x pass works on AR rows at a time (NP passes; two at V=128 so that the
+// input rows need only half a slice of smem), the y pass on the whole unit.
 // NT = threads per CTA: 256 (one task per thread and phase) or 128 (two tasks per thread and
 // phase, twice as many independent CTAs resident per SM to overlap load / barrier bubbles).
-template <int K, int NT>
+template <int V, int K, int NT>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(NT, 768 / NT)
 #else
 static void
 #endif
-dpc_conv_xy64_kernel(DpcConvXY64Args a) {
-  constexpr int V = DPC_F64_V, S = DPC_F64_S, PL = (K - 1) / 2;
+dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
+  constexpr int S = V + 4, PL = (K - 1) / 2;
+  constexpr int SPC = (V == 32) ? 4 : 1;            // slices per unit
+  constexpr int UNIT = SPC * V * V;                 // voxels per CTA: 4096, 4096, 16384
+  constexpr int MR = SPC * V;                       // rows of the unit: 128, 64, 128
+  constexpr int AR = (V == 128) ? 64 : MR;          // rows per x pass
+  constexpr int NP = MR / AR;
   constexpr int WL = ((PL + 3) / 4) * 4;            // window starts WL floats left of the first output
   constexpr int NW4 = (WL + 16 + WL) / 4;           // float4 groups in the x window
+  constexpr int XR = V / 16;                        // x runs of 16 outputs per row
+  constexpr int XT = AR * XR;                       // x tasks per pass: 256, 256, 512
+  constexpr int YT = (V / 2) * (V / 8);             // y tasks per slice: 64, 256, 1024
   static_assert((K & 1) == 1 && K <= 21, "odd K <= 21");
-  __shared__ __align__(16) float A[V * S];
-  __shared__ __align__(16) float M[V * S];
+  static_assert(V == 32 || V == 64 || V == 128, "V");
+  static_assert((S / 4) % 2 == 1, "row pitch must be an odd number of 16-byte units");
+  DPC_DYN_SMEM(float, sm);
+  float* A = sm;                                     // [AR][S]
+  float* M = sm + AR * S;                            // [MR][S]
   __shared__ __align__(8) float txe[24];            // E[i] = t[i-1], i = 0..K+1 (zero outside)
   __shared__ __align__(8) float txo[24];            // O[i] = E[i+1]
   __shared__ __align__(8) float2 tyd[24];           // y taps, each duplicated into a float2 (FFMA2 operand)
   const int tid = threadIdx.x;
-  const size_t slice = (size_t)blockIdx.x * (V * V);
+  const size_t slice = (size_t)blockIdx.x * UNIT;   // first voxel of this CTA's unit
   if (tid < 24) {
     const int a_e = tid - 1, a_o = tid;              // tap indices behind E[tid], O[tid]
     txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
@@ -75,16 +89,19 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
   }
   dpc_grid_dep_sync();
 
-  // ---- phase 0: slice -> smem (float4, coalesced), clip, clip-mask bits
+#pragma unroll 1
+  for (int ps = 0; ps < NP; ++ps) {
+  const size_t poff = (size_t)ps * AR * V;          // first voxel of this pass within the unit
+  // ---- phase 0: AR rows -> smem (float4, coalesced), clip, clip-mask bits
   {
-    const float4* src = reinterpret_cast<const float4*>(a.in + slice);
-    constexpr int NL = 1024 / NT;
+    const float4* src = reinterpret_cast<const float4*>(a.in + slice + poff);
+    constexpr int NL = AR * V / 4 / NT;
     float4 v[NL];
 #pragma unroll
     for (int k = 0; k < NL; ++k) v[k] = src[tid + NT * k];        // all loads in flight
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
-      const int i = tid + NT * k;             // float4 index in the slice: row = i/16, col4 = i%16
+      const int i = tid + NT * k;             // float4 index within the pass
       if (a.mask_out) {
         unsigned nib = ((v[k].x >= 0.0f && v[k].x <= 1.0f) ? 1u : 0u) | ((v[k].y >= 0.0f && v[k].y <= 1.0f) ? 2u : 0u) |
                        ((v[k].z >= 0.0f && v[k].z <= 1.0f) ? 4u : 0u) | ((v[k].w >= 0.0f && v[k].w <= 1.0f) ? 8u : 0u);
@@ -92,19 +109,20 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
         word |= __shfl_xor_sync(DPC_FULL, word, 1);
         word |= __shfl_xor_sync(DPC_FULL, word, 2);
         word |= __shfl_xor_sync(DPC_FULL, word, 4);
-        if ((tid & 7) == 0) a.mask_out[(slice >> 5) + (i >> 3)] = word;
+        if ((tid & 7) == 0) a.mask_out[((slice + poff) >> 5) + (i >> 3)] = word;
       }
       if (a.clip_in) { v[k].x = dpc_clip01(v[k].x); v[k].y = dpc_clip01(v[k].y); v[k].z = dpc_clip01(v[k].z); v[k].w = dpc_clip01(v[k].w); }
-      *reinterpret_cast<float4*>(&A[(i >> 4) * S + (i & 15) * 4]) = v[k];
-      if (a.zero_ptr) reinterpret_cast<float4*>(a.zero_ptr + slice)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int e = 4 * i, row = e / V, c0 = e % V;     // row within the pass
+      *reinterpret_cast<float4*>(&A[row * S + c0]) = v[k];
+      if (a.zero_ptr) reinterpret_cast<float4*>(a.zero_ptr + slice + poff)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncthreads();
 
-  // ---- phase 1: x correlation.  Task = (row y, run r of 16 outputs); a warp = 32 rows, one r.
+  // ---- phase 1: x correlation.  Task = (row of the pass, run r of 16 outputs); a warp = 32 rows, one r.
 #pragma unroll 1
-  for (int task = tid; task < 256; task += NT) {
-    const int y = task & 63, r = task >> 6;
+  for (int task = tid; task < XT; task += NT) {
+    const int y = task % AR, r = task / AR;
     const int x0 = r * 16;
     // tap pairs (t[a], t[a+1]), a = -1..K-1, index q = a+1: aligned float2 in E for even q, in O for odd q
     float2 tp[K + 1];
@@ -131,7 +149,7 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
         }
       }
     }
-    float* dst = M + y * S + x0;
+    float* dst = M + (ps * AR + y) * S + x0;
 #pragma unroll
     for (int o = 0; o < 16; o += 4) {
       *reinterpret_cast<float4*>(dst + o) = make_float4(acc[o].x + acc[o].y, acc[o + 1].x + acc[o + 1].y,
@@ -139,21 +157,24 @@ dpc_conv_xy64_kernel(DpcConvXY64Args a) {
     }
   }
   __syncthreads();
+  }  // x passes
 
-  // ---- phase 2: y correlation.  Task = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
+  // ---- phase 2: y correlation.  Task = (slice, x pair, run of 8 rows).
 #pragma unroll 1
-  for (int task = tid; task < 256; task += NT) {
-    const int xp = task & 31, y0 = (task >> 5) * 8;
+  for (int task = tid; task < SPC * YT; task += NT) {
+    const int sl = task / YT, t = task % YT;
+    const int xp = t % (V / 2), y0 = (t / (V / 2)) * 8;
     float2 acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-    dpc_col_conv_pairs<K, 8>(M + 2 * xp, S, y0, V, tyd, acc);
-    float* dst = a.out + slice + (size_t)y0 * V + 2 * xp;
+    dpc_col_conv_pairs<K, 8>(M + sl * V * S + 2 * xp, S, y0, V, tyd, acc);
+    const size_t base = slice + (size_t)sl * V * V;
+    float* dst = a.out + base + (size_t)y0 * V + 2 * xp;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       float2 v = acc[o];
       if (a.mask_in) {
-        const size_t e = slice + (size_t)(y0 + o) * V + 2 * xp;
+        const size_t e = base + (size_t)(y0 + o) * V + 2 * xp;
         const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
         if (!(wbits & 1u)) v.x = 0.0f;
         if (!(wbits & 2u)) v.y = 0.0f;
@@ -197,29 +218,28 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
 #define DPC_ZF_TY 4
 #define DPC_ZF_THREADS 256
 
-// Forward: CTA = 2 image rows x all 64 depth levels (32 KiB tile), 256 threads = 8 warps; warp w
-// works on row w>>2 and depth quarter w&3 (levels 16q .. 16q+15, two 8-output register chunks).
-// 1024 CTAs of this size fill the 148 SMs far more evenly than 512 four-row CTAs (whose second
-// wave was 15% full), and four of them are resident per SM.
-#define DPC_ZFW_TY 2
-
-template <int K, int MINB>
+// Forward, V = Vz in {32, 64, 128}.  A CTA owns 128 rays (TY = 128/V image rows) over all depth
+// levels: tile [Vz][128] fp32 (16 / 32 / 64 KiB) loaded by Vz TMA bulk copies of 512 B.  256 threads =
+// 4 depth segments x 64 ray pairs; a thread runs CPS = Vz/32 register chunks of 8 outputs.  The ray
+// scan starts from T = 1 in every segment and the segments are combined through smem:
+//   proj = S0 + T0 (S1 + T1 (S2 + T2 S3)),  max = max of the segment maxima.
+// At 64^3 that is 1024 CTAs, four resident per SM.
+template <int V, int K, int MINB>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(DPC_ZF_THREADS, MINB)
 #else
 static void
 #endif
-dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
-  constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZFW_TY, RW = TY * V;
-  DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]
+dpc_conv_z_fast_fwd_kernel(DpcConvZArgs a) {
+  constexpr int Vz = V, TY = 128 / V, RW = 128, CPS = Vz / 32, NW = Vz / 32;
+  static_assert(V == 32 || V == 64 || V == 128, "V");
+  DPC_DYN_SMEM(float, tile);                // [Vz][TY][V] = [Vz][128]
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(8) float2 tzd[K];          // taps, each duplicated into a float2 (FFMA2 operand)
-  __shared__ __align__(8) float comb[4][TY][V][2];   // per depth quarter and ray: (T, S) or (max, -)
+  __shared__ __align__(8) float comb[4][128][2];  // per depth segment and ray: (T, S) or (max, -)
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
   if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
-  // ---- tile load: 64 bulk copies (one per depth level, TY*V*4 = 512 B each) through the TMA
-  // engine, two per lane of warp 0, completion on one mbarrier; no register staging.
   const float* src = a.in + ((size_t)b * Vz * V + y0) * V;
   if (tid == 0) dpc_mbar_init(&bar, 1);
   dpc_grid_dep_sync();
@@ -228,21 +248,19 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
   dpc_mbar_wait(&bar, 0);
   __syncthreads();
 
-  const int w = tid >> 5, xp = tid & 31;
-  const int ty = w >> 2, qd = w & 3, y = y0 + ty;
-  float2 tt[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) tt[j] = tzd[j];
+  const int seg = tid >> 6, pidx = tid & 63;              // depth segment, ray pair within the CTA
+  const int ty = pidx / (V / 2), xp = pidx % (V / 2), y = y0 + ty;
+  const float2* tt = tzd;
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
   float2 T = dpc_f2(1.f, 1.f), S = dpc_f2(0.f, 0.f), mx = dpc_f2(-INFINITY, -INFINITY);
-  uint32_t m0 = 0u, m1 = 0u;   // clip-pass bits of the two rays for this depth quarter (16 bits each)
+  uint32_t m0 = 0u, m1 = 0u;   // clip-pass bits of the two rays for this depth segment (8*CPS bits each)
   float* vout = a.vox_out + ((size_t)b * Vz * V + y) * V + 2 * xp;
-  const float* col = tile + ty * V + 2 * xp;
+  const float* col = tile + 2 * pidx;
 #pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    const int zc = (2 * qd + c) * 8;
+  for (int c = 0; c < CPS; ++c) {
+    const int zc = (CPS * seg + c) * 8;
     float2 acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
@@ -271,30 +289,30 @@ dpc_conv_z64_fwd_kernel(DpcConvZArgs a) {
     }
   }
   if (a.mask2_out && has_s) {
-    // per ray two 32-bit words (depth 0..31, 32..63); this warp owns 16 bits of one of them
-    uint16_t* mp = reinterpret_cast<uint16_t*>(a.mask2_out + (((size_t)b * V + y) * V + 2 * xp) * 2) + qd;
-    mp[0] = (uint16_t)m0; mp[4] = (uint16_t)m1;
+    // per ray NW 32-bit words of clip-pass bits, bit z = depth level z; this thread owns CPS bytes of each ray
+    uint8_t* mp = reinterpret_cast<uint8_t*>(a.mask2_out + (((size_t)b * V + y) * V + 2 * xp) * NW) + seg * CPS;
+#pragma unroll
+    for (int c = 0; c < CPS; ++c) { mp[c] = (uint8_t)(m0 >> (8 * c)); mp[4 * NW + c] = (uint8_t)(m1 >> (8 * c)); }
   }
   if (a.mode == DPC_PROJ_NONE) return;
-  // combine the four depth quarters:  proj = S0 + T0 (S1 + T1 (S2 + T2 S3)),  max = max of maxima
-  *reinterpret_cast<float2*>(&comb[qd][ty][2 * xp][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.x, 0.f) : dpc_f2(T.x, S.x);
-  *reinterpret_cast<float2*>(&comb[qd][ty][2 * xp + 1][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.y, 0.f) : dpc_f2(T.y, S.y);
+  *reinterpret_cast<float2*>(&comb[seg][2 * pidx][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.x, 0.f) : dpc_f2(T.x, S.x);
+  *reinterpret_cast<float2*>(&comb[seg][2 * pidx + 1][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.y, 0.f) : dpc_f2(T.y, S.y);
   __syncthreads();
-  if (qd == 0) {
+  if (seg == 0) {
     float2 out;
     if (a.mode == DPC_PROJ_MAX) {
       out = mx;
 #pragma unroll
       for (int q = 1; q < 4; ++q) {
-        out.x = fmaxf(out.x, comb[q][ty][2 * xp][0]);
-        out.y = fmaxf(out.y, comb[q][ty][2 * xp + 1][0]);
+        out.x = fmaxf(out.x, comb[q][2 * pidx][0]);
+        out.y = fmaxf(out.y, comb[q][2 * pidx + 1][0]);
       }
     } else {
-      float r0 = comb[3][ty][2 * xp][1], r1 = comb[3][ty][2 * xp + 1][1];
+      float r0 = comb[3][2 * pidx][1], r1 = comb[3][2 * pidx + 1][1];
 #pragma unroll
       for (int q = 2; q >= 0; --q) {
-        r0 = fmaf(comb[q][ty][2 * xp][0], r0, comb[q][ty][2 * xp][1]);
-        r1 = fmaf(comb[q][ty][2 * xp + 1][0], r1, comb[q][ty][2 * xp + 1][1]);
+        r0 = fmaf(comb[q][2 * pidx][0], r0, comb[q][2 * pidx][1]);
+        r1 = fmaf(comb[q][2 * pidx + 1][0], r1, comb[q][2 * pidx + 1][1]);
       }
       out = dpc_f2(r0, r1);
     }
@@ -452,23 +470,23 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
   }
 }
 
-// Lean backward (training configuration: DRC silhouette gradient only, occupancy scale present):
-// 2-row tiles like the forward.  Thread = (depth half, row, x): the product over a ray is split in
-// two 32-level halves exchanged through smem, after which every level's gradient is independent
-// (quotient form, see dpc_conv_z64_bwd_kernel).  Then warp = (row, depth quarter) for the
-// transposed correlation.
-template <int K, int MINB>
+// Lean backward (training configuration: DRC silhouette gradient only, occupancy scale present),
+// V = Vz in {32, 64, 128}, same 128-ray tiles as the forward.  Thread = (depth half, ray): the
+// product over a ray is split in two halves exchanged through smem, after which every level's
+// gradient is independent (quotient form, see dpc_conv_z64_bwd_kernel).  Then 4 depth segments x 64
+// ray pairs for the transposed correlation.
+template <int V, int K, int MINB>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(DPC_ZF_THREADS, MINB)
 #else
 static void
 #endif
-dpc_conv_z64_bwd_lean_kernel(DpcConvZBwdArgs a) {
-  constexpr int V = DPC_F64_V, Vz = DPC_F64_V, TY = DPC_ZFW_TY, RW = TY * V;
-  DPC_DYN_SMEM(float, tile);                // [Vz][TY][V]: forward voxels, overwritten by dL/d(smoothed)
+dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
+  constexpr int Vz = V, TY = 128 / V, RW = 128, CPS = Vz / 32, NW = Vz / 32, HL = Vz / 2;
+  DPC_DYN_SMEM(float, tile);                // [Vz][128]: forward voxels, overwritten by dL/d(smoothed)
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(8) float2 tzd[K];
-  __shared__ float pp[2][TY * V];
+  __shared__ float pp[2][128];
   __shared__ float red[DPC_ZF_THREADS / 32];
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
@@ -480,17 +498,17 @@ dpc_conv_z64_bwd_lean_kernel(DpcConvZBwdArgs a) {
   const float s = a.scale[b];
   const float inv_s = (s != 0.0f) ? 1.0f / s : 0.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
-  const int h = tid >> 7, rx = tid & 127;            // depth half, (row, x) within the tile
-  const int ty = rx >> 6, x = rx & 63, y = y0 + ty;
+  const int h = tid >> 7, rx = tid & 127;            // depth half, ray within the tile
+  const int ty = rx / V, x = rx % V, y = y0 + ty;
   const int yo = a.flip_y ? (V - 1 - y) : y;
   const float gp = a.g_proj[((size_t)b * V + yo) * V + x];
-  uint32_t wbits = a.mask2[(((size_t)b * V + y) * V + x) * 2 + h];
-  float* col = tile + (size_t)(32 * h) * RW + rx;
+  const uint32_t* mrow = a.mask2 + (((size_t)b * V + y) * V + x) * NW;
+  float* col = tile + (size_t)(HL * h) * RW + rx;
   dpc_mbar_wait(&bar, 0);
   {
     float T0 = 1.0f, T1 = 1.0f, T2 = 1.0f, T3 = 1.0f;
 #pragma unroll 4
-    for (int z = 0; z < 32; z += 4) {
+    for (int z = 0; z < HL; z += 4) {
       T0 *= 1.0f - fminf(fmaxf(col[(z + 0) * RW], D.lo), D.hi);
       T1 *= 1.0f - fminf(fmaxf(col[(z + 1) * RW], D.lo), D.hi);
       T2 *= 1.0f - fminf(fmaxf(col[(z + 2) * RW], D.lo), D.hi);
@@ -501,34 +519,37 @@ dpc_conv_z64_bwd_lean_kernel(DpcConvZBwdArgs a) {
   __syncthreads();
   const float gT = gp * (pp[0][rx] * pp[1][rx]);
   float dsv = 0.0f;
+  constexpr int NB = HL < 32 ? HL : 32;              // levels served by one mask word
+#pragma unroll 1
+  for (int zb = 0; zb < HL; zb += NB) {
+    const int zg = HL * h + zb;                       // global depth level of this block
+    uint32_t wbits = mrow[zg >> 5] >> (zg & 31);
 #pragma unroll 8
-  for (int zz = 0; zz < 32; ++zz) {
-    const float v = col[zz * RW];
-    const float u = fminf(fmaxf(v, D.lo), D.hi);
-    float dv = __fdividef(gT, 1.0f - u);
-    if (zz == 0 && h == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
-    if ((u != v) || !(wbits & 1u)) dv = 0.0f;
-    wbits >>= 1;
-    dsv = fmaf(dv, v, dsv);
-    col[zz * RW] = dv * s;
+    for (int zz = 0; zz < NB; ++zz) {
+      const float v = col[(zb + zz) * RW];
+      const float u = fminf(fmaxf(v, D.lo), D.hi);
+      float dv = __fdividef(gT, 1.0f - u);
+      if (zg + zz == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
+      if ((u != v) || !(wbits & 1u)) dv = 0.0f;
+      wbits >>= 1;
+      dsv = fmaf(dv, v, dsv);
+      col[(zb + zz) * RW] = dv * s;
+    }
   }
   const float ds = dsv * inv_s;
   __syncthreads();
   {
-    const int w = tid >> 5, xp = tid & 31;
-    const int wy = w >> 2, qd = w & 3, yy = y0 + wy;
-    const float* c2 = tile + wy * V + 2 * xp;
+    const int seg = tid >> 6, pidx = tid & 63;
+    const int wy = pidx / (V / 2), xp = pidx % (V / 2), yy = y0 + wy;
+    const float* c2 = tile + 2 * pidx;
     float* dout = a.d_in + ((size_t)b * Vz * V + yy) * V + 2 * xp;
-    float2 tt[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) tt[j] = tzd[j];
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int zc = (2 * qd + c) * 8;
+    for (int c = 0; c < CPS; ++c) {
+      const int zc = (CPS * seg + c) * 8;
       float2 acc[8];
 #pragma unroll
       for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      dpc_col_conv_pairs<K, 8>(c2, RW, zc, Vz, tt, acc);
+      dpc_col_conv_pairs<K, 8>(c2, RW, zc, Vz, tzd, acc);
 #pragma unroll
       for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(dout + (size_t)(zc + o) * V * V) = acc[o];
     }
@@ -546,37 +567,63 @@ dpc_conv_z64_bwd_lean_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
-static int dpc_z_minblocks = 4;    // experiment knob (dpc_debug_set key 4): resident CTAs/SM the conv_z kernels are compiled for
 static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256 | 128 threads per conv_xy CTA
 
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
 
 static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, int ply) {
-  return V == 64 && Kx == Ky && dpc_fast_k(Kx) && plx == (Kx - 1) / 2 && ply == (Ky - 1) / 2;
+  return (V == 128 || V == 64 || V == 32) && Kx == Ky && dpc_fast_k(Kx) && plx == (Kx - 1) / 2 && ply == (Ky - 1) / 2;
+}
+
+template <int V, int K, int NT>
+static inline int dpc_conv_xy_fast_go(const DpcConvXY64Args& a, void* stream) {
+  constexpr int S = V + 4, MR = (V == 32) ? 128 : V, AR = (V == 128) ? 64 : MR;
+  const size_t smem = (size_t)(AR + MR) * S * sizeof(float);
+#ifndef DPC_EMU
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(dpc_conv_xy_fast_kernel<V, K, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return DPC_ERR_CUDA;
+#endif
+  DPC_LAUNCH((dpc_conv_xy_fast_kernel<V, K, NT>), dim3(a.nslices), dim3(NT), smem, stream, a);
+  return DPC_OK;
 }
 
 static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const float* taps_x, const float* taps_y, int K,
                                           int B, int Vz, int V, int clip_in, uint32_t* mask_out, const uint32_t* mask_in,
                                           int rev, float* zero_ptr, void* stream) {
-  (void)V;
   if ((((uintptr_t)in) & 15u) || (((uintptr_t)out) & 7u)) return DPC_ERR_ARG;
+  const int64_t voxels = (int64_t)B * Vz * V * V;
+  const int unit = (V == 128) ? 16384 : 4096;
+  if (voxels % unit != 0) return DPC_ERR_SHAPE;     // V=32 needs B*Vz to be a multiple of 4
   DpcConvXY64Args a;
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
-  a.nslices = B * Vz; a.rev = rev; a.zero_ptr = zero_ptr;
+  a.nslices = (int)(voxels / unit); a.rev = rev; a.zero_ptr = zero_ptr;
   const bool small = dpc_xy_threads == 128;
-  if (K == 21) {
-    if (small) { DPC_LAUNCH((dpc_conv_xy64_kernel<21, 128>), dim3(a.nslices), dim3(128), 0, stream, a); }
-    else { DPC_LAUNCH((dpc_conv_xy64_kernel<21, 256>), dim3(a.nslices), dim3(256), 0, stream, a); }
-  } else {
-    if (small) { DPC_LAUNCH((dpc_conv_xy64_kernel<11, 128>), dim3(a.nslices), dim3(128), 0, stream, a); }
-    else { DPC_LAUNCH((dpc_conv_xy64_kernel<11, 256>), dim3(a.nslices), dim3(256), 0, stream, a); }
+  if (V == 64) {
+    if (K == 21) return small ? dpc_conv_xy_fast_go<64, 21, 128>(a, stream) : dpc_conv_xy_fast_go<64, 21, 256>(a, stream);
+    return small ? dpc_conv_xy_fast_go<64, 11, 128>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256>(a, stream);
   }
-  return DPC_OK;
+  if (V == 32) return K == 21 ? dpc_conv_xy_fast_go<32, 21, 256>(a, stream) : dpc_conv_xy_fast_go<32, 11, 256>(a, stream);
+  return K == 21 ? dpc_conv_xy_fast_go<128, 21, 256>(a, stream) : dpc_conv_xy_fast_go<128, 11, 256>(a, stream);
 }
 
 // `extras`: drc_probs / proj_depth outputs (forward) or their gradients (backward) requested
+static inline bool dpc_fast_v(int V) { return V == 32 || V == 64 || V == 128; }
 static inline bool dpc_conv_z_fast_supported(int V, int Vz, int Kz, int plz, bool extras) {
-  return V == 64 && Vz == 64 && dpc_fast_k(Kz) && plz == (Kz - 1) / 2 && !extras;
+  return dpc_fast_v(V) && Vz == V && dpc_fast_k(Kz) && plz == (Kz - 1) / 2 && !extras;
+}
+
+template <int V, int K>
+static inline int dpc_conv_z_fwd_fast_go(const DpcConvZArgs& a, int B, void* stream) {
+  constexpr int MINB = (V == 128) ? 3 : 4;
+  const size_t smem = (size_t)V * 128 * sizeof(float);
+#ifndef DPC_EMU
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(dpc_conv_z_fast_fwd_kernel<V, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return DPC_ERR_CUDA;
+#endif
+  DPC_LAUNCH((dpc_conv_z_fast_fwd_kernel<V, K, MINB>), dim3(V / (128 / V), B), dim3(DPC_ZF_THREADS), smem, stream, a);
+  return DPC_OK;
 }
 
 static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_z, int Kz, const float* scale, int mode,
@@ -585,18 +632,23 @@ static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_
                                              void* stream) {
   DpcConvZArgs a;
   a.in = in; a.taps = taps_z; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = eps;
-  a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZFW_TY;
+  a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = 128 / V;
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = probs; a.depth = depth;
-  const size_t smem = (size_t)Vz * DPC_ZFW_TY * V * sizeof(float);
-  dim3 grid(V / DPC_ZFW_TY, B), block(DPC_ZF_THREADS);
-  const bool b3 = dpc_z_minblocks == 3;
-  if (Kz == 21) {
-    if (b3) { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<21, 3>), grid, block, smem, stream, a); }
-    else { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<21, 4>), grid, block, smem, stream, a); }
-  } else {
-    if (b3) { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<11, 3>), grid, block, smem, stream, a); }
-    else { DPC_LAUNCH((dpc_conv_z64_fwd_kernel<11, 4>), grid, block, smem, stream, a); }
-  }
+  if (V == 32) return Kz == 21 ? dpc_conv_z_fwd_fast_go<32, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<32, 11>(a, B, stream);
+  if (V == 64) return Kz == 21 ? dpc_conv_z_fwd_fast_go<64, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<64, 11>(a, B, stream);
+  return Kz == 21 ? dpc_conv_z_fwd_fast_go<128, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<128, 11>(a, B, stream);
+}
+
+template <int V, int K>
+static inline int dpc_conv_z_bwd_lean_go(const DpcConvZBwdArgs& a, int B, void* stream) {
+  constexpr int MINB = (V == 128) ? 3 : 4;
+  const size_t smem = (size_t)V * 128 * sizeof(float);
+#ifndef DPC_EMU
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(dpc_conv_z_fast_bwd_lean_kernel<V, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return DPC_ERR_CUDA;
+#endif
+  DPC_LAUNCH((dpc_conv_z_fast_bwd_lean_kernel<V, K, MINB>), dim3(V / (128 / V), B), dim3(DPC_ZF_THREADS), smem, stream, a);
   return DPC_OK;
 }
 
@@ -610,22 +662,15 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
   a.mode = mode; a.eps = eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
   a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;
   a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;
-  const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
-  dim3 grid(V / DPC_ZF_TY, B), block(DPC_ZF_THREADS);
   const bool lean = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
   if (lean) {
-    const size_t smem2 = (size_t)Vz * DPC_ZFW_TY * V * sizeof(float);
-    dim3 grid2(V / DPC_ZFW_TY, B);
-    const bool b3 = dpc_z_minblocks == 3;
-    if (Kz == 21) {
-      if (b3) { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<21, 3>), grid2, block, smem2, stream, a); }
-      else { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<21, 4>), grid2, block, smem2, stream, a); }
-    } else {
-      if (b3) { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<11, 3>), grid2, block, smem2, stream, a); }
-      else { DPC_LAUNCH((dpc_conv_z64_bwd_lean_kernel<11, 4>), grid2, block, smem2, stream, a); }
-    }
-    return DPC_OK;
+    if (V == 32) return Kz == 21 ? dpc_conv_z_bwd_lean_go<32, 21>(a, B, stream) : dpc_conv_z_bwd_lean_go<32, 11>(a, B, stream);
+    if (V == 64) return Kz == 21 ? dpc_conv_z_bwd_lean_go<64, 21>(a, B, stream) : dpc_conv_z_bwd_lean_go<64, 11>(a, B, stream);
+    return Kz == 21 ? dpc_conv_z_bwd_lean_go<128, 21>(a, B, stream) : dpc_conv_z_bwd_lean_go<128, 11>(a, B, stream);
   }
+  if (V != 64) return DPC_ERR_ARG;   // caller falls back to the generic kernel (see dpc_conv_z_bwd_fast_general_ok)
+  const size_t smem = (size_t)Vz * DPC_ZF_TY * V * sizeof(float);
+  dim3 grid(V / DPC_ZF_TY, B), block(DPC_ZF_THREADS);
 #ifndef DPC_EMU
 #define DPC_ZB_LAUNCH(KK, LL) do { \
     if (cudaFuncSetAttribute(dpc_conv_z64_bwd_kernel<KK, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DPC_ERR_CUDA; \
@@ -637,3 +682,6 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
 #undef DPC_ZB_LAUNCH
   return DPC_OK;
 }
+
+// the non-lean fast backward exists for the 64^3 grid only
+static inline bool dpc_conv_z_bwd_fast_general_ok(int V) { return V == 64; }

@@ -16,7 +16,7 @@ class Product:
     pointcloud_project_fast = staticmethod(pcm.pointcloud_project_fast)
 
 
-SMALL = [n for n in cases.golden_names() if n not in ("cfg1_drc_k21_sigma3",)]
+SMALL = cases.golden_names()
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -49,3 +49,30 @@ def test_conv_xy_128_thread_variant(emu):  # noqa: F811
             cases.assert_parity(fx, outs, grads)
     finally:
         emu.dpc_debug_set(2, 256)
+
+
+@pytest.mark.parametrize("v,k", [(128, 11), (32, 21)])
+def test_other_grid_sizes_against_oracle(emu, v, k):  # noqa: F811
+    """The 32^3 and 128^3 instantiations of the shape-specialised kernels (BASELINE config 5 shapes)."""
+    import dpc_b200.util.gauss_kernel as gkm
+    from dpc_b200.util.config import default_config
+    from oracle import dpc_oracle as O
+    cfg = default_config(vox_size=v, pc_gauss_kernel_size=k)
+    g = torch.Generator().manual_seed(3)
+    b = 1 if v == 128 else 4
+    pc = torch.tanh(0.5 * torch.randn(b, 300, 3, generator=g)) / 2
+    q = torch.randn(b, 4, generator=g)
+    sc = torch.sigmoid(torch.randn(b, 1, generator=g))
+    gt = (torch.rand(b, v, v, 1, generator=g) > 0.5).float()
+    res = {}
+    for name, mp, mg in (("emu", pcm, gkm), ("oracle", O, O)):
+        a = [x.clone().requires_grad_(True) for x in (pc, q, sc)]
+        out = mp.pointcloud_project_fast(cfg, a[0], a[1], None, None, mg.smoothing_kernel(cfg, torch.tensor(2.0)), a[2])
+        (((gt - out["proj"]) ** 2).sum() / 2 / b).backward()
+        res[name] = (out, [x.grad for x in a])
+    (eo, eg), (oo, og) = res["emu"], res["oracle"]
+    assert torch.equal(eo["tr_pc"], oo["tr_pc"])
+    for key in ("proj", "voxels"):
+        assert float((eo[key].detach() - oo[key].detach()).abs().max()) <= 1e-5
+    for x, y in zip(eg, og):
+        assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max()))

@@ -133,6 +133,33 @@ def test_max_projection_full_shape():
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
 
 
+@pytest.mark.parametrize("v,n,b", [(32, 2000, 8), (32, 32000, 4), (128, 2000, 2), (64, 16000, 2)])
+def test_sweep_shapes_against_oracle(v, n, b):
+    """BASELINE config 5 shapes (N in 2k..32k, V in 32/64/128) against the oracle."""
+    cfg = default_config(vox_size=v, pc_gauss_kernel_size=21)
+    g = torch.Generator().manual_seed(77)
+    pc = torch.tanh(0.5 * torch.randn(b, n, 3, generator=g)) / 2
+    q = torch.randn(b, 4, generator=g)
+    sc = torch.sigmoid(torch.randn(b, 1, generator=g))
+    gt = (torch.rand(b, v, v, 1, generator=g) > 0.5).float()
+    _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
+
+
+def test_transform_bit_exact_on_a_million_points():
+    """The branch-free division of the camera transform (dpc_math.cuh: dpc_div) against IEEE division
+    in the oracle, with translation and per-sample focal length: every bit of every coordinate."""
+    cfg = default_config()
+    g = torch.Generator().manual_seed(5)
+    pc = torch.tanh(0.6 * torch.randn(32, 32768, 3, generator=g)) / 2
+    q = torch.randn(32, 4, generator=g)
+    tr = 0.05 * torch.randn(32, 3, generator=g)
+    fl = 1.875 + 0.2 * torch.randn(32, 1, generator=g)
+    a = pcm.pc_perspective_transform(cfg, pc.to(DEV), q.to(DEV), tr.to(DEV), fl.to(DEV)).cpu()
+    assert torch.equal(a, O.pc_perspective_transform(cfg, pc, q, tr, fl))
+    a = pcm.pc_perspective_transform(cfg, pc.to(DEV), q.to(DEV)).cpu()
+    assert torch.equal(a, O.pc_perspective_transform(cfg, pc, q))
+
+
 def test_properties_at_b32_n8000_v64():
     """Size-independent checks at BASELINE's full size (the oracle is too slow here to be the
     checker for every run): mass conservation, range, determinism of the index path, zero
