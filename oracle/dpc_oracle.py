@@ -46,12 +46,22 @@ def _hamilton(a, b):
     return torch.stack((w, x, y, z), dim=-1)
 
 
+def _sqrt_rn(x):
+    """Correctly rounded square root.  torch's CPU float32 sqrt is NOT IEEE-exact on this build (about
+    0.7% of inputs are off by one ulp; found when a whole sample's tr_pc disagreed with the GPU's
+    sqrt.rn); TensorFlow/Eigen use the hardware sqrtps, which is.  sqrt in float64 followed by one
+    rounding to float32 is exact (53 >= 2*24+2)."""
+    if x.dtype == torch.float32:
+        return torch.sqrt(x.double()).float()
+    return torch.sqrt(x)
+
+
 def quaternion_rotate(pc, q):
     """q * (0,p) * conj(q) with q normalised first (quaternion.py:96-117).
     |q| = sqrt(((q0^2+q1^2)+q2^2)+q3^2): squares summed left to right -- this order
     DEFINES parity for tf.norm."""
     sq = q * q
-    nrm = torch.sqrt(sq[..., 0] + sq[..., 1] + sq[..., 2] + sq[..., 3]).unsqueeze(-1)
+    nrm = _sqrt_rn(sq[..., 0] + sq[..., 1] + sq[..., 2] + sq[..., 3]).unsqueeze(-1)
     qn = (q / nrm).unsqueeze(1)  # [B,1,4]
     conj = qn * torch.tensor([1.0, -1.0, -1.0, -1.0], dtype=q.dtype)
     p4 = F.pad(pc, (1, 0))  # (0, x, y, z)  quaternion.py:45

@@ -304,9 +304,15 @@ def _bi(fn):
     return f
 
 
+def _sqrt_rn(t):
+    # torch's CPU float32 sqrt is not correctly rounded (off by one ulp for ~0.7% of inputs);
+    # TF/Eigen use sqrtps (IEEE).  float64 sqrt + one rounding is exact for float32.
+    return torch.sqrt(t.double()).float() if t.dtype == torch.float32 else torch.sqrt(t)
+
+
 exp = _un(torch.exp)
 log = _un(torch.log)
-sqrt = _un(torch.sqrt)
+sqrt = _un(_sqrt_rn)
 square = _un(torch.square)
 floor = _un(torch.floor)
 sigmoid = _un(torch.sigmoid)
@@ -367,7 +373,7 @@ def norm(x, axis=None, keepdims=False):
     s = parts[0]
     for p in parts[1:]:
         s = s + p
-    r = torch.sqrt(s)
+    r = _sqrt_rn(s)
     if keepdims:
         r = r.unsqueeze(int(axis))
     return Tensor(r)
