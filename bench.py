@@ -324,6 +324,87 @@ def e2e_pipelined(pipe, steps):
     return dt, loss
 
 
+def e2e_graphed(pipe, steps):
+    """As e2e_pipelined, but the step a user builds with the public API (pointcloud_project_fast ->
+    loss -> autograd) is captured once per buffer set in a CUDA graph and replayed: the ~25 small
+    launches and the Python/autograd time of a step collapse into one graph launch, which is what
+    bounds the eager path (the GPU work is ~0.14 ms, the eager host time ~0.5 ms)."""
+    from dpc_b200.util import point_cloud as pcm
+    dev = pipe.dev
+    if not hasattr(pipe, "h_in"):
+        pipe._e2e_setup()
+    s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    d_in = [torch.empty_like(pipe.d_in) for _ in range(2)]
+    d_out = [torch.empty_like(pipe.d_out) for _ in range(2)]
+    h_out = [torch.empty_like(pipe.h_out).pin_memory() for _ in range(2)]
+    for k in range(2):
+        d_in[k].copy_(pipe.h_in)
+
+    def step_fn(k):
+        parts = torch.split(d_in[k], pipe.in_sizes)
+        pc, q, sc, gt = [p.reshape(sh) for p, sh in zip(parts, pipe.in_shapes)]
+        pc, q, sc = pc.detach().requires_grad_(True), q.detach().requires_grad_(True), sc.detach().requires_grad_(True)
+        out = pcm.pointcloud_project_fast(pipe.cfg, pc, q, None, None, pipe.kernel, sc)
+        l = ((gt - out["proj"]) ** 2).sum() / 2 / B
+        gpc, gq, gsc = torch.autograd.grad(l, (pc, q, sc))
+        for d, t in zip(torch.split(d_out[k], pipe.out_sizes), (l.detach(), out["proj"].detach(), gpc, gq, gsc)):
+            d.copy_(t.reshape(-1))
+
+    graphs = []
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s_cmp):
+        for _ in range(3):
+            step_fn(0)
+            step_fn(1)
+    torch.cuda.synchronize()
+    for k in range(2):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s_cmp):
+            step_fn(k)
+        graphs.append(g)
+    torch.cuda.synchronize()
+
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    for k in range(2):
+        ev_free[k].record(s_cmp)
+        ev_out[k].record(s_out)
+    torch.cuda.synchronize()
+
+    def h2d(i):
+        k = i & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[k])
+            d_in[k].copy_(pipe.h_in, non_blocking=True)
+            ev_in[k].record(s_in)
+
+    t0 = time.perf_counter()
+    h2d(0)
+    for i in range(steps):
+        k = i & 1
+        if i + 1 < steps:
+            h2d(i + 1)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[k])
+            s_cmp.wait_event(ev_out[k])
+            graphs[k].replay()
+            ev_free[k].record(s_cmp)
+            ev_cmp[k].record(s_cmp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp[k])
+            h_out[k].copy_(d_out[k], non_blocking=True)
+            ev_out[k].record(s_out)
+        if i >= 1:
+            ev_out[(i - 1) & 1].synchronize()
+    ev_out[(steps - 1) & 1].synchronize()
+    loss = float(h_out[(steps - 1) & 1][0])
+    dt = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    return dt, loss
+
+
 def run_ours(args, rank, local_rank, world):
     from dpc_b200 import distributed as D
     if not torch.cuda.is_available():
@@ -375,6 +456,21 @@ def run_ours(args, rank, local_rank, world):
     t_pipe = D.reduce_scalar(t_pipe, "max", dev)
     e2e_value = world * B * n_e2e / t_pipe
     t_e2e_serial, t_e2e = t_e2e, t_pipe
+    e2e_mode = "eager API calls; copies of neighbouring steps overlap compute (3 streams, double buffered)"
+    e2e_eager = e2e_value
+    try:
+        n_g = max(n_e2e, 100)
+        e2e_graphed(pipe, 10)
+        D.barrier()
+        t_g, loss_g = e2e_graphed(pipe, n_g)
+        t_g = D.reduce_scalar(t_g, "max", dev)
+        if abs(loss_g - loss) <= 1e-3 * max(1.0, abs(loss)):
+            e2e_value, t_e2e, n_e2e_used = world * B * n_g / t_g, t_g, n_g
+            e2e_mode = ("the API-built step (pointcloud_project_fast -> loss -> autograd) captured in a CUDA graph and "
+                        "replayed; H2D/D2H of neighbouring steps overlap compute (3 streams, double buffered)")
+            n_e2e = n_g
+    except Exception as exc:  # capture not possible: keep the eager number
+        print("graph capture failed: %r" % (exc,), file=sys.stderr)
 
     line = None
     if rank == 0:
@@ -402,7 +498,7 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * t_e2e / n_e2e, "loss": loss,
-                    "mode": "copies of neighbouring steps overlap compute (3 streams, double buffered)",
+                    "mode": e2e_mode, "eager_pipelined_value": e2e_eager,
                     "serial_value": e2e_serial, "serial_ms_per_step": 1000.0 * t_e2e_serial / n_e2e},
             "gpu_launches": Pipeline.LAUNCHES_PER_STEP * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
