@@ -51,9 +51,11 @@ struct DpcConvXY64Args {
 // input rows need only half a slice of smem), the y pass on the whole unit.
 // NT = threads per CTA: 256 (one task per thread and phase) or 128 (two tasks per thread and
 // phase, twice as many independent CTAs resident per SM to overlap load / barrier bubbles).
-template <int V, int K, int NT>
+// TS = tap pairs of the x pass read from smem at each use instead of being held in 44 registers:
+// the kernel then fits 64 registers and a fourth CTA per SM.
+template <int V, int K, int NT, bool TS>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(NT, 768 / NT)
+__global__ void __launch_bounds__(NT, (TS ? 1024 : 768) / NT)
 #else
 static void
 #endif
@@ -125,10 +127,12 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
     const int y = task % AR, r = task / AR;
     const int x0 = r * 16;
     // tap pairs (t[a], t[a+1]), a = -1..K-1, index q = a+1: aligned float2 in E for even q, in O for odd q
-    float2 tp[K + 1];
+    float2 tp[TS ? 1 : K + 1];
+    if (!TS) {
 #pragma unroll
-    for (int q = 0; q < K + 1; ++q)
-      tp[q] = (q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1)) : *reinterpret_cast<const float2*>(txe + q);
+      for (int q = 0; q < K + 1; ++q)
+        tp[TS ? 0 : q] = (q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1)) : *reinterpret_cast<const float2*>(txe + q);
+    }
     float2 acc[16];
 #pragma unroll
     for (int o = 0; o < 16; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
@@ -144,8 +148,14 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
         // window pair index i = 4g + 2h; for output o the first tap of the pair is a = i - o - WL + PL
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
-          if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1)
-            acc[o] = dpc_ffma2(w, tp[4 * g + 2 * h - o - WL + PL + 1], acc[o]);
+          if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1) {
+            constexpr int dummy = 0; (void)dummy;
+            const int q = 4 * g + 2 * h - o - WL + PL + 1;   // compile-time after unrolling
+            const float2 tq = TS ? ((q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1))
+                                            : *reinterpret_cast<const float2*>(txe + q))
+                                 : tp[TS ? 0 : q];
+            acc[o] = dpc_ffma2(w, tq, acc[o]);
+          }
         }
       }
     }
@@ -567,6 +577,7 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
+static int dpc_xy_taps_smem = 0;   // experiment knob (dpc_debug_set key 5)
 static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256 | 128 threads per conv_xy CTA
 
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
@@ -575,16 +586,16 @@ static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, in
   return (V == 128 || V == 64 || V == 32) && Kx == Ky && dpc_fast_k(Kx) && plx == (Kx - 1) / 2 && ply == (Ky - 1) / 2;
 }
 
-template <int V, int K, int NT>
+template <int V, int K, int NT, bool TS = false>
 static inline int dpc_conv_xy_fast_go(const DpcConvXY64Args& a, void* stream) {
   constexpr int S = V + 4, MR = (V == 32) ? 128 : V, AR = (V == 128) ? 64 : MR;
   const size_t smem = (size_t)(AR + MR) * S * sizeof(float);
 #ifndef DPC_EMU
   if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(dpc_conv_xy_fast_kernel<V, K, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      cudaFuncSetAttribute(dpc_conv_xy_fast_kernel<V, K, NT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return DPC_ERR_CUDA;
 #endif
-  DPC_LAUNCH((dpc_conv_xy_fast_kernel<V, K, NT>), dim3(a.nslices), dim3(NT), smem, stream, a);
+  DPC_LAUNCH((dpc_conv_xy_fast_kernel<V, K, NT, TS>), dim3(a.nslices), dim3(NT), smem, stream, a);
   return DPC_OK;
 }
 
@@ -600,6 +611,7 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   a.nslices = (int)(voxels / unit); a.rev = rev; a.zero_ptr = zero_ptr;
   const bool small = dpc_xy_threads == 128;
   if (V == 64) {
+    if (K == 21 && dpc_xy_taps_smem) return dpc_conv_xy_fast_go<64, 21, 256, true>(a, stream);
     if (K == 21) return small ? dpc_conv_xy_fast_go<64, 21, 128>(a, stream) : dpc_conv_xy_fast_go<64, 21, 256>(a, stream);
     return small ? dpc_conv_xy_fast_go<64, 11, 128>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256>(a, stream);
   }
