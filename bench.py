@@ -562,7 +562,7 @@ def run_train(args, rank, local_rank, world):
 
 
 def main():
-    os.environ["NCCL_DEBUG"] = os.environ.get("DPC_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner must not share stdout with the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="projection", choices=["projection", "train_supervised", "train_unsupervised"])
     ap.add_argument("--objects-per-rank", type=int, default=0)
