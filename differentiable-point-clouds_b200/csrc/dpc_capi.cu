@@ -62,7 +62,7 @@ int dpc_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return DPC_ERR_ARG;
   g_tune[key] = value;
   if (key == 2) dpc_xy_threads = (value == 128) ? 128 : 256;
-  if (key == 5) dpc_xy_taps_smem = value ? 1 : 0;
+  if (key == 5) dpc_xy_taps_smem = value;
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }

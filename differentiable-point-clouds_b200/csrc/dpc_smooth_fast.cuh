@@ -217,6 +217,143 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
 #endif
 }
 
+// ------------------------------------------------------------------------------ conv_xy, persistent (64^3)
+// Same arithmetic as dpc_conv_xy_fast_kernel<64,K,256>, but 3 resident CTAs per SM walk the slices
+// round-robin and the NEXT slice is copied into the other half of a double buffer by the TMA engine
+// (64 row copies issued by the 32 lanes of warp 0, one mbarrier per buffer) while the current one is
+// being correlated, so no warp waits on HBM latency in steady state.  Co-resident CTAs of the
+// one-slice-per-CTA kernel start and stop together, i.e. they all wait on their loads at the same
+// time; here the load is hidden inside each CTA.  The landed slice is clipped (and its clip mask
+// extracted) in place by a short smem pass.
+#define DPC_XYPF_SMEM_BYTES (3 * DPC_F64_V * DPC_F64_S * 4)
+
+template <int K>
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(256, 3)
+#else
+static void
+#endif
+dpc_conv_xy64_pf_kernel(DpcConvXY64Args a) {
+  constexpr int V = DPC_F64_V, S = DPC_F64_S, PL = (K - 1) / 2;
+  constexpr int WL = ((PL + 3) / 4) * 4;
+  constexpr int NW4 = (WL + 16 + WL) / 4;
+  DPC_DYN_SMEM(float, sm);
+  float* Abuf = sm;                                  // [2][V*S]
+  float* M = sm + 2 * V * S;                         // [V*S]
+  __shared__ __align__(8) float txe[24];
+  __shared__ __align__(8) float txo[24];
+  __shared__ __align__(8) float2 tyd[24];
+  __shared__ __align__(8) uint64_t bars[2];
+  const int tid = threadIdx.x;
+  if (tid < 24) {
+    const int a_e = tid - 1, a_o = tid;
+    txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
+    txo[tid] = (a_o >= 0 && a_o < K) ? dpc_tap(a.taps_x, K, a_o, a.rev) : 0.0f;
+    const float tyv = (tid < K) ? dpc_tap(a.taps_y, K, tid, a.rev) : 0.0f;
+    tyd[tid] = dpc_f2(tyv, tyv);
+  }
+  if (tid == 0) { dpc_mbar_init(&bars[0], 1); dpc_mbar_init(&bars[1], 1); }
+  dpc_grid_dep_sync();
+  __syncthreads();
+  int slice = blockIdx.x;
+  if (slice >= a.nslices) return;
+  if (tid < 32) dpc_warp_bulk_rows(Abuf, S, a.in + (size_t)slice * (V * V), V, V, V * 4, &bars[0]);
+
+  for (int it = 0; slice < a.nslices; ++it, slice += gridDim.x) {
+    const int cb = it & 1;
+    float* A = Abuf + cb * (V * S);
+    const int next = slice + gridDim.x;
+    // the other buffer was last read in the x pass of the previous iteration, which every thread left
+    // before that iteration's barriers
+    if (tid < 32 && next < a.nslices)
+      dpc_warp_bulk_rows(Abuf + (cb ^ 1) * (V * S), S, a.in + (size_t)next * (V * V), V, V, V * 4, &bars[cb ^ 1]);
+    dpc_mbar_wait(&bars[cb], (it >> 1) & 1);
+    const size_t sl = (size_t)slice * (V * V);
+
+    // ---- in-place clip + clip-mask bits of the landed slice (each thread its own four float4)
+    if (a.clip_in || a.mask_out) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = tid + 256 * k;            // float4 index in the slice: row = i/16, col4 = i%16
+        float4* p4 = reinterpret_cast<float4*>(&A[(i >> 4) * S + (i & 15) * 4]);
+        float4 v = *p4;
+        if (a.mask_out) {
+          unsigned nib = ((v.x >= 0.0f && v.x <= 1.0f) ? 1u : 0u) | ((v.y >= 0.0f && v.y <= 1.0f) ? 2u : 0u) |
+                         ((v.z >= 0.0f && v.z <= 1.0f) ? 4u : 0u) | ((v.w >= 0.0f && v.w <= 1.0f) ? 8u : 0u);
+          unsigned word = nib << (4 * (tid & 7));
+          word |= __shfl_xor_sync(DPC_FULL, word, 1);
+          word |= __shfl_xor_sync(DPC_FULL, word, 2);
+          word |= __shfl_xor_sync(DPC_FULL, word, 4);
+          if ((tid & 7) == 0) a.mask_out[(sl >> 5) + (i >> 3)] = word;
+        }
+        if (a.clip_in) {
+          v.x = dpc_clip01(v.x); v.y = dpc_clip01(v.y); v.z = dpc_clip01(v.z); v.w = dpc_clip01(v.w);
+          *p4 = v;
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- x correlation.  Thread = (row y, run r of 16 outputs); a warp = 32 rows, one r.
+    {
+      const int y = tid & 63, r = tid >> 6;
+      const int x0 = r * 16;
+      float2 tp[K + 1];
+#pragma unroll
+      for (int q = 0; q < K + 1; ++q)
+        tp[q] = (q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1)) : *reinterpret_cast<const float2*>(txe + q);
+      float2 acc[16];
+#pragma unroll
+      for (int o = 0; o < 16; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+      const float* rowp = A + y * S;
+#pragma unroll
+      for (int g = 0; g < NW4; ++g) {
+        const int xs = x0 - WL + 4 * g;
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xs >= 0 && xs < V) w4 = *reinterpret_cast<const float4*>(rowp + xs);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 w = h ? dpc_f2(w4.z, w4.w) : dpc_f2(w4.x, w4.y);
+#pragma unroll
+          for (int o = 0; o < 16; ++o) {
+            if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1)
+              acc[o] = dpc_ffma2(w, tp[4 * g + 2 * h - o - WL + PL + 1], acc[o]);
+          }
+        }
+      }
+      float* dst = M + y * S + x0;
+#pragma unroll
+      for (int o = 0; o < 16; o += 4) {
+        *reinterpret_cast<float4*>(dst + o) = make_float4(acc[o].x + acc[o].y, acc[o + 1].x + acc[o + 1].y,
+                                                           acc[o + 2].x + acc[o + 2].y, acc[o + 3].x + acc[o + 3].y);
+      }
+    }
+    __syncthreads();
+
+    // ---- y correlation.  Thread = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
+    {
+      const int xp = tid & 31, y0 = (tid >> 5) * 8;
+      float2 acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
+      dpc_col_conv_pairs<K, 8>(M + 2 * xp, S, y0, V, tyd, acc);
+      float* dst = a.out + sl + (size_t)y0 * V + 2 * xp;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        float2 v = acc[o];
+        if (a.mask_in) {
+          const size_t e = sl + (size_t)(y0 + o) * V + 2 * xp;
+          const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
+          if (!(wbits & 1u)) v.x = 0.0f;
+          if (!(wbits & 2u)) v.y = 0.0f;
+        }
+        *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
+      }
+    }
+    __syncthreads();   // M (and this iteration's A) are free
+  }
+}
+
 // ------------------------------------------------------------------------------ conv_z, V = Vz = 64
 // CTA = 4 image rows x all 64 depth levels (64 KiB tile, TMA bulk loads), 256 threads = 8 warps.
 // Warp w works on image row w>>1 and on depth half w&1 (levels 32h .. 32h+31): the correlation has
@@ -260,7 +397,9 @@ dpc_conv_z_fast_fwd_kernel(DpcConvZArgs a) {
 
   const int seg = tid >> 6, pidx = tid & 63;              // depth segment, ray pair within the CTA
   const int ty = pidx / (V / 2), xp = pidx % (V / 2), y = y0 + ty;
-  const float2* tt = tzd;
+  float2 tt[K];                                   // taps in registers: measured 3 us faster than reading smem per FFMA2
+#pragma unroll
+  for (int j = 0; j < K; ++j) tt[j] = tzd[j];
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
@@ -553,13 +692,16 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
     const int wy = pidx / (V / 2), xp = pidx % (V / 2), yy = y0 + wy;
     const float* c2 = tile + 2 * pidx;
     float* dout = a.d_in + ((size_t)b * Vz * V + yy) * V + 2 * xp;
+    float2 tt[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) tt[j] = tzd[j];
 #pragma unroll 1
     for (int c = 0; c < CPS; ++c) {
       const int zc = (CPS * seg + c) * 8;
       float2 acc[8];
 #pragma unroll
       for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      dpc_col_conv_pairs<K, 8>(c2, RW, zc, Vz, tzd, acc);
+      dpc_col_conv_pairs<K, 8>(c2, RW, zc, Vz, tt, acc);
 #pragma unroll
       for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(dout + (size_t)(zc + o) * V * V) = acc[o];
     }
@@ -610,8 +752,20 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
   a.nslices = (int)(voxels / unit); a.rev = rev; a.zero_ptr = zero_ptr;
   const bool small = dpc_xy_threads == 128;
+  if (V == 64 && dpc_xy_taps_smem == 2 && !zero_ptr) {
+    const int grid = a.nslices < 3 * 148 ? a.nslices : 3 * 148;
+#ifndef DPC_EMU
+    cudaError_t e = (K == 21)
+        ? cudaFuncSetAttribute(dpc_conv_xy64_pf_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XYPF_SMEM_BYTES)
+        : cudaFuncSetAttribute(dpc_conv_xy64_pf_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XYPF_SMEM_BYTES);
+    if (e != cudaSuccess) return DPC_ERR_CUDA;
+#endif
+    if (K == 21) { DPC_LAUNCH(dpc_conv_xy64_pf_kernel<21>, dim3(grid), dim3(256), DPC_XYPF_SMEM_BYTES, stream, a); }
+    else { DPC_LAUNCH(dpc_conv_xy64_pf_kernel<11>, dim3(grid), dim3(256), DPC_XYPF_SMEM_BYTES, stream, a); }
+    return DPC_OK;
+  }
   if (V == 64) {
-    if (K == 21 && dpc_xy_taps_smem) return dpc_conv_xy_fast_go<64, 21, 256, true>(a, stream);
+    if (K == 21 && dpc_xy_taps_smem == 1) return dpc_conv_xy_fast_go<64, 21, 256, true>(a, stream);
     if (K == 21) return small ? dpc_conv_xy_fast_go<64, 21, 128>(a, stream) : dpc_conv_xy_fast_go<64, 21, 256>(a, stream);
     return small ? dpc_conv_xy_fast_go<64, 11, 128>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256>(a, stream);
   }

@@ -21,7 +21,7 @@ def main():
         if clustered:
             pc = bench.make_inputs(bench.B, 0, clustered=True)[0]
             pipe.pc.copy_(pc.to(dev))
-        for zmin in (0, 1):
+        for zmin in (0, 2):
             pipe.L.dpc_debug_set(5, zmin)
             for _ in range(3):
                 pipe.step()

@@ -76,3 +76,27 @@ def test_other_grid_sizes_against_oracle(emu, v, k):  # noqa: F811
         assert float((eo[key].detach() - oo[key].detach()).abs().max()) <= 1e-5
     for x, y in zip(eg, og):
         assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max()))
+
+
+def test_persistent_prefetch_conv_xy(emu):  # noqa: F811
+    """Persistent conv_xy variant (dpc_debug_set(5, 2)): with B=1 every CTA has one slice, so also run a
+    batch of 8 (512 slices on 444 CTAs: some CTAs loop twice through the double-buffered prefetch)."""
+    import dpc_b200.util.gauss_kernel as gkm
+    from dpc_b200.util.config import default_config
+    from oracle import dpc_oracle as O
+    emu.dpc_debug_set(5, 2)
+    try:
+        fx = cases.load_golden("v64_small")
+        outs, grads = cases.run_impl(Product, fx)
+        cases.assert_parity(fx, outs, grads)
+        cfg = default_config(vox_size=64, pc_gauss_kernel_size=11)
+        g = torch.Generator().manual_seed(11)
+        pc = torch.tanh(0.5 * torch.randn(8, 64, 3, generator=g)) / 2
+        q = torch.randn(8, 4, generator=g)
+        sc = torch.sigmoid(torch.randn(8, 1, generator=g))
+        o1 = pcm.pointcloud_project_fast(cfg, pc, q, None, None, gkm.smoothing_kernel(cfg, torch.tensor(1.5)), sc)
+        o2 = O.pointcloud_project_fast(cfg, pc, q, None, None, O.smoothing_kernel(cfg, torch.tensor(1.5)), sc)
+        assert float((o1["voxels"] - o2["voxels"]).abs().max()) <= 1e-5
+        assert float((o1["proj"] - o2["proj"]).abs().max()) <= 1e-5
+    finally:
+        emu.dpc_debug_set(5, 0)
