@@ -217,6 +217,27 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
 #endif
 }
 
+// Alternative tile load: the whole CTA copies nrows x 512 B with 16-byte cp.async (LDGSTS), no TMA op
+// per row.  Returns after the data is visible to every thread.
+static int dpc_z_tile_cpasync = 0;   // experiment knob (dpc_debug_set key 6)
+DPC_DEV void dpc_cta_cpasync_rows(float* dst, const float* src, size_t src_pitch, int nrows) {
+  // rows of 128 floats = 32 chunks of 16 bytes; thread t copies chunk (t & 31) of rows (t >> 5), +8, ...
+  const int ch = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r < nrows; r += (int)(blockDim.x >> 5)) {
+#ifndef DPC_EMU
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (size_t)r * 128 + ch * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t)r * src_pitch + ch * 4) : "memory");
+#else
+    memcpy(dst + (size_t)r * 128 + ch * 4, src + (size_t)r * src_pitch + ch * 4, 16);
+#endif
+  }
+#ifndef DPC_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------ conv_xy, persistent (64^3)
 // Same arithmetic as dpc_conv_xy_fast_kernel<64,K,256>, but 3 resident CTAs per SM walk the slices
 // round-robin and the NEXT slice is copied into the other half of a double buffer by the TMA engine
@@ -225,7 +246,7 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
 // one-slice-per-CTA kernel start and stop together, i.e. they all wait on their loads at the same
 // time; here the load is hidden inside each CTA.  The landed slice is clipped (and its clip mask
 // extracted) in place by a short smem pass.
-#define DPC_XYPF_SMEM_BYTES (3 * DPC_F64_V * DPC_F64_S * 4)
+#define DPC_XYPF_SMEM_BYTES ((2 * DPC_F64_V * DPC_F64_S + 2 * DPC_F64_V * DPC_F64_V) * 4)
 
 template <int K>
 #ifndef DPC_EMU
@@ -238,8 +259,9 @@ dpc_conv_xy64_pf_kernel(DpcConvXY64Args a) {
   constexpr int WL = ((PL + 3) / 4) * 4;
   constexpr int NW4 = (WL + 16 + WL) / 4;
   DPC_DYN_SMEM(float, sm);
-  float* Abuf = sm;                                  // [2][V*S]
-  float* M = sm + 2 * V * S;                         // [V*S]
+  float* Lbuf = sm;                                  // [2][V*V] landing buffers: ONE 16 KiB bulk copy per slice
+  float* A = sm + 2 * V * V;                         // [V*S] padded, clipped copy the x pass reads
+  float* M = A + V * S;                              // [V*S]
   __shared__ __align__(8) float txe[24];
   __shared__ __align__(8) float txo[24];
   __shared__ __align__(8) float2 tyd[24];
@@ -257,26 +279,25 @@ dpc_conv_xy64_pf_kernel(DpcConvXY64Args a) {
   __syncthreads();
   int slice = blockIdx.x;
   if (slice >= a.nslices) return;
-  if (tid < 32) dpc_warp_bulk_rows(Abuf, S, a.in + (size_t)slice * (V * V), V, V, V * 4, &bars[0]);
+  if (tid == 0) dpc_bulk_load(Lbuf, a.in + (size_t)slice * (V * V), V * V * 4, &bars[0]);
 
   for (int it = 0; slice < a.nslices; ++it, slice += gridDim.x) {
     const int cb = it & 1;
-    float* A = Abuf + cb * (V * S);
+    const float* L = Lbuf + cb * (V * V);
     const int next = slice + gridDim.x;
-    // the other buffer was last read in the x pass of the previous iteration, which every thread left
-    // before that iteration's barriers
-    if (tid < 32 && next < a.nslices)
-      dpc_warp_bulk_rows(Abuf + (cb ^ 1) * (V * S), S, a.in + (size_t)next * (V * V), V, V, V * 4, &bars[cb ^ 1]);
+    // the other landing buffer was drained by the copy pass of the previous iteration (barrier after it)
+    if (tid == 0 && next < a.nslices)
+      dpc_bulk_load(Lbuf + (cb ^ 1) * (V * V), a.in + (size_t)next * (V * V), V * V * 4, &bars[cb ^ 1]);
     dpc_mbar_wait(&bars[cb], (it >> 1) & 1);
     const size_t sl = (size_t)slice * (V * V);
 
-    // ---- in-place clip + clip-mask bits of the landed slice (each thread its own four float4)
-    if (a.clip_in || a.mask_out) {
+    // ---- landing buffer -> padded A, with the clip and the clip-mask bits (each thread four float4)
+    {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int i = tid + 256 * k;            // float4 index in the slice: row = i/16, col4 = i%16
         float4* p4 = reinterpret_cast<float4*>(&A[(i >> 4) * S + (i & 15) * 4]);
-        float4 v = *p4;
+        float4 v = reinterpret_cast<const float4*>(L)[i];
         if (a.mask_out) {
           unsigned nib = ((v.x >= 0.0f && v.x <= 1.0f) ? 1u : 0u) | ((v.y >= 0.0f && v.y <= 1.0f) ? 2u : 0u) |
                          ((v.z >= 0.0f && v.z <= 1.0f) ? 4u : 0u) | ((v.w >= 0.0f && v.w <= 1.0f) ? 8u : 0u);
@@ -286,10 +307,8 @@ dpc_conv_xy64_pf_kernel(DpcConvXY64Args a) {
           word |= __shfl_xor_sync(DPC_FULL, word, 4);
           if ((tid & 7) == 0) a.mask_out[(sl >> 5) + (i >> 3)] = word;
         }
-        if (a.clip_in) {
-          v.x = dpc_clip01(v.x); v.y = dpc_clip01(v.y); v.z = dpc_clip01(v.z); v.w = dpc_clip01(v.w);
-          *p4 = v;
-        }
+        if (a.clip_in) { v.x = dpc_clip01(v.x); v.y = dpc_clip01(v.y); v.z = dpc_clip01(v.z); v.w = dpc_clip01(v.w); }
+        *p4 = v;
       }
       __syncthreads();
     }
@@ -391,13 +410,20 @@ dpc_conv_z_fast_fwd_kernel(DpcConvZArgs a) {
   if (tid == 0) dpc_mbar_init(&bar, 1);
   dpc_grid_dep_sync();
   __syncthreads();
-  if (tid < 32) dpc_warp_bulk_rows(tile, RW, src, (size_t)V * V, Vz, RW * 4, &bar);
-  dpc_mbar_wait(&bar, 0);
-  __syncthreads();
+  if (a.TY < 0) {
+    dpc_cta_cpasync_rows(tile, src, (size_t)V * V, Vz);
+  } else {
+    if (tid < 32) dpc_warp_bulk_rows(tile, RW, src, (size_t)V * V, Vz, RW * 4, &bar);
+    dpc_mbar_wait(&bar, 0);
+    __syncthreads();
+  }
 
-  const int seg = tid >> 6, pidx = tid & 63;              // depth segment, ray pair within the CTA
+  // depth segment and ray pair of this thread.  At V = 64 consecutive warps take the four segments of
+  // one image row (measured ~3 us faster per launch than consecutive warps taking the two rows of one segment).
+  const int seg = (V == 64) ? ((tid >> 5) & 3) : (tid >> 6);
+  const int pidx = (V == 64) ? (((tid >> 7) << 5) | (tid & 31)) : (tid & 63);
   const int ty = pidx / (V / 2), xp = pidx % (V / 2), y = y0 + ty;
-  float2 tt[K];                                   // taps in registers: measured 3 us faster than reading smem per FFMA2
+  float2 tt[K];                                   // taps in registers: measured faster than reading smem per FFMA2
 #pragma unroll
   for (int j = 0; j < K; ++j) tt[j] = tzd[j];
   const bool has_s = a.scale != nullptr;
@@ -440,8 +466,9 @@ dpc_conv_z_fast_fwd_kernel(DpcConvZArgs a) {
   if (a.mask2_out && has_s) {
     // per ray NW 32-bit words of clip-pass bits, bit z = depth level z; this thread owns CPS bytes of each ray
     uint8_t* mp = reinterpret_cast<uint8_t*>(a.mask2_out + (((size_t)b * V + y) * V + 2 * xp) * NW) + seg * CPS;
-#pragma unroll
-    for (int c = 0; c < CPS; ++c) { mp[c] = (uint8_t)(m0 >> (8 * c)); mp[4 * NW + c] = (uint8_t)(m1 >> (8 * c)); }
+    if (CPS == 1) { mp[0] = (uint8_t)m0; mp[4 * NW] = (uint8_t)m1; }
+    else if (CPS == 2) { *reinterpret_cast<uint16_t*>(mp) = (uint16_t)m0; *reinterpret_cast<uint16_t*>(mp + 4 * NW) = (uint16_t)m1; }
+    else { *reinterpret_cast<uint32_t*>(mp) = m0; *reinterpret_cast<uint32_t*>(mp + 4 * NW) = m1; }
   }
   if (a.mode == DPC_PROJ_NONE) return;
   *reinterpret_cast<float2*>(&comb[seg][2 * pidx][0]) = (a.mode == DPC_PROJ_MAX) ? dpc_f2(mx.x, 0.f) : dpc_f2(T.x, S.x);
@@ -643,7 +670,9 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
   if (tid == 0) dpc_mbar_init(&bar, 1);
   dpc_grid_dep_sync();
   __syncthreads();
-  if (tid < 32) dpc_warp_bulk_rows(tile, RW, a.vox + ((size_t)b * Vz * V + y0) * V, (size_t)V * V, Vz, RW * 4, &bar);
+  const bool use_cpasync = a.TY < 0;
+  if (use_cpasync) dpc_cta_cpasync_rows(tile, a.vox + ((size_t)b * Vz * V + y0) * V, (size_t)V * V, Vz);
+  else if (tid < 32) dpc_warp_bulk_rows(tile, RW, a.vox + ((size_t)b * Vz * V + y0) * V, (size_t)V * V, Vz, RW * 4, &bar);
   const float s = a.scale[b];
   const float inv_s = (s != 0.0f) ? 1.0f / s : 0.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
@@ -653,7 +682,7 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
   const float gp = a.g_proj[((size_t)b * V + yo) * V + x];
   const uint32_t* mrow = a.mask2 + (((size_t)b * V + y) * V + x) * NW;
   float* col = tile + (size_t)(HL * h) * RW + rx;
-  dpc_mbar_wait(&bar, 0);
+  if (!use_cpasync) dpc_mbar_wait(&bar, 0);
   {
     float T0 = 1.0f, T1 = 1.0f, T2 = 1.0f, T3 = 1.0f;
 #pragma unroll 4
@@ -688,7 +717,8 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
   const float ds = dsv * inv_s;
   __syncthreads();
   {
-    const int seg = tid >> 6, pidx = tid & 63;
+    const int seg = (V == 64) ? ((tid >> 5) & 3) : (tid >> 6);
+    const int pidx = (V == 64) ? (((tid >> 7) << 5) | (tid & 31)) : (tid & 63);
     const int wy = pidx / (V / 2), xp = pidx % (V / 2), yy = y0 + wy;
     const float* c2 = tile + 2 * pidx;
     float* dout = a.d_in + ((size_t)b * Vz * V + yy) * V + 2 * xp;
@@ -798,7 +828,8 @@ static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_
                                              void* stream) {
   DpcConvZArgs a;
   a.in = in; a.taps = taps_z; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = eps;
-  a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = 128 / V;
+  a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V;
+  a.TY = dpc_z_tile_cpasync ? -(128 / V) : (128 / V);      // sign = tile load method (experiment knob)
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = probs; a.depth = depth;
   if (V == 32) return Kz == 21 ? dpc_conv_z_fwd_fast_go<32, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<32, 11>(a, B, stream);
   if (V == 64) return Kz == 21 ? dpc_conv_z_fwd_fast_go<64, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<64, 11>(a, B, stream);
@@ -830,6 +861,7 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
   a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;
   const bool lean = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
   if (lean) {
+    if (dpc_z_tile_cpasync) a.TY = -1;
     if (V == 32) return Kz == 21 ? dpc_conv_z_bwd_lean_go<32, 21>(a, B, stream) : dpc_conv_z_bwd_lean_go<32, 11>(a, B, stream);
     if (V == 64) return Kz == 21 ? dpc_conv_z_bwd_lean_go<64, 21>(a, B, stream) : dpc_conv_z_bwd_lean_go<64, 11>(a, B, stream);
     return Kz == 21 ? dpc_conv_z_bwd_lean_go<128, 21>(a, B, stream) : dpc_conv_z_bwd_lean_go<128, 11>(a, B, stream);

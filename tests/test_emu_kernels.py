@@ -100,3 +100,14 @@ def test_persistent_prefetch_conv_xy(emu):  # noqa: F811
         assert float((o1["proj"] - o2["proj"]).abs().max()) <= 1e-5
     finally:
         emu.dpc_debug_set(5, 0)
+
+
+def test_conv_z_cpasync_tile_load_variant(emu):  # noqa: F811
+    emu.dpc_debug_set(6, 1)
+    try:
+        for name in ("v64_small", "cfg1_drc_k11"):
+            fx = cases.load_golden(name)
+            outs, grads = cases.run_impl(Product, fx)
+            cases.assert_parity(fx, outs, grads)
+    finally:
+        emu.dpc_debug_set(6, 0)
