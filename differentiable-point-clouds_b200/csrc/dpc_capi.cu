@@ -64,6 +64,7 @@ int dpc_debug_set(int key, int value) {
   if (key == 2) dpc_xy_threads = (value == 128) ? 128 : 256;
   if (key == 5) dpc_xy_taps_smem = value;
   if (key == 6) dpc_z_tile_cpasync = value ? 1 : 0;
+  if (key == 7) dpc_xy_dbg = value;
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }

@@ -44,6 +44,7 @@ struct DpcConvXY64Args {
   const float* in; float* out; const float* taps_x; const float* taps_y;
   int clip_in; uint32_t* mask_out; const uint32_t* mask_in; int nslices;
   int rev; float* zero_ptr;
+  int dbg;   // diagnostics only: 1 = memory path only (no correlation), 2 = arithmetic only (no global load/store)
 };
 
 // V in {32, 64, 128}: a CTA owns one "unit" of contiguous voxels: four 32x32 slices, one 64x64 slice or
@@ -100,7 +101,7 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
     constexpr int NL = AR * V / 4 / NT;
     float4 v[NL];
 #pragma unroll
-    for (int k = 0; k < NL; ++k) v[k] = src[tid + NT * k];        // all loads in flight
+    for (int k = 0; k < NL; ++k) v[k] = (a.dbg == 2) ? make_float4(0.5f, 0.25f, 0.f, 1.f) : src[tid + NT * k];   // all loads in flight
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
       const int i = tid + NT * k;             // float4 index within the pass
@@ -122,6 +123,9 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
   __syncthreads();
 
   // ---- phase 1: x correlation.  Task = (row of the pass, run r of 16 outputs); a warp = 32 rows, one r.
+  if (a.dbg == 1) {
+    for (int i = tid; i < AR * S; i += NT) M[ps * AR * S + i] = A[i];
+  } else
 #pragma unroll 1
   for (int task = tid; task < XT; task += NT) {
     const int y = task % AR, r = task / AR;
@@ -177,7 +181,12 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
     float2 acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-    dpc_col_conv_pairs<K, 8>(M + sl * V * S + 2 * xp, S, y0, V, tyd, acc);
+    if (a.dbg == 1) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = *reinterpret_cast<const float2*>(M + (sl * V + y0 + o) * S + 2 * xp);
+    } else {
+      dpc_col_conv_pairs<K, 8>(M + sl * V * S + 2 * xp, S, y0, V, tyd, acc);
+    }
     const size_t base = slice + (size_t)sl * V * V;
     float* dst = a.out + base + (size_t)y0 * V + 2 * xp;
 #pragma unroll
@@ -189,7 +198,7 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
         if (!(wbits & 1u)) v.x = 0.0f;
         if (!(wbits & 2u)) v.y = 0.0f;
       }
-      *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
+      if (a.dbg != 2 || v.x == 123456.0f) *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
     }
   }
 }
@@ -749,6 +758,7 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
+static int dpc_xy_dbg = 0;         // diagnostics knob (dpc_debug_set key 7)
 static int dpc_xy_taps_smem = 0;   // experiment knob (dpc_debug_set key 5)
 static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256 | 128 threads per conv_xy CTA
 
@@ -780,7 +790,7 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   if (voxels % unit != 0) return DPC_ERR_SHAPE;     // V=32 needs B*Vz to be a multiple of 4
   DpcConvXY64Args a;
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
-  a.nslices = (int)(voxels / unit); a.rev = rev; a.zero_ptr = zero_ptr;
+  a.nslices = (int)(voxels / unit); a.rev = rev; a.zero_ptr = zero_ptr; a.dbg = dpc_xy_dbg;
   const bool small = dpc_xy_threads == 128;
   if (V == 64 && dpc_xy_taps_smem == 2 && !zero_ptr) {
     const int grid = a.nslices < 3 * 148 ? a.nslices : 3 * 148;
