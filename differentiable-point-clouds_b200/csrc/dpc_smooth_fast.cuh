@@ -19,6 +19,48 @@
 
 DPC_DEV float2 dpc_f2(float a, float b) { return make_float2(a, b); }
 
+// ------------------------------------------------------------------------------ taps in the constant bank
+// The filter taps are warp-uniform FFMA2 operands.  Read from a __constant__ array they are
+// fetched by LDCU straight into UNIFORM registers (FFMA2 takes a UR pair as its second operand),
+// which frees the 44 vector registers per thread that held them and lets two more CTAs fit on an
+// SM.  The taps arrive as device pointers, so each call first runs dpc_taps_prep_kernel (builds
+// every operand form, forward and reversed) and copies the 1.1 KiB image into the next slot of a
+// ring in constant memory (cudaMemcpyToSymbolAsync, stream-ordered).  DPC_TAP_SLOTS calls may be
+// in flight at once on different streams before a slot is reused.
+#define DPC_TAP_SLOTS 32
+struct DpcTapSlot {
+  float2 px[2][24];   // [rev][q], q = 0..K:  (t[q-1], t[q]) of the x taps, zero outside 0..K-1
+  float2 dy[2][24];   // [rev][j]:            (t[j], t[j]) of the y taps
+  float2 dz[2][24];   // [rev][j]:            (t[j], t[j]) of the depth taps
+};
+#ifndef DPC_EMU
+__constant__ DpcTapSlot c_dpc_taps[DPC_TAP_SLOTS];
+__device__ DpcTapSlot d_dpc_tap_staging[DPC_TAP_SLOTS];
+#else
+static DpcTapSlot c_dpc_taps[DPC_TAP_SLOTS];
+#endif
+
+#ifndef DPC_EMU
+__global__ void
+#else
+static void
+#endif
+dpc_taps_prep_kernel(const float* tx, int Kx, const float* ty, int Ky, const float* tz, int Kz, DpcTapSlot* dst) {
+  const int tid = threadIdx.x;           // 144 threads: (form, rev, index)
+  if (tid >= 144) return;
+  const int form = tid / 48, rev = (tid / 24) & 1, i = tid % 24;
+  if (form == 0) {
+    const float lo = (tx && i - 1 >= 0 && i - 1 < Kx) ? tx[rev ? (Kx - i) : (i - 1)] : 0.0f;
+    const float hi = (tx && i < Kx) ? tx[rev ? (Kx - 1 - i) : i] : 0.0f;
+    dst->px[rev][i] = make_float2(lo, hi);
+  } else {
+    const float* t = (form == 1) ? ty : tz;
+    const int K = (form == 1) ? Ky : Kz;
+    const float v = (t && i < K) ? t[rev ? (K - 1 - i) : i] : 0.0f;
+    if (form == 1) dst->dy[rev][i] = make_float2(v, v); else dst->dz[rev][i] = make_float2(v, v);
+  }
+}
+
 // acc[o] += sum_j tt[j] * in[r0 + o + j - PL][pair], rows outside [0, nrows) read as zero.
 // base points at the pair's element in row 0; stride in floats.
 template <int K, int R>
@@ -45,6 +87,7 @@ struct DpcConvXY64Args {
   int clip_in; uint32_t* mask_out; const uint32_t* mask_in; int nslices;
   int rev; float* zero_ptr;
   int dbg;   // diagnostics only: 1 = memory path only (no correlation), 2 = arithmetic only (no global load/store)
+  int slot;  // TS kernels: slot of c_dpc_taps holding the taps
 };
 
 // V in {32, 64, 128}: a CTA owns one "unit" of contiguous voxels: four 32x32 slices, one 64x64 slice or
@@ -52,11 +95,11 @@ struct DpcConvXY64Args {
 // input rows need only half a slice of smem), the y pass on the whole unit.
 // NT = threads per CTA: 256 (one task per thread and phase) or 128 (two tasks per thread and
 // phase, twice as many independent CTAs resident per SM to overlap load / barrier bubbles).
-// TS = tap pairs of the x pass read from smem at each use instead of being held in 44 registers:
-// the kernel then fits 64 registers and a fourth CTA per SM.
-template <int V, int K, int NT, bool TS>
+// TS = taps read from the constant-bank slot a.slot (uniform-register operands) instead of being
+// held in 44 vector registers: the kernel then fits TS (5 or 6) CTAs per SM instead of 3.
+template <int V, int K, int NT, int TS>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(NT, (TS ? 1024 : 768) / NT)
+__global__ void __launch_bounds__(NT, (TS ? TS * 256 : 768) / NT)
 #else
 static void
 #endif
@@ -83,7 +126,9 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
   __shared__ __align__(8) float2 tyd[24];           // y taps, each duplicated into a float2 (FFMA2 operand)
   const int tid = threadIdx.x;
   const size_t slice = (size_t)blockIdx.x * UNIT;   // first voxel of this CTA's unit
-  if (tid < 24) {
+  const float2* cpx = c_dpc_taps[TS ? a.slot : 0].px[a.rev ? 1 : 0];
+  const float2* cdy = c_dpc_taps[TS ? a.slot : 0].dy[a.rev ? 1 : 0];
+  if (!TS && tid < 24) {
     const int a_e = tid - 1, a_o = tid;              // tap indices behind E[tid], O[tid]
     txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
     txo[tid] = (a_o >= 0 && a_o < K) ? dpc_tap(a.taps_x, K, a_o, a.rev) : 0.0f;
@@ -91,6 +136,7 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
     tyd[tid] = dpc_f2(tyv, tyv);
   }
   dpc_grid_dep_sync();
+  if (a.dbg == 3) return;
 
 #pragma unroll 1
   for (int ps = 0; ps < NP; ++ps) {
@@ -123,7 +169,7 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
   __syncthreads();
 
   // ---- phase 1: x correlation.  Task = (row of the pass, run r of 16 outputs); a warp = 32 rows, one r.
-  if (a.dbg == 1) {
+  if (a.dbg == 1 || a.dbg == 4) {
     for (int i = tid; i < AR * S; i += NT) M[ps * AR * S + i] = A[i];
   } else
 #pragma unroll 1
@@ -155,9 +201,7 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
           if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1) {
             constexpr int dummy = 0; (void)dummy;
             const int q = 4 * g + 2 * h - o - WL + PL + 1;   // compile-time after unrolling
-            const float2 tq = TS ? ((q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1))
-                                            : *reinterpret_cast<const float2*>(txe + q))
-                                 : tp[TS ? 0 : q];
+            const float2 tq = TS ? cpx[q] : tp[TS ? 0 : q];
             acc[o] = dpc_ffma2(w, tq, acc[o]);
           }
         }
@@ -181,20 +225,24 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
     float2 acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-    if (a.dbg == 1) {
+    const size_t base = slice + (size_t)sl * V * V;
+    uint32_t mw[8];                       // clip-mask words of the 8 output rows, fetched before the arithmetic
+    if (a.mask_in) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) mw[o] = a.mask_in[(base + (size_t)(y0 + o) * V + 2 * xp) >> 5];
+    }
+    if (a.dbg == 1 || a.dbg == 5) {
 #pragma unroll
       for (int o = 0; o < 8; ++o) acc[o] = *reinterpret_cast<const float2*>(M + (sl * V + y0 + o) * S + 2 * xp);
     } else {
-      dpc_col_conv_pairs<K, 8>(M + sl * V * S + 2 * xp, S, y0, V, tyd, acc);
+      dpc_col_conv_pairs<K, 8>(M + sl * V * S + 2 * xp, S, y0, V, TS ? cdy : tyd, acc);
     }
-    const size_t base = slice + (size_t)sl * V * V;
     float* dst = a.out + base + (size_t)y0 * V + 2 * xp;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       float2 v = acc[o];
       if (a.mask_in) {
-        const size_t e = base + (size_t)(y0 + o) * V + 2 * xp;
-        const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
+        const uint32_t wbits = mw[o] >> ((2 * xp) & 31);      // V is a multiple of 32: the row offset drops out
         if (!(wbits & 1u)) v.x = 0.0f;
         if (!(wbits & 2u)) v.y = 0.0f;
       }
@@ -764,11 +812,28 @@ static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256
 
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
 
+// Build the operand image of the taps and copy it into the next constant-bank slot (stream-ordered).
+// NULL pointers leave that axis zero.  Returns the slot, or -1 on a CUDA error.
+static unsigned g_dpc_tap_next = 0;
+static inline int dpc_taps_upload(const float* tx, int Kx, const float* ty, int Ky, const float* tz, int Kz, void* stream) {
+  const int slot = (int)(__atomic_fetch_add(&g_dpc_tap_next, 1u, __ATOMIC_RELAXED) % DPC_TAP_SLOTS);
+#ifndef DPC_EMU
+  DpcTapSlot* staging = nullptr;
+  if (cudaGetSymbolAddress((void**)&staging, d_dpc_tap_staging) != cudaSuccess) return -1;
+  dpc_taps_prep_kernel<<<1, 160, 0, (cudaStream_t)stream>>>(tx, Kx, ty, Ky, tz, Kz, staging + slot);
+  if (cudaMemcpyToSymbolAsync(c_dpc_taps, staging + slot, sizeof(DpcTapSlot), (size_t)slot * sizeof(DpcTapSlot),
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return -1;
+#else
+  dpc_emu::launch(dim3(1), dim3(160), 0, [=]() { dpc_taps_prep_kernel(tx, Kx, ty, Ky, tz, Kz, &c_dpc_taps[slot]); });
+#endif
+  return slot;
+}
+
 static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, int ply) {
   return (V == 128 || V == 64 || V == 32) && Kx == Ky && dpc_fast_k(Kx) && plx == (Kx - 1) / 2 && ply == (Ky - 1) / 2;
 }
 
-template <int V, int K, int NT, bool TS = false>
+template <int V, int K, int NT, int TS = 0>
 static inline int dpc_conv_xy_fast_go(const DpcConvXY64Args& a, void* stream) {
   constexpr int S = V + 4, MR = (V == 32) ? 128 : V, AR = (V == 128) ? 64 : MR;
   const size_t smem = (size_t)(AR + MR) * S * sizeof(float);
@@ -783,7 +848,7 @@ static inline int dpc_conv_xy_fast_go(const DpcConvXY64Args& a, void* stream) {
 
 static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const float* taps_x, const float* taps_y, int K,
                                           int B, int Vz, int V, int clip_in, uint32_t* mask_out, const uint32_t* mask_in,
-                                          int rev, float* zero_ptr, void* stream) {
+                                          int rev, float* zero_ptr, void* stream, int slot = -1) {
   if ((((uintptr_t)in) & 15u) || (((uintptr_t)out) & 7u)) return DPC_ERR_ARG;
   const int64_t voxels = (int64_t)B * Vz * V * V;
   const int unit = (V == 128) ? 16384 : 4096;
@@ -792,6 +857,11 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
   a.nslices = (int)(voxels / unit); a.rev = rev; a.zero_ptr = zero_ptr; a.dbg = dpc_xy_dbg;
   const bool small = dpc_xy_threads == 128;
+  a.slot = slot;
+  if ((dpc_xy_taps_smem == 1 || dpc_xy_taps_smem == 3) && a.slot < 0) {
+    a.slot = dpc_taps_upload(taps_x, K, taps_y, K, nullptr, 0, stream);
+    if (a.slot < 0) return DPC_ERR_CUDA;
+  }
   if (V == 64 && dpc_xy_taps_smem == 2 && !zero_ptr) {
     const int grid = a.nslices < 3 * 148 ? a.nslices : 3 * 148;
 #ifndef DPC_EMU
@@ -805,7 +875,8 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
     return DPC_OK;
   }
   if (V == 64) {
-    if (K == 21 && dpc_xy_taps_smem == 1) return dpc_conv_xy_fast_go<64, 21, 256, true>(a, stream);
+    if (dpc_xy_taps_smem == 1) return K == 21 ? dpc_conv_xy_fast_go<64, 21, 256, 5>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256, 5>(a, stream);
+    if (dpc_xy_taps_smem == 3) return K == 21 ? dpc_conv_xy_fast_go<64, 21, 256, 6>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256, 6>(a, stream);
     if (K == 21) return small ? dpc_conv_xy_fast_go<64, 21, 128>(a, stream) : dpc_conv_xy_fast_go<64, 21, 256>(a, stream);
     return small ? dpc_conv_xy_fast_go<64, 11, 128>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256>(a, stream);
   }
