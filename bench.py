@@ -176,12 +176,16 @@ class Pipeline:
         self.pc, self.q, self.sc, self.gt = [t.to(dev) for t in host]
         self.sc1 = self.sc.reshape(-1).contiguous()
         self.gt3 = self.gt.reshape(B, V, V).contiguous()
-        self.kernel = gk.smoothing_kernel(self.cfg, torch.tensor(SIGMA, device=dev))
-        self.taps = self.kernel.taps_xy
+        # sigma is a host value (the reference's schedule is a function of the step count, model_pc.py:35-40):
+        # the kernel object holds the taps on the host and on the device
+        self.kernel = gk.smoothing_kernel(self.cfg, SIGMA)
+        self.taps = self.kernel.device_taps(dev)[0]
         self.p = _capi.ProjectParams(B=B, N=N, Vz=V, V=V, pose_kind=_capi.POSE_QUAT, mode=_capi.PROJ_DRC, K=K, Kz=K,
                                      focal_const=float(self.cfg.focal_length), cam_dist=float(self.cfg.camera_distance),
                                      clip_eps=float(self.cfg.drc_logsum_clip_val), max_depth=float(self.cfg.max_depth))
         self.p.flags = 0
+        self.p.taps_xy_host = self.kernel.host_taps_xy.data_ptr()
+        self.p.taps_z_host = self.kernel.host_taps_z.data_ptr()
         self.scratch_bytes = self.L.dpc_project_fast_scratch_bytes(ctypes.byref(self.p))
         self.saved_bytes = self.L.dpc_project_fast_saved_bytes(ctypes.byref(self.p))
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731

@@ -41,7 +41,7 @@ static bool shape_ok(int B, int Vz, int V) {
 
 extern "C" {
 
-int dpc_abi_version(void) { return 1; }
+int dpc_abi_version(void) { return 2; }
 /* ms between the stage marks of the last instrumented forward+backward (synchronises):
  * out[0..5] = splat_fwd(+memset), conv_xy_fwd, conv_z_fwd, conv_z_bwd(+memsets), conv_xy_bwd, splat_bwd */
 int dpc_debug_stage_ms(float* out6) {
@@ -61,8 +61,7 @@ int dpc_debug_stage_ms(float* out6) {
 int dpc_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return DPC_ERR_ARG;
   g_tune[key] = value;
-  if (key == 2) dpc_xy_threads = (value == 128) ? 128 : 256;
-  if (key == 5) dpc_xy_taps_smem = value;
+  if (key == 5) dpc_ignore_host_taps = value ? 1 : 0;
   if (key == 6) dpc_z_tile_cpasync = value ? 1 : 0;
   if (key == 7) dpc_xy_dbg = value;
   return DPC_OK;
@@ -145,7 +144,7 @@ int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float
 static int launch_conv_xy(const float* in, float* out, const float* taps_x, int Kx, int pad_lo_x,
                           const float* taps_y, int Ky, int pad_lo_y, int B, int Vz, int V,
                           int clip_in, uint32_t* mask_bits_out, const uint32_t* mask_bits_in,
-                          int rev, int zero_in, void* stream) {
+                          int rev, int zero_in, void* stream, const float* hx = nullptr, const float* hy = nullptr) {
   if (!in || !out) return DPC_ERR_NULL;
   if (!shape_ok(B, Vz, V) || Kx < 1 || Ky < 1 || Kx > DPC_MAX_TAPS || Ky > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo_x < 0 || pad_lo_x >= Kx || pad_lo_y < 0 || pad_lo_y >= Ky) return DPC_ERR_ARG;
@@ -154,7 +153,7 @@ static int launch_conv_xy(const float* in, float* out, const float* taps_x, int 
   float* zero_ptr = zero_in ? const_cast<float*>(in) : nullptr;
   if (taps_x && taps_y && dpc_conv_xy_fast_supported(V, Kx, pad_lo_x, Ky, pad_lo_y) && ((int64_t)B * Vz * V * V) % (V == 128 ? 16384 : 4096) == 0) {
     DPC_TRY(dpc_conv_xy_fast_launch(in, out, taps_x, taps_y, Kx, B, Vz, V, clip_in, mask_bits_out, mask_bits_in,
-                                    rev, zero_ptr, stream));
+                                    rev, zero_ptr, hx, hy, stream));
     return dpc_check_launch();
   }
   DpcConvXYArgs a;
@@ -178,7 +177,7 @@ static int launch_conv_z_fwd(const float* in, const float* taps_z, int Kz, int p
                              const float* scale, int mode, float clip_eps, float cam_dist, float max_depth,
                              int flip_y, int B, int Vz, int V,
                              float* vox_out, uint32_t* mask2_out, float* proj, float* drc_probs,
-                             float* proj_depth, void* stream) {
+                             float* proj_depth, void* stream, const float* hz = nullptr) {
   if (!in || !vox_out) return DPC_ERR_NULL;
   if (mode < DPC_PROJ_NONE || mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
   if (mode != DPC_PROJ_NONE && !proj) return DPC_ERR_NULL;
@@ -187,10 +186,11 @@ static int launch_conv_z_fwd(const float* in, const float* taps_z, int Kz, int p
   if (pad_lo_z < 0 || pad_lo_z >= Kz) return DPC_ERR_ARG;
   if (taps_z && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z, drc_probs != nullptr || proj_depth != nullptr)) {
     DPC_TRY(dpc_conv_z_fwd_fast_launch(in, taps_z, Kz, scale, mode, clip_eps, cam_dist, max_depth, flip_y, B, Vz, V,
-                                       vox_out, mask2_out, proj, drc_probs, proj_depth, stream));
+                                       vox_out, mask2_out, proj, drc_probs, proj_depth, hz, stream));
     return dpc_check_launch();
   }
   DpcConvZArgs a;
+  dpc_set_taps_z(&a.ht, &a.use_ht, nullptr, 0, 0);
   a.in = in; a.taps = taps_z; a.K = Kz; a.pl = pad_lo_z; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = clip_eps;
   a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = conv_z_ty(V);
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = drc_probs; a.depth = proj_depth;
@@ -208,7 +208,7 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
                              int mode, float clip_eps, float cam_dist, float max_depth, int flip_y,
                              int B, int Vz, int V,
                              const float* g_proj, const float* g_vox, const float* g_probs, const float* g_depth,
-                             float* d_in, float* d_scale, void* stream) {
+                             float* d_in, float* d_scale, void* stream, const float* hz = nullptr) {
   if (!vox || !d_in) return DPC_ERR_NULL;
   if (mode < DPC_PROJ_NONE || mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
   if ((g_probs || g_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
@@ -218,10 +218,11 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
   if (taps && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo, g_probs != nullptr || g_depth != nullptr) &&
       (lean_case || dpc_conv_z_bwd_fast_general_ok(V))) {
     DPC_TRY(dpc_conv_z_bwd_fast_launch(vox, mask2, scale, taps, Kz, mode, clip_eps, cam_dist, max_depth, flip_y,
-                                       B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, rev, stream));
+                                       B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, rev, hz, stream));
     return dpc_check_launch();
   }
   DpcConvZBwdArgs a;
+  dpc_set_taps_z(&a.ht, &a.use_ht, nullptr, 0, 0);
   a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps; a.K = Kz; a.pl = pad_lo; a.rev = rev;
   a.mode = mode; a.eps = clip_eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
   a.B = B; a.Vz = Vz; a.V = V; a.TY = conv_z_ty(V);
@@ -332,6 +333,8 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   const float* tz = p->Kz > 0 ? taps_z : nullptr;
   const int64_t g = (int64_t)p->B * p->Vz * p->V * p->V;
   stage_mark(0, stream);
+  const float* hxy = (tx && p->taps_xy_host) ? p->taps_xy_host : nullptr;   // host copies of the taps (optional)
+  const float* hz = (tz && p->taps_z_host) ? p->taps_z_host : nullptr;
   // cudaMemsetAsync beat a hand-written float4 zero kernel here (23.6 vs 28.4 us for memset + splat,
   // gpurun round 7), so the driver's memset stays.
   if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO))
@@ -345,12 +348,12 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   // so the default path keeps the memset and leaves the flag to callers that want it.
   DPC_TRY(launch_conv_xy(w.raw, w.tmp, tx, K, (K - 1) / 2, tx, K, (K - 1) / 2,
                          p->B, p->Vz, p->V, /*clip_in=*/1, sv.mask1, nullptr, /*rev=*/0,
-                         /*zero_in=*/(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) ? 1 : 0, stream));
+                         /*zero_in=*/(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) ? 1 : 0, stream, hxy, hxy));
   stage_mark(2, stream);
   const bool want_probs = (p->mode != DPC_PROJ_MAX);
   DPC_TRY(launch_conv_z_fwd(w.tmp, tz, Kz, (Kz - 1) / 2, scale, p->mode, p->clip_eps, p->cam_dist,
                             p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V, voxels, scale ? sv.mask2 : nullptr, proj,
-                            want_probs ? drc_probs : nullptr, want_probs ? proj_depth : nullptr, stream));
+                            want_probs ? drc_probs : nullptr, want_probs ? proj_depth : nullptr, stream, hz));
   stage_mark(3, stream);
   return DPC_OK;
 }
@@ -381,15 +384,17 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   const bool any_grid_grad = g_proj || g_voxels || g_probs || g_depth;
   const float* d_raw = nullptr;
   stage_mark(4, stream);
+  const float* hxy = (tx && p->taps_xy_host) ? p->taps_xy_host : nullptr;
+  const float* hz = (tz && p->taps_z_host) ? p->taps_z_host : nullptr;
   if (any_grid_grad) {
     // voxels/proj -> dL/d(xy-smoothed) in tmp -> dL/d(raw) in tmp again (per-slice in place; the saved
     // clip mask applied).  `raw` is not touched: it stays all-zero for the next forward.
     DPC_TRY(launch_conv_z_bwd(voxels, scale ? sv.mask2 : nullptr, scale, tz, Kz, Kz - 1 - (Kz - 1) / 2, /*rev=*/1,
                               p->mode, p->clip_eps, p->cam_dist, p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V,
-                              g_proj, g_voxels, g_probs, g_depth, w.tmp, d_scale, stream));
+                              g_proj, g_voxels, g_probs, g_depth, w.tmp, d_scale, stream, hz));
     stage_mark(5, stream);
     DPC_TRY(launch_conv_xy(w.tmp, w.tmp, tx, K, K - 1 - (K - 1) / 2, tx, K, K - 1 - (K - 1) / 2,
-                           p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, sv.mask1, /*rev=*/1, /*zero_in=*/0, stream));
+                           p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, sv.mask1, /*rev=*/1, /*zero_in=*/0, stream, hxy, hxy));
     d_raw = w.tmp;
   }
   stage_mark(6, stream);

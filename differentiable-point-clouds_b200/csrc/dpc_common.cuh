@@ -19,6 +19,7 @@
 #define DPC_FULL 0xffffffffu
 
 #ifndef DPC_EMU
+#define DPC_GRID_CONSTANT __grid_constant__
 #define DPC_DEV __device__ __forceinline__
 // Every kernel is launched with Programmatic Dependent Launch allowed: its CTAs may be scheduled
 // while the previous kernel of the stream is still draining, run their prologue (taps into smem,
@@ -39,6 +40,7 @@ static inline void dpc_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 #define DPC_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; \
   type* name = reinterpret_cast<type*>(name##_raw)
 #else
+#define DPC_GRID_CONSTANT
 #define DPC_DEV static inline
 #define DPC_LAUNCH(kernel, grid, block, smem, stream, ...) \
   dpc_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })

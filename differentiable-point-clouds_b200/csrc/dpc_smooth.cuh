@@ -19,6 +19,9 @@ DPC_DEV float dpc_tap(const float* taps, int K, int j, int rev) {
   return taps ? taps[rev ? (K - 1 - j) : j] : 1.0f;
 }
 
+// depth taps as FFMA2 operands, (t[j], t[j]), carried in the launch parameters (dpc_smooth_fast.cuh)
+struct DpcTapsZ { float2 dz[24]; };
+
 struct DpcConvXYArgs {
   const float* in; float* out;
   const float* taps_x; int Kx; int plx;
@@ -92,6 +95,7 @@ struct DpcConvZArgs {
   const float* scale; int mode; float eps; float cam_dist; float max_depth; int flip_y;
   int B, Vz, V, TY;
   float* vox_out; uint32_t* mask2_out; float* proj; float* probs; float* depth;
+  DpcTapsZ ht; int use_ht;   // fast kernels: host-provided taps in the launch parameters (dpc_smooth_fast.cuh)
 };
 
 // DRC constants shared by forward and backward
@@ -191,6 +195,7 @@ struct DpcConvZBwdArgs {
   int B, Vz, V, TY;
   const float* g_proj; const float* g_vox; const float* g_probs; const float* g_depth;
   float* d_in; float* d_scale;
+  DpcTapsZ ht; int use_ht;   // fast kernels: host-provided taps in the launch parameters
 };
 
 #ifndef DPC_EMU

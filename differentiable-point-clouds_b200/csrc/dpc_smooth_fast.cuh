@@ -19,48 +19,6 @@
 
 DPC_DEV float2 dpc_f2(float a, float b) { return make_float2(a, b); }
 
-// ------------------------------------------------------------------------------ taps in the constant bank
-// The filter taps are warp-uniform FFMA2 operands.  Read from a __constant__ array they are
-// fetched by LDCU straight into UNIFORM registers (FFMA2 takes a UR pair as its second operand),
-// which frees the 44 vector registers per thread that held them and lets two more CTAs fit on an
-// SM.  The taps arrive as device pointers, so each call first runs dpc_taps_prep_kernel (builds
-// every operand form, forward and reversed) and copies the 1.1 KiB image into the next slot of a
-// ring in constant memory (cudaMemcpyToSymbolAsync, stream-ordered).  DPC_TAP_SLOTS calls may be
-// in flight at once on different streams before a slot is reused.
-#define DPC_TAP_SLOTS 32
-struct DpcTapSlot {
-  float2 px[2][24];   // [rev][q], q = 0..K:  (t[q-1], t[q]) of the x taps, zero outside 0..K-1
-  float2 dy[2][24];   // [rev][j]:            (t[j], t[j]) of the y taps
-  float2 dz[2][24];   // [rev][j]:            (t[j], t[j]) of the depth taps
-};
-#ifndef DPC_EMU
-__constant__ DpcTapSlot c_dpc_taps[DPC_TAP_SLOTS];
-__device__ DpcTapSlot d_dpc_tap_staging[DPC_TAP_SLOTS];
-#else
-static DpcTapSlot c_dpc_taps[DPC_TAP_SLOTS];
-#endif
-
-#ifndef DPC_EMU
-__global__ void
-#else
-static void
-#endif
-dpc_taps_prep_kernel(const float* tx, int Kx, const float* ty, int Ky, const float* tz, int Kz, DpcTapSlot* dst) {
-  const int tid = threadIdx.x;           // 144 threads: (form, rev, index)
-  if (tid >= 144) return;
-  const int form = tid / 48, rev = (tid / 24) & 1, i = tid % 24;
-  if (form == 0) {
-    const float lo = (tx && i - 1 >= 0 && i - 1 < Kx) ? tx[rev ? (Kx - i) : (i - 1)] : 0.0f;
-    const float hi = (tx && i < Kx) ? tx[rev ? (Kx - 1 - i) : i] : 0.0f;
-    dst->px[rev][i] = make_float2(lo, hi);
-  } else {
-    const float* t = (form == 1) ? ty : tz;
-    const int K = (form == 1) ? Ky : Kz;
-    const float v = (t && i < K) ? t[rev ? (K - 1 - i) : i] : 0.0f;
-    if (form == 1) dst->dy[rev][i] = make_float2(v, v); else dst->dz[rev][i] = make_float2(v, v);
-  }
-}
-
 // acc[o] += sum_j tt[j] * in[r0 + o + j - PL][pair], rows outside [0, nrows) read as zero.
 // base points at the pair's element in row 0; stride in floats.
 template <int K, int R>
@@ -78,6 +36,31 @@ DPC_DEV void dpc_col_conv_pairs(const float* base, int stride, int r0, int nrows
   }
 }
 
+// ------------------------------------------------------------------------------ taps as launch parameters
+// The filter taps are warp-uniform FFMA2 operands.  Held in vector registers they cost 44 (x pass)
+// / 42 (y, depth pass) registers per thread and cap the kernels at 3-4 CTAs per SM, which is what
+// bounds them (gpurun rounds 19-23: every stage of a CTA is latency-exposed; FMA pipe 46 % busy).
+// When the CALLER knows the taps on the host -- the reference derives sigma from the global step
+// (model_pc.py:35-40), so a training loop does -- they travel inside the kernel's launch parameters
+// instead: constant bank 0, fetched by LDCU into UNIFORM registers, which FFMA2 accepts as its
+// second operand.  The kernels then need 40-45 registers and 5-6 CTAs fit per SM.  (Copying
+// device taps into a __constant__ array per call was measured too: the copy costs more stream time
+// than the kernels gain.)  Without host taps the vector-register kernels run.
+struct DpcTapsXY {
+  float2 px[24];      // q = 0..K: (t[q-1], t[q]) of the x taps (zero outside 0..K-1)
+  float2 dy[24];      // j = 0..K-1: (t[j], t[j]) of the y taps
+};
+
+static inline float dpc_host_tap(const float* t, int K, int i, int rev) {
+  return (i >= 0 && i < K) ? t[rev ? (K - 1 - i) : i] : 0.0f;
+}
+static inline void dpc_build_taps_pairs(const float* t, int K, int rev, float2* px) {
+  for (int q = 0; q < 24; ++q) px[q] = make_float2(dpc_host_tap(t, K, q - 1, rev), dpc_host_tap(t, K, q, rev));
+}
+static inline void dpc_build_taps_dup(const float* t, int K, int rev, float2* d) {
+  for (int j = 0; j < 24; ++j) { const float v = dpc_host_tap(t, K, j, rev); d[j] = make_float2(v, v); }
+}
+
 // ------------------------------------------------------------------------------ conv_xy, V = 64
 // One CTA per depth slice (2048 CTAs at B=32, three resident per SM, so the load phase of one
 // overlaps the arithmetic of the others).  A persistent, TMA-prefetching variant was measured and
@@ -87,7 +70,7 @@ struct DpcConvXY64Args {
   int clip_in; uint32_t* mask_out; const uint32_t* mask_in; int nslices;
   int rev; float* zero_ptr;
   int dbg;   // diagnostics only: 1 = memory path only (no correlation), 2 = arithmetic only (no global load/store)
-  int slot;  // TS kernels: slot of c_dpc_taps holding the taps
+  DpcTapsXY ht;   // TS kernels: the taps (already reversed when rev), built on the host
 };
 
 // V in {32, 64, 128}: a CTA owns one "unit" of contiguous voxels: four 32x32 slices, one 64x64 slice or
@@ -95,15 +78,15 @@ struct DpcConvXY64Args {
 // input rows need only half a slice of smem), the y pass on the whole unit.
 // NT = threads per CTA: 256 (one task per thread and phase) or 128 (two tasks per thread and
 // phase, twice as many independent CTAs resident per SM to overlap load / barrier bubbles).
-// TS = taps read from the constant-bank slot a.slot (uniform-register operands) instead of being
-// held in 44 vector registers: the kernel then fits TS (5 or 6) CTAs per SM instead of 3.
+// TS = taps taken from the launch parameters a.ht (uniform-register operands) instead of being
+// held in 44 vector registers: the kernel is then compiled for TS CTAs per SM (5 at V <= 64) instead of 3.
 template <int V, int K, int NT, int TS>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(NT, (TS ? TS * 256 : 768) / NT)
 #else
 static void
 #endif
-dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
+dpc_conv_xy_fast_kernel(const DPC_GRID_CONSTANT DpcConvXY64Args a) {
   constexpr int S = V + 4, PL = (K - 1) / 2;
   constexpr int SPC = (V == 32) ? 4 : 1;            // slices per unit
   constexpr int UNIT = SPC * V * V;                 // voxels per CTA: 4096, 4096, 16384
@@ -126,8 +109,6 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
   __shared__ __align__(8) float2 tyd[24];           // y taps, each duplicated into a float2 (FFMA2 operand)
   const int tid = threadIdx.x;
   const size_t slice = (size_t)blockIdx.x * UNIT;   // first voxel of this CTA's unit
-  const float2* cpx = c_dpc_taps[TS ? a.slot : 0].px[a.rev ? 1 : 0];
-  const float2* cdy = c_dpc_taps[TS ? a.slot : 0].dy[a.rev ? 1 : 0];
   if (!TS && tid < 24) {
     const int a_e = tid - 1, a_o = tid;              // tap indices behind E[tid], O[tid]
     txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
@@ -201,7 +182,7 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
           if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1) {
             constexpr int dummy = 0; (void)dummy;
             const int q = 4 * g + 2 * h - o - WL + PL + 1;   // compile-time after unrolling
-            const float2 tq = TS ? cpx[q] : tp[TS ? 0 : q];
+            const float2 tq = TS ? a.ht.px[q] : tp[TS ? 0 : q];
             acc[o] = dpc_ffma2(w, tq, acc[o]);
           }
         }
@@ -235,7 +216,7 @@ dpc_conv_xy_fast_kernel(DpcConvXY64Args a) {
 #pragma unroll
       for (int o = 0; o < 8; ++o) acc[o] = *reinterpret_cast<const float2*>(M + (sl * V + y0 + o) * S + 2 * xp);
     } else {
-      dpc_col_conv_pairs<K, 8>(M + sl * V * S + 2 * xp, S, y0, V, TS ? cdy : tyd, acc);
+      dpc_col_conv_pairs<K, 8>(M + sl * V * S + 2 * xp, S, y0, V, TS ? a.ht.dy : tyd, acc);
     }
     float* dst = a.out + base + (size_t)y0 * V + 2 * xp;
 #pragma unroll
@@ -295,141 +276,6 @@ DPC_DEV void dpc_cta_cpasync_rows(float* dst, const float* src, size_t src_pitch
   __syncthreads();
 }
 
-// ------------------------------------------------------------------------------ conv_xy, persistent (64^3)
-// Same arithmetic as dpc_conv_xy_fast_kernel<64,K,256>, but 3 resident CTAs per SM walk the slices
-// round-robin and the NEXT slice is copied into the other half of a double buffer by the TMA engine
-// (64 row copies issued by the 32 lanes of warp 0, one mbarrier per buffer) while the current one is
-// being correlated, so no warp waits on HBM latency in steady state.  Co-resident CTAs of the
-// one-slice-per-CTA kernel start and stop together, i.e. they all wait on their loads at the same
-// time; here the load is hidden inside each CTA.  The landed slice is clipped (and its clip mask
-// extracted) in place by a short smem pass.
-#define DPC_XYPF_SMEM_BYTES ((2 * DPC_F64_V * DPC_F64_S + 2 * DPC_F64_V * DPC_F64_V) * 4)
-
-template <int K>
-#ifndef DPC_EMU
-__global__ void __launch_bounds__(256, 3)
-#else
-static void
-#endif
-dpc_conv_xy64_pf_kernel(DpcConvXY64Args a) {
-  constexpr int V = DPC_F64_V, S = DPC_F64_S, PL = (K - 1) / 2;
-  constexpr int WL = ((PL + 3) / 4) * 4;
-  constexpr int NW4 = (WL + 16 + WL) / 4;
-  DPC_DYN_SMEM(float, sm);
-  float* Lbuf = sm;                                  // [2][V*V] landing buffers: ONE 16 KiB bulk copy per slice
-  float* A = sm + 2 * V * V;                         // [V*S] padded, clipped copy the x pass reads
-  float* M = A + V * S;                              // [V*S]
-  __shared__ __align__(8) float txe[24];
-  __shared__ __align__(8) float txo[24];
-  __shared__ __align__(8) float2 tyd[24];
-  __shared__ __align__(8) uint64_t bars[2];
-  const int tid = threadIdx.x;
-  if (tid < 24) {
-    const int a_e = tid - 1, a_o = tid;
-    txe[tid] = (a_e >= 0 && a_e < K) ? dpc_tap(a.taps_x, K, a_e, a.rev) : 0.0f;
-    txo[tid] = (a_o >= 0 && a_o < K) ? dpc_tap(a.taps_x, K, a_o, a.rev) : 0.0f;
-    const float tyv = (tid < K) ? dpc_tap(a.taps_y, K, tid, a.rev) : 0.0f;
-    tyd[tid] = dpc_f2(tyv, tyv);
-  }
-  if (tid == 0) { dpc_mbar_init(&bars[0], 1); dpc_mbar_init(&bars[1], 1); }
-  dpc_grid_dep_sync();
-  __syncthreads();
-  int slice = blockIdx.x;
-  if (slice >= a.nslices) return;
-  if (tid == 0) dpc_bulk_load(Lbuf, a.in + (size_t)slice * (V * V), V * V * 4, &bars[0]);
-
-  for (int it = 0; slice < a.nslices; ++it, slice += gridDim.x) {
-    const int cb = it & 1;
-    const float* L = Lbuf + cb * (V * V);
-    const int next = slice + gridDim.x;
-    // the other landing buffer was drained by the copy pass of the previous iteration (barrier after it)
-    if (tid == 0 && next < a.nslices)
-      dpc_bulk_load(Lbuf + (cb ^ 1) * (V * V), a.in + (size_t)next * (V * V), V * V * 4, &bars[cb ^ 1]);
-    dpc_mbar_wait(&bars[cb], (it >> 1) & 1);
-    const size_t sl = (size_t)slice * (V * V);
-
-    // ---- landing buffer -> padded A, with the clip and the clip-mask bits (each thread four float4)
-    {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = tid + 256 * k;            // float4 index in the slice: row = i/16, col4 = i%16
-        float4* p4 = reinterpret_cast<float4*>(&A[(i >> 4) * S + (i & 15) * 4]);
-        float4 v = reinterpret_cast<const float4*>(L)[i];
-        if (a.mask_out) {
-          unsigned nib = ((v.x >= 0.0f && v.x <= 1.0f) ? 1u : 0u) | ((v.y >= 0.0f && v.y <= 1.0f) ? 2u : 0u) |
-                         ((v.z >= 0.0f && v.z <= 1.0f) ? 4u : 0u) | ((v.w >= 0.0f && v.w <= 1.0f) ? 8u : 0u);
-          unsigned word = nib << (4 * (tid & 7));
-          word |= __shfl_xor_sync(DPC_FULL, word, 1);
-          word |= __shfl_xor_sync(DPC_FULL, word, 2);
-          word |= __shfl_xor_sync(DPC_FULL, word, 4);
-          if ((tid & 7) == 0) a.mask_out[(sl >> 5) + (i >> 3)] = word;
-        }
-        if (a.clip_in) { v.x = dpc_clip01(v.x); v.y = dpc_clip01(v.y); v.z = dpc_clip01(v.z); v.w = dpc_clip01(v.w); }
-        *p4 = v;
-      }
-      __syncthreads();
-    }
-
-    // ---- x correlation.  Thread = (row y, run r of 16 outputs); a warp = 32 rows, one r.
-    {
-      const int y = tid & 63, r = tid >> 6;
-      const int x0 = r * 16;
-      float2 tp[K + 1];
-#pragma unroll
-      for (int q = 0; q < K + 1; ++q)
-        tp[q] = (q & 1) ? *reinterpret_cast<const float2*>(txo + (q - 1)) : *reinterpret_cast<const float2*>(txe + q);
-      float2 acc[16];
-#pragma unroll
-      for (int o = 0; o < 16; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      const float* rowp = A + y * S;
-#pragma unroll
-      for (int g = 0; g < NW4; ++g) {
-        const int xs = x0 - WL + 4 * g;
-        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xs >= 0 && xs < V) w4 = *reinterpret_cast<const float4*>(rowp + xs);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 w = h ? dpc_f2(w4.z, w4.w) : dpc_f2(w4.x, w4.y);
-#pragma unroll
-          for (int o = 0; o < 16; ++o) {
-            if (4 * g + 2 * h - o - WL + PL >= -1 && 4 * g + 2 * h - o - WL + PL <= K - 1)
-              acc[o] = dpc_ffma2(w, tp[4 * g + 2 * h - o - WL + PL + 1], acc[o]);
-          }
-        }
-      }
-      float* dst = M + y * S + x0;
-#pragma unroll
-      for (int o = 0; o < 16; o += 4) {
-        *reinterpret_cast<float4*>(dst + o) = make_float4(acc[o].x + acc[o].y, acc[o + 1].x + acc[o + 1].y,
-                                                           acc[o + 2].x + acc[o + 2].y, acc[o + 3].x + acc[o + 3].y);
-      }
-    }
-    __syncthreads();
-
-    // ---- y correlation.  Thread = (x pair, run of 8 rows); a warp = one run, 32 x pairs.
-    {
-      const int xp = tid & 31, y0 = (tid >> 5) * 8;
-      float2 acc[8];
-#pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = dpc_f2(0.0f, 0.0f);
-      dpc_col_conv_pairs<K, 8>(M + 2 * xp, S, y0, V, tyd, acc);
-      float* dst = a.out + sl + (size_t)y0 * V + 2 * xp;
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        float2 v = acc[o];
-        if (a.mask_in) {
-          const size_t e = sl + (size_t)(y0 + o) * V + 2 * xp;
-          const uint32_t wbits = a.mask_in[e >> 5] >> (e & 31);
-          if (!(wbits & 1u)) v.x = 0.0f;
-          if (!(wbits & 2u)) v.y = 0.0f;
-        }
-        *reinterpret_cast<float2*>(dst + (size_t)o * V) = v;
-      }
-    }
-    __syncthreads();   // M (and this iteration's A) are free
-  }
-}
-
 // ------------------------------------------------------------------------------ conv_z, V = Vz = 64
 // CTA = 4 image rows x all 64 depth levels (64 KiB tile, TMA bulk loads), 256 threads = 8 warps.
 // Warp w works on image row w>>1 and on depth half w&1 (levels 32h .. 32h+31): the correlation has
@@ -447,13 +293,13 @@ dpc_conv_xy64_pf_kernel(DpcConvXY64Args a) {
 // scan starts from T = 1 in every segment and the segments are combined through smem:
 //   proj = S0 + T0 (S1 + T1 (S2 + T2 S3)),  max = max of the segment maxima.
 // At 64^3 that is 1024 CTAs, four resident per SM.
-template <int V, int K, int MINB>
+template <int V, int K, int MINB, bool CT>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(DPC_ZF_THREADS, MINB)
 #else
 static void
 #endif
-dpc_conv_z_fast_fwd_kernel(DpcConvZArgs a) {
+dpc_conv_z_fast_fwd_kernel(const DPC_GRID_CONSTANT DpcConvZArgs a) {
   constexpr int Vz = V, TY = 128 / V, RW = 128, CPS = Vz / 32, NW = Vz / 32;
   static_assert(V == 32 || V == 64 || V == 128, "V");
   DPC_DYN_SMEM(float, tile);                // [Vz][TY][V] = [Vz][128]
@@ -462,7 +308,7 @@ dpc_conv_z_fast_fwd_kernel(DpcConvZArgs a) {
   __shared__ __align__(8) float comb[4][128][2];  // per depth segment and ray: (T, S) or (max, -)
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
-  if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
+  if (!CT && tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
   const float* src = a.in + ((size_t)b * Vz * V + y0) * V;
   if (tid == 0) dpc_mbar_init(&bar, 1);
   dpc_grid_dep_sync();
@@ -480,9 +326,12 @@ dpc_conv_z_fast_fwd_kernel(DpcConvZArgs a) {
   const int seg = (V == 64) ? ((tid >> 5) & 3) : (tid >> 6);
   const int pidx = (V == 64) ? (((tid >> 7) << 5) | (tid & 31)) : (tid & 63);
   const int ty = pidx / (V / 2), xp = pidx % (V / 2), y = y0 + ty;
-  float2 tt[K];                                   // taps in registers: measured faster than reading smem per FFMA2
+  float2 ttr[CT ? 1 : K];                         // taps in registers: measured faster than reading smem per FFMA2
+  if (!CT) {
 #pragma unroll
-  for (int j = 0; j < K; ++j) tt[j] = tzd[j];
+    for (int j = 0; j < K; ++j) ttr[CT ? 0 : j] = tzd[j];
+  }
+  const float2* tt = CT ? a.ht.dz : ttr;          // CT: launch-parameter taps -> uniform-register operands
   const bool has_s = a.scale != nullptr;
   const float s = has_s ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
@@ -708,13 +557,13 @@ dpc_conv_z64_bwd_kernel(DpcConvZBwdArgs a) {
 // product over a ray is split in two halves exchanged through smem, after which every level's
 // gradient is independent (quotient form, see dpc_conv_z64_bwd_kernel).  Then 4 depth segments x 64
 // ray pairs for the transposed correlation.
-template <int V, int K, int MINB>
+template <int V, int K, int MINB, bool CT>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(DPC_ZF_THREADS, MINB)
 #else
 static void
 #endif
-dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
+dpc_conv_z_fast_bwd_lean_kernel(const DPC_GRID_CONSTANT DpcConvZBwdArgs a) {
   constexpr int Vz = V, TY = 128 / V, RW = 128, CPS = Vz / 32, NW = Vz / 32, HL = Vz / 2;
   DPC_DYN_SMEM(float, tile);                // [Vz][128]: forward voxels, overwritten by dL/d(smoothed)
   __shared__ __align__(8) uint64_t bar;
@@ -723,7 +572,7 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
   __shared__ float red[DPC_ZF_THREADS / 32];
   const int tid = threadIdx.x;
   const int b = blockIdx.y, y0 = blockIdx.x * TY;
-  if (tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
+  if (!CT && tid < K) { const float t = dpc_tap(a.taps, K, tid, a.rev); tzd[tid] = dpc_f2(t, t); }
   if (tid == 0) dpc_mbar_init(&bar, 1);
   dpc_grid_dep_sync();
   __syncthreads();
@@ -779,9 +628,12 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
     const int wy = pidx / (V / 2), xp = pidx % (V / 2), yy = y0 + wy;
     const float* c2 = tile + 2 * pidx;
     float* dout = a.d_in + ((size_t)b * Vz * V + yy) * V + 2 * xp;
-    float2 tt[K];
+    float2 ttr[CT ? 1 : K];
+    if (!CT) {
 #pragma unroll
-    for (int j = 0; j < K; ++j) tt[j] = tzd[j];
+      for (int j = 0; j < K; ++j) ttr[CT ? 0 : j] = tzd[j];
+    }
+    const float2* tt = CT ? a.ht.dz : ttr;
 #pragma unroll 1
     for (int c = 0; c < CPS; ++c) {
       const int zc = (CPS * seg + c) * 8;
@@ -806,36 +658,18 @@ dpc_conv_z_fast_bwd_lean_kernel(DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
-static int dpc_xy_dbg = 0;         // diagnostics knob (dpc_debug_set key 7)
-static int dpc_xy_taps_smem = 0;   // experiment knob (dpc_debug_set key 5)
-static int dpc_xy_threads = 256;   // experiment knob (dpc_debug_set key 2): 256 | 128 threads per conv_xy CTA
+static int dpc_xy_dbg = 0;           // diagnostics knob (dpc_debug_set key 7)
+static int dpc_ignore_host_taps = 0; // experiment knob (dpc_debug_set key 5): 1 = run the vector-register kernels even when host taps are given
 
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
-
-// Build the operand image of the taps and copy it into the next constant-bank slot (stream-ordered).
-// NULL pointers leave that axis zero.  Returns the slot, or -1 on a CUDA error.
-static unsigned g_dpc_tap_next = 0;
-static inline int dpc_taps_upload(const float* tx, int Kx, const float* ty, int Ky, const float* tz, int Kz, void* stream) {
-  const int slot = (int)(__atomic_fetch_add(&g_dpc_tap_next, 1u, __ATOMIC_RELAXED) % DPC_TAP_SLOTS);
-#ifndef DPC_EMU
-  DpcTapSlot* staging = nullptr;
-  if (cudaGetSymbolAddress((void**)&staging, d_dpc_tap_staging) != cudaSuccess) return -1;
-  dpc_taps_prep_kernel<<<1, 160, 0, (cudaStream_t)stream>>>(tx, Kx, ty, Ky, tz, Kz, staging + slot);
-  if (cudaMemcpyToSymbolAsync(c_dpc_taps, staging + slot, sizeof(DpcTapSlot), (size_t)slot * sizeof(DpcTapSlot),
-                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return -1;
-#else
-  dpc_emu::launch(dim3(1), dim3(160), 0, [=]() { dpc_taps_prep_kernel(tx, Kx, ty, Ky, tz, Kz, &c_dpc_taps[slot]); });
-#endif
-  return slot;
-}
 
 static inline bool dpc_conv_xy_fast_supported(int V, int Kx, int plx, int Ky, int ply) {
   return (V == 128 || V == 64 || V == 32) && Kx == Ky && dpc_fast_k(Kx) && plx == (Kx - 1) / 2 && ply == (Ky - 1) / 2;
 }
 
-template <int V, int K, int NT, int TS = 0>
+template <int V, int K, int TS>
 static inline int dpc_conv_xy_fast_go(const DpcConvXY64Args& a, void* stream) {
-  constexpr int S = V + 4, MR = (V == 32) ? 128 : V, AR = (V == 128) ? 64 : MR;
+  constexpr int NT = 256, S = V + 4, MR = (V == 32) ? 128 : V, AR = (V == 128) ? 64 : MR;
   const size_t smem = (size_t)(AR + MR) * S * sizeof(float);
 #ifndef DPC_EMU
   if (smem > 48 * 1024 &&
@@ -846,9 +680,16 @@ static inline int dpc_conv_xy_fast_go(const DpcConvXY64Args& a, void* stream) {
   return DPC_OK;
 }
 
+template <int V, int K>
+static inline int dpc_conv_xy_fast_pick(const DpcConvXY64Args& a, bool host_taps, void* stream) {
+  constexpr int CTAS = (V == 128) ? 2 : 5;       // the 99 KiB of smem at V = 128 allow two CTAs per SM either way
+  return host_taps ? dpc_conv_xy_fast_go<V, K, CTAS>(a, stream) : dpc_conv_xy_fast_go<V, K, 0>(a, stream);
+}
+
+// hx / hy: the same taps on the HOST (nullable): given both, they travel in the launch parameters.
 static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const float* taps_x, const float* taps_y, int K,
                                           int B, int Vz, int V, int clip_in, uint32_t* mask_out, const uint32_t* mask_in,
-                                          int rev, float* zero_ptr, void* stream, int slot = -1) {
+                                          int rev, float* zero_ptr, const float* hx, const float* hy, void* stream) {
   if ((((uintptr_t)in) & 15u) || (((uintptr_t)out) & 7u)) return DPC_ERR_ARG;
   const int64_t voxels = (int64_t)B * Vz * V * V;
   const int unit = (V == 128) ? 16384 : 4096;
@@ -856,32 +697,12 @@ static inline int dpc_conv_xy_fast_launch(const float* in, float* out, const flo
   DpcConvXY64Args a;
   a.in = in; a.out = out; a.taps_x = taps_x; a.taps_y = taps_y; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
   a.nslices = (int)(voxels / unit); a.rev = rev; a.zero_ptr = zero_ptr; a.dbg = dpc_xy_dbg;
-  const bool small = dpc_xy_threads == 128;
-  a.slot = slot;
-  if ((dpc_xy_taps_smem == 1 || dpc_xy_taps_smem == 3) && a.slot < 0) {
-    a.slot = dpc_taps_upload(taps_x, K, taps_y, K, nullptr, 0, stream);
-    if (a.slot < 0) return DPC_ERR_CUDA;
-  }
-  if (V == 64 && dpc_xy_taps_smem == 2 && !zero_ptr) {
-    const int grid = a.nslices < 3 * 148 ? a.nslices : 3 * 148;
-#ifndef DPC_EMU
-    cudaError_t e = (K == 21)
-        ? cudaFuncSetAttribute(dpc_conv_xy64_pf_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XYPF_SMEM_BYTES)
-        : cudaFuncSetAttribute(dpc_conv_xy64_pf_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_XYPF_SMEM_BYTES);
-    if (e != cudaSuccess) return DPC_ERR_CUDA;
-#endif
-    if (K == 21) { DPC_LAUNCH(dpc_conv_xy64_pf_kernel<21>, dim3(grid), dim3(256), DPC_XYPF_SMEM_BYTES, stream, a); }
-    else { DPC_LAUNCH(dpc_conv_xy64_pf_kernel<11>, dim3(grid), dim3(256), DPC_XYPF_SMEM_BYTES, stream, a); }
-    return DPC_OK;
-  }
-  if (V == 64) {
-    if (dpc_xy_taps_smem == 1) return K == 21 ? dpc_conv_xy_fast_go<64, 21, 256, 5>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256, 5>(a, stream);
-    if (dpc_xy_taps_smem == 3) return K == 21 ? dpc_conv_xy_fast_go<64, 21, 256, 6>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256, 6>(a, stream);
-    if (K == 21) return small ? dpc_conv_xy_fast_go<64, 21, 128>(a, stream) : dpc_conv_xy_fast_go<64, 21, 256>(a, stream);
-    return small ? dpc_conv_xy_fast_go<64, 11, 128>(a, stream) : dpc_conv_xy_fast_go<64, 11, 256>(a, stream);
-  }
-  if (V == 32) return K == 21 ? dpc_conv_xy_fast_go<32, 21, 256>(a, stream) : dpc_conv_xy_fast_go<32, 11, 256>(a, stream);
-  return K == 21 ? dpc_conv_xy_fast_go<128, 21, 256>(a, stream) : dpc_conv_xy_fast_go<128, 11, 256>(a, stream);
+  const bool host_taps = hx && hy && !dpc_ignore_host_taps;
+  if (host_taps) { dpc_build_taps_pairs(hx, K, rev, a.ht.px); dpc_build_taps_dup(hy, K, rev, a.ht.dy); }
+  else { for (int i = 0; i < 24; ++i) { a.ht.px[i] = make_float2(0.f, 0.f); a.ht.dy[i] = make_float2(0.f, 0.f); } }
+  if (V == 64) return K == 21 ? dpc_conv_xy_fast_pick<64, 21>(a, host_taps, stream) : dpc_conv_xy_fast_pick<64, 11>(a, host_taps, stream);
+  if (V == 32) return K == 21 ? dpc_conv_xy_fast_pick<32, 21>(a, host_taps, stream) : dpc_conv_xy_fast_pick<32, 11>(a, host_taps, stream);
+  return K == 21 ? dpc_conv_xy_fast_pick<128, 21>(a, host_taps, stream) : dpc_conv_xy_fast_pick<128, 11>(a, host_taps, stream);
 }
 
 // `extras`: drc_probs / proj_depth outputs (forward) or their gradients (backward) requested
@@ -890,57 +711,75 @@ static inline bool dpc_conv_z_fast_supported(int V, int Vz, int Kz, int plz, boo
   return dpc_fast_v(V) && Vz == V && dpc_fast_k(Kz) && plz == (Kz - 1) / 2 && !extras;
 }
 
-template <int V, int K>
-static inline int dpc_conv_z_fwd_fast_go(const DpcConvZArgs& a, int B, void* stream) {
-  constexpr int MINB = (V == 128) ? 3 : 4;
+// CT (host taps): 40 registers -> six 256-thread CTAs per SM at V <= 64 (the 64 KiB tile of V = 128 allows three either way)
+template <int V, int K, bool CT>
+static inline int dpc_conv_z_fwd_fast_go1(const DpcConvZArgs& a, int B, void* stream) {
+  constexpr int MINB = (V == 128) ? 3 : (CT ? 6 : 4);
   const size_t smem = (size_t)V * 128 * sizeof(float);
 #ifndef DPC_EMU
   if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(dpc_conv_z_fast_fwd_kernel<V, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      cudaFuncSetAttribute(dpc_conv_z_fast_fwd_kernel<V, K, MINB, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return DPC_ERR_CUDA;
 #endif
-  DPC_LAUNCH((dpc_conv_z_fast_fwd_kernel<V, K, MINB>), dim3(V / (128 / V), B), dim3(DPC_ZF_THREADS), smem, stream, a);
+  DPC_LAUNCH((dpc_conv_z_fast_fwd_kernel<V, K, MINB, CT>), dim3(V / (128 / V), B), dim3(DPC_ZF_THREADS), smem, stream, a);
   return DPC_OK;
+}
+template <int V, int K>
+static inline int dpc_conv_z_fwd_fast_go(const DpcConvZArgs& a, int B, void* stream) {
+  return a.use_ht ? dpc_conv_z_fwd_fast_go1<V, K, true>(a, B, stream) : dpc_conv_z_fwd_fast_go1<V, K, false>(a, B, stream);
+}
+
+static inline void dpc_set_taps_z(DpcTapsZ* ht, int* use_ht, const float* hz, int K, int rev) {
+  *use_ht = (hz && !dpc_ignore_host_taps) ? 1 : 0;
+  if (*use_ht) dpc_build_taps_dup(hz, K, rev, ht->dz);
+  else for (int i = 0; i < 24; ++i) ht->dz[i] = make_float2(0.f, 0.f);
 }
 
 static inline int dpc_conv_z_fwd_fast_launch(const float* in, const float* taps_z, int Kz, const float* scale, int mode,
                                              float eps, float cam_dist, float max_depth, int flip_y, int B, int Vz, int V,
                                              float* vox_out, uint32_t* mask2_out, float* proj, float* probs, float* depth,
-                                             void* stream) {
+                                             const float* hz, void* stream) {
   DpcConvZArgs a;
   a.in = in; a.taps = taps_z; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = eps;
   a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V;
   a.TY = dpc_z_tile_cpasync ? -(128 / V) : (128 / V);      // sign = tile load method (experiment knob)
   a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = probs; a.depth = depth;
+  dpc_set_taps_z(&a.ht, &a.use_ht, hz, Kz, 0);
   if (V == 32) return Kz == 21 ? dpc_conv_z_fwd_fast_go<32, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<32, 11>(a, B, stream);
   if (V == 64) return Kz == 21 ? dpc_conv_z_fwd_fast_go<64, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<64, 11>(a, B, stream);
   return Kz == 21 ? dpc_conv_z_fwd_fast_go<128, 21>(a, B, stream) : dpc_conv_z_fwd_fast_go<128, 11>(a, B, stream);
 }
 
-template <int V, int K>
-static inline int dpc_conv_z_bwd_lean_go(const DpcConvZBwdArgs& a, int B, void* stream) {
-  constexpr int MINB = (V == 128) ? 3 : 4;
+template <int V, int K, bool CT>
+static inline int dpc_conv_z_bwd_lean_go1(const DpcConvZBwdArgs& a, int B, void* stream) {
+  constexpr int MINB = (V == 128) ? 3 : (CT ? 6 : 4);
   const size_t smem = (size_t)V * 128 * sizeof(float);
 #ifndef DPC_EMU
   if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(dpc_conv_z_fast_bwd_lean_kernel<V, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      cudaFuncSetAttribute(dpc_conv_z_fast_bwd_lean_kernel<V, K, MINB, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return DPC_ERR_CUDA;
 #endif
-  DPC_LAUNCH((dpc_conv_z_fast_bwd_lean_kernel<V, K, MINB>), dim3(V / (128 / V), B), dim3(DPC_ZF_THREADS), smem, stream, a);
+  DPC_LAUNCH((dpc_conv_z_fast_bwd_lean_kernel<V, K, MINB, CT>), dim3(V / (128 / V), B), dim3(DPC_ZF_THREADS), smem, stream, a);
   return DPC_OK;
 }
+template <int V, int K>
+static inline int dpc_conv_z_bwd_lean_go(const DpcConvZBwdArgs& a, int B, void* stream) {
+  return a.use_ht ? dpc_conv_z_bwd_lean_go1<V, K, true>(a, B, stream) : dpc_conv_z_bwd_lean_go1<V, K, false>(a, B, stream);
+}
 
+// hz: the FORWARD taps on the host (nullable); `rev` says the kernel is to read them back to front.
 static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* mask2, const float* scale,
                                              const float* taps_rev, int Kz, int mode, float eps, float cam_dist,
                                              float max_depth, int flip_y, int B, int Vz, int V, const float* g_proj,
                                              const float* g_vox, const float* g_probs, const float* g_depth, float* d_in,
-                                             float* d_scale, int rev, void* stream) {
+                                             float* d_scale, int rev, const float* hz, void* stream) {
   DpcConvZBwdArgs a;
   a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps_rev; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = rev;
   a.mode = mode; a.eps = eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
   a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;
   a.g_proj = g_proj; a.g_vox = g_vox; a.g_probs = g_probs; a.g_depth = g_depth; a.d_in = d_in; a.d_scale = d_scale;
   const bool lean = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
+  dpc_set_taps_z(&a.ht, &a.use_ht, lean ? hz : nullptr, Kz, rev);
   if (lean) {
     if (dpc_z_tile_cpasync) a.TY = -1;
     if (V == 32) return Kz == 21 ? dpc_conv_z_bwd_lean_go<32, 21>(a, B, stream) : dpc_conv_z_bwd_lean_go<32, 11>(a, B, stream);

@@ -88,8 +88,9 @@ class ModelPointCloud(nn.Module):
         if is_training and cfg.pc_point_dropout != 1:
             keep = get_dropout_prob(cfg, global_step)
             all_points, all_rgb = point_cloud.pc_point_dropout(all_points, all_rgb, keep)
-        sigma = torch.tensor(get_smooth_sigma(cfg, global_step), dtype=torch.float32, device=all_points.device)
-        kernel = gauss_kernel.smoothing_kernel(cfg, sigma)
+        # sigma is a function of the step count (model_pc.py:35-40): a host value, so the taps are built
+        # on the CPU and the renderer receives them as launch parameters as well as a device buffer
+        kernel = gauss_kernel.smoothing_kernel(cfg, float(get_smooth_sigma(cfg, global_step)))
         trans = outputs.get("predicted_translation") if cfg.predict_translation else None
         with torch.autocast(device_type=all_points.device.type, enabled=False):   # the renderer is fp32
             proj_out = point_cloud.pointcloud_project_fast(

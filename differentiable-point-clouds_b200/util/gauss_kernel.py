@@ -6,7 +6,11 @@
 
 sigma is a run-time value (a function of the global step, model_pc.py:35-40), so the taps are a
 device buffer handed to the kernels, never a compile-time constant.  They are a few dozen
-floats; building them is plain torch on whatever device sigma lives on.
+floats; building them is plain torch on whatever device sigma lives on.  When sigma is known on
+the HOST (a Python float or a CPU tensor -- the reference's schedule is a function of the step
+count) the taps are built on the CPU, exactly as the oracle builds them, and the kernel object
+keeps that host copy next to the device copy: the fused path then passes the taps to the
+smoothing kernels as launch parameters (uniform registers; see csrc/dpc_smooth_fast.cuh).
 """
 import math
 
@@ -28,13 +32,20 @@ def gauss_kernel_1d(l, sig):
     return k / k.sum()
 
 
+def _attach_taps(out, taps_xy, taps_z):
+    out.taps_xy = taps_xy.contiguous()
+    out.taps_z = out.taps_xy if taps_z is taps_xy else taps_z.contiguous()
+    if out.taps_xy.device.type == "cpu":
+        out.host_taps_xy = out.taps_xy.detach()
+        out.host_taps_z = out.taps_z.detach()
+    return out
+
+
 def separable_kernels(kernel):
     size = kernel.shape[0]
     out = SeparableKernel([kernel.reshape(1, 1, size, 1, 1), kernel.reshape(1, size, 1, 1, 1),
                            kernel.reshape(size, 1, 1, 1, 1)])
-    out.taps_xy = kernel.contiguous()
-    out.taps_z = out.taps_xy
-    return out
+    return _attach_taps(out, kernel, kernel)
 
 
 def smoothing_kernel(cfg, sigma):
@@ -50,9 +61,7 @@ def smoothing_kernel(cfg, sigma):
         kz = gauss_kernel_1d(fsz_z, sigma * ratio)
         out = SeparableKernel([k1d.reshape(1, 1, fsz, 1, 1), k1d.reshape(1, fsz, 1, 1, 1),
                                kz.reshape(fsz_z, 1, 1, 1, 1)])
-        out.taps_xy = k1d.contiguous()
-        out.taps_z = kz.contiguous()
-        return out
+        return _attach_taps(out, k1d, kz)
     if not cfg.pc_separable_gauss_filter:
         # the reference reaches an unbound local here (gauss_kernel.py:51-54)
         raise NotImplementedError("pc_separable_gauss_filter=false has no kernel in the reference either")

@@ -70,15 +70,36 @@ def _taps_1d(k):
 
 class SeparableKernel(list):
     """[k1, k2, k3] as the reference builds it (gauss_kernel.py:27-32,46-50) that also remembers
-    the 1-D taps, so the fused path knows x and y share one tap vector."""
+    the 1-D taps, so the fused path knows x and y share one tap vector.
+
+    host_taps_xy / host_taps_z: the same taps as CPU fp32 tensors when sigma was known on the host
+    (a float, or a CPU tensor): the fused path then hands them to the kernels as launch parameters
+    (include/dpc_b200.h, taps_xy_host).  The device copies are made once per device and cached."""
     taps_xy = None
     taps_z = None
+    host_taps_xy = None
+    host_taps_z = None
+    _dev_cache = None
+
+    def device_taps(self, device):
+        """(taps_xy, taps_z) on `device`."""
+        if self.taps_xy.device == device:
+            return self.taps_xy, self.taps_z
+        if self._dev_cache is None:
+            self._dev_cache = {}
+        hit = self._dev_cache.get(device)
+        if hit is None:
+            txy = self.taps_xy.to(device)
+            tz = txy if self.taps_z is self.taps_xy else self.taps_z.to(device)
+            hit = self._dev_cache[device] = (txy, tz)
+        return hit
 
 
-def _split_kernel(kernel):
-    """-> (taps_x, taps_y, taps_z, shared_xy) as 1-D fp32 tensors."""
+def _split_kernel(kernel, device=None):
+    """-> (taps_x, taps_y, taps_z, shared_xy) as 1-D fp32 tensors (on `device` when given)."""
     if isinstance(kernel, SeparableKernel) and kernel.taps_xy is not None:
-        return kernel.taps_xy, kernel.taps_xy, kernel.taps_z, True
+        txy, tz = kernel.device_taps(device) if device is not None else (kernel.taps_xy, kernel.taps_z)
+        return txy, txy, tz, True
     if not isinstance(kernel, (list, tuple)) or len(kernel) != 3:
         raise ValueError("kernel must be the list of three separable filters returned by smoothing_kernel "
                          "(the reference's non-separable branch is dead code, gauss_kernel.py:51-54)")
@@ -215,16 +236,16 @@ def smoothen_voxels3d(cfg, voxels, kernel):
                                   "gauss_kernel.py:51-54)")
     if voxels.dim() != 5 or voxels.shape[-1] != 1:
         raise ValueError("voxels must be [B,Vz,V,V,1]")
-    tx, ty, tz, _ = _split_kernel(kernel)
     dev = voxels.device
+    tx, ty, tz, _ = _split_kernel(kernel, dev)
     out = _SmoothFn.apply(voxels.squeeze(-1), _dev_taps(tx, dev), _dev_taps(ty, dev), _dev_taps(tz, dev))
     return out.unsqueeze(-1)
 
 
 def convolve_rgb(cfg, voxels_rgb, kernel):
     """[B,Vz,V,V,3] -> same: each colour channel smoothed separately (point_cloud.py:148-154)."""
-    tx, ty, tz, _ = _split_kernel(kernel)
     dev = voxels_rgb.device
+    tx, ty, tz, _ = _split_kernel(kernel, dev)
     b = voxels_rgb.shape[0]
     chans = voxels_rgb.permute(4, 0, 1, 2, 3).reshape((3 * b,) + tuple(voxels_rgb.shape[1:4])).contiguous()
     out = _SmoothFn.apply(chans, _dev_taps(tx, dev), _dev_taps(ty, dev), _dev_taps(tz, dev))
@@ -429,16 +450,23 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation,
     if scaling_factor is not None and scaling_factor.numel() != b:
         raise ValueError("scaling_factor must be [B,1]")
     parts = None
+    host_xy = host_z = None
     if kernel is not None:
         if not cfg.pc_separable_gauss_filter:
             raise NotImplementedError("only the separable filter exists (gauss_kernel.py:51-54)")
-        tx, ty, tz, shared = _split_kernel(kernel)
+        tx, ty, tz, shared = _split_kernel(kernel, dev)
         parts = (_dev_taps(tx, dev), _dev_taps(ty, dev), _dev_taps(tz, dev), shared)
+        host_xy = getattr(kernel, "host_taps_xy", None)
+        host_z = getattr(kernel, "host_taps_z", None)
     if all_rgb is None and _fused_supported(cfg, point_cloud, parts):
         params = ProjectParams(B=b, N=n, Vz=vz, V=v, pose_kind=_pose_kind(cfg), mode=_proj_mode(cfg),
                                K=parts[0].numel() if parts else 0, Kz=parts[2].numel() if parts else 0,
                                focal_const=float(cfg.focal_length), cam_dist=float(cfg.camera_distance),
                                clip_eps=float(cfg.drc_logsum_clip_val), max_depth=float(cfg.max_depth))
+        if parts and host_xy is not None and host_z is not None:
+            # CPU copies of the taps: read by the C-ABI during each call, kept alive on `params`
+            params.taps_xy_host, params.taps_z_host = host_xy.data_ptr(), host_z.data_ptr()
+            params._host_taps = (host_xy, host_z)
         tr_pc, voxels, proj = _ProjectFastFn.apply(
             point_cloud, transform, predicted_translation, focal_length, scaling_factor,
             parts[0] if parts else None, parts[2] if parts else None, params)

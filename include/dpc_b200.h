@@ -52,9 +52,11 @@ extern "C" {
 int dpc_abi_version(void);
 const char* dpc_error_string(int code);
 int dpc_last_cuda_error(void);
-/* Experiment knob for benchmark sweeps (key 0/1: points per thread of the splat forward/backward
- * kernels, 1|2|4; key 2: threads per CTA of the 64^3 xy-smoothing kernel, 256|128).
- * Process-wide, not thread-safe, not needed in normal use. */
+/* Experiment / diagnostics knobs used by the benchmark sweeps (not needed in normal use; process-wide,
+ * not thread-safe).  key 0 / 1: points per thread of the forward / backward splat kernel (1|2|4);
+ * key 3: stage events (see dpc_debug_stage_ms); key 5: 1 = ignore host taps (run the vector-register
+ * smoothing kernels); key 6: 1 = cp.async tile load in the depth kernels; key 7: conv_xy diagnostics
+ * (1 memory path only, 2 arithmetic only, 3 empty CTAs, 4/5 skip the x / y correlation). */
 int dpc_debug_set(int key, int value);
 /* key 3 = 1: record CUDA events around every stage of the fused forward/backward; this returns the
  * six stage durations (ms) of the last instrumented step (synchronises on the last event). */
@@ -133,7 +135,13 @@ int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
  *   saved (dpc_project_fast_saved_bytes): the two clip masks as bit planes; written by the forward,
  *     read by the backward of the same call -- keep it until then.
  * taps: fp32 device arrays of K / Kz taps (K = Kz = 0: no smoothing kernel, taps ignored); the
- * backward takes the SAME taps (it reads them back to front). */
+ * backward takes the SAME taps (it reads them back to front).
+ * taps_xy_host / taps_z_host (optional, may be NULL): the SAME tap values in HOST memory, read
+ *   during the call (not retained).  The reference derives sigma from the global step
+ *   (model_pc.py:35-40), so a training loop knows the taps on the host.  Given them, the smoothing
+ *   kernels receive the taps as launch parameters (constant bank -> uniform registers), need half
+ *   the registers and run 5-6 CTAs per SM instead of 3-4 (~10 % faster forward+backward at 64^3,
+ *   K = 21).  The caller guarantees host and device taps hold identical values. */
 #define DPC_FLAG_SCRATCH_RAW_ZERO 1
 
 typedef struct {
@@ -143,6 +151,8 @@ typedef struct {
   int K, Kz;            /* tap counts along x/y and along depth; 0 = no smoothing */
   float focal_const, cam_dist, clip_eps, max_depth;
   int flags;            /* DPC_FLAG_* */
+  const float* taps_xy_host;   /* optional host copy of taps_xy (K floats), or NULL */
+  const float* taps_z_host;    /* optional host copy of taps_z (Kz floats), or NULL */
 } dpc_project_params;
 
 int64_t dpc_project_fast_scratch_bytes(const dpc_project_params* p);

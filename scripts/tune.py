@@ -21,8 +21,9 @@ def main():
         if clustered:
             pc = bench.make_inputs(bench.B, 0, clustered=True)[0]
             pipe.pc.copy_(pc.to(dev))
-        for zmin, zcp in ((0, 0), (1, 0), (3, 0)):
-            pipe.L.dpc_debug_set(5, zmin)        # conv_xy diagnostics: 0 normal, 1 memory path only, 2 arithmetic only
+        for zmin, zcp in ((1, 0), (0, 0), (0, 1)):
+            pipe.L.dpc_debug_set(5, zmin)        # 1 = ignore the host taps (vector-register kernels)
+            pipe.L.dpc_debug_set(6, zcp)         # 1 = cp.async tile load in the depth kernels
             for _ in range(3):
                 pipe.step()
             st = pipe.stage_times(20, flush)
@@ -33,11 +34,12 @@ def main():
                 pipe.step()
             e1.record()
             torch.cuda.synchronize()
-            key = "%s_xyct%d" % ("clustered" if clustered else "spread", zmin)
+            key = "%s_devtaps%d_zcp%d" % ("clustered" if clustered else "spread", zmin, zcp)
             out[key] = {k: round(v * 1000, 2) for k, v in st.items()}
             out[key]["step_us"] = round(e0.elapsed_time(e1) / 20 * 1000, 2)
             print(key, out[key], flush=True)
     pipe.L.dpc_debug_set(5, 0)
+    pipe.L.dpc_debug_set(6, 0)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune.json"), "w"), indent=1)
 
 

@@ -32,8 +32,9 @@ def make_cfg(over):
     return default_config(**over)
 
 
-def run_impl(impl, fx, device="cpu", need_grad=True, dtype=torch.float32):
+def run_impl(impl, fx, device="cpu", need_grad=True, dtype=torch.float32, host_sigma=False):
     """impl: module-like with smoothing_kernel() and pointcloud_project_fast().
+    host_sigma: hand sigma over as a Python float (the product then also keeps the taps on the host).
     Returns (outputs dict of detached cpu tensors, grads dict)."""
     cfg = make_cfg(fx["cfg_over"])
     leaves, args = {}, {}
@@ -49,7 +50,8 @@ def run_impl(impl, fx, device="cpu", need_grad=True, dtype=torch.float32):
         args[k] = t
     kernel = None
     if "in_sigma" in fx:
-        kernel = impl.smoothing_kernel(cfg, torch.tensor(float(fx["in_sigma"]), dtype=torch.float32, device=device))
+        sig = float(fx["in_sigma"])
+        kernel = impl.smoothing_kernel(cfg, sig if host_sigma else torch.tensor(sig, dtype=torch.float32, device=device))
         if dtype != torch.float32:
             kernel = [k.to(dtype) for k in kernel]
     out = impl.pointcloud_project_fast(cfg, args["point_cloud"], args["transform"], args["predicted_translation"],

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_is_the_cuda_build_with_sm100a_code(lib):
     assert lib.dpc_is_cuda_build() == 1
-    assert lib.dpc_abi_version() == 1
+    assert lib.dpc_abi_version() == 2
     assert lib.dpc_error_string(-2).decode().startswith("unsupported shape")
 
 

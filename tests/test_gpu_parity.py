@@ -40,6 +40,14 @@ def test_golden_fixture(name):
     cases.assert_parity(fx, outs, grads)
 
 
+@pytest.mark.parametrize("name", cases.golden_names())
+def test_golden_fixture_host_sigma(name):
+    """sigma as a host value: the taps also travel as launch parameters (uniform-register kernels)."""
+    fx = cases.load_golden(name)
+    outs, grads = cases.run_impl(Product, fx, device=DEV, host_sigma=True)
+    cases.assert_parity(fx, outs, grads)
+
+
 @pytest.mark.parametrize("name", ["cfg1_drc_k11", "v64_small", "edge_points", "vox_z", "clustered_init"])
 def test_voxel_indices_bit_exact_through_c_abi(name):
     fx = cases.load_golden(name)
@@ -73,12 +81,14 @@ def _bench_inputs(b, n, v, spread, seed=1234):
     return pc, q, sc, gt
 
 
-def _run_both(cfg, pc, q, sc, gt, sigma, trans=None):
+def _run_both(cfg, pc, q, sc, gt, sigma, trans=None, host_sigma=False):
+    """host_sigma: sigma reaches the product as a Python float -> taps also on the host -> the
+    launch-parameter (uniform-register) smoothing kernels; otherwise the vector-register ones."""
     res = {}
     for name, mod_pc, mod_gk, dev in (("cuda", pcm, gk, DEV), ("oracle", O, O, "cpu")):
         leaves = [t.clone().to(dev).requires_grad_(True) for t in (pc, q, sc)]
         tr = trans.clone().to(dev).requires_grad_(True) if trans is not None else None
-        ker = mod_gk.smoothing_kernel(cfg, torch.tensor(sigma, device=dev))
+        ker = mod_gk.smoothing_kernel(cfg, sigma if (host_sigma and name == "cuda") else torch.tensor(sigma, device=dev))
         out = mod_pc.pointcloud_project_fast(cfg, leaves[0], leaves[1], tr, None, ker, leaves[2])
         loss = ((gt.to(dev) - out["proj"]) ** 2).sum() / 2 / pc.shape[0]
         loss.backward()
@@ -112,12 +122,13 @@ def test_config1_against_oracle(spread):
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
 
 
+@pytest.mark.parametrize("host_sigma", [False, True])
 @pytest.mark.parametrize("sigma", [3.0, 0.2])
-def test_full_benchmark_shape_against_oracle(sigma):
+def test_full_benchmark_shape_against_oracle(sigma, host_sigma):
     """BASELINE config 2 shape (V=64, N=8000, K=21); B=4 keeps the CPU oracle to a few seconds."""
     cfg = default_config(vox_size=64, pc_gauss_kernel_size=21)
     pc, q, sc, gt = _bench_inputs(4, 8000, 64, 0.5)
-    _compare(_run_both(cfg, pc, q, sc, gt, sigma))
+    _compare(_run_both(cfg, pc, q, sc, gt, sigma, host_sigma=host_sigma))
 
 
 def test_full_benchmark_shape_clustered_and_translation():
@@ -125,6 +136,7 @@ def test_full_benchmark_shape_clustered_and_translation():
     pc, q, sc, gt = _bench_inputs(2, 8000, 64, 0.025, seed=1235)
     tr = 0.05 * torch.randn(2, 3, generator=torch.Generator().manual_seed(9))
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0, trans=tr))
+    _compare(_run_both(cfg, pc, q, sc, gt, 3.0, trans=tr, host_sigma=True))
 
 
 def test_max_projection_full_shape():
@@ -143,6 +155,7 @@ def test_sweep_shapes_against_oracle(v, n, b):
     sc = torch.sigmoid(torch.randn(b, 1, generator=g))
     gt = (torch.rand(b, v, v, 1, generator=g) > 0.5).float()
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
+    _compare(_run_both(cfg, pc, q, sc, gt, 3.0, host_sigma=True))
 
 
 def test_transform_bit_exact_on_a_million_points():
