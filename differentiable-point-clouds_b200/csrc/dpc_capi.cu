@@ -5,6 +5,7 @@
 #include "dpc_splat.cuh"
 #include "dpc_smooth.cuh"
 #include "dpc_smooth_fast.cuh"
+#include "dpc_smooth_tc.cuh"
 
 static thread_local int g_last_cuda_error = 0;
 
@@ -17,7 +18,7 @@ static int dpc_check_launch() {
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
 // Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[8] = {4, 4, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
+static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
 // ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are
@@ -59,11 +60,14 @@ int dpc_debug_stage_ms(float* out6) {
 }
 
 int dpc_debug_set(int key, int value) {
-  if (key < 0 || key >= 8) return DPC_ERR_ARG;
+  if (key < 0 || key >= 16) return DPC_ERR_ARG;
   g_tune[key] = value;
   if (key == 5) dpc_ignore_host_taps = value ? 1 : 0;
   if (key == 6) dpc_z_tile_cpasync = value ? 1 : 0;
   if (key == 7) dpc_xy_dbg = value;
+#ifndef DPC_EMU
+  if (key == 8) dpc_tc_enable = value ? 1 : 0;
+#endif
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
@@ -151,6 +155,13 @@ static int launch_conv_xy(const float* in, float* out, const float* taps_x, int 
   if ((mask_bits_out || mask_bits_in) && ((V * V) % 32 != 0)) return DPC_ERR_SHAPE;
   if ((int64_t)B * Vz > 2147483647LL) return DPC_ERR_SHAPE;
   float* zero_ptr = zero_in ? const_cast<float*>(in) : nullptr;
+#ifndef DPC_EMU
+  // tensor-core path (dpc_smooth_tc.cuh): 64^3 grids, any tap count, same taps along x and y
+  if (dpc_tc_conv_xy_supported(V, Kx, pad_lo_x, Ky, pad_lo_y, taps_x, taps_y, (int64_t)B * Vz, zero_ptr)) {
+    DPC_TRY(dpc_tc_conv_xy_launch(in, out, taps_x, Kx, pad_lo_x, (int64_t)B * Vz, clip_in, mask_bits_out, mask_bits_in, rev, stream));
+    return dpc_check_launch();
+  }
+#endif
   if (taps_x && taps_y && dpc_conv_xy_fast_supported(V, Kx, pad_lo_x, Ky, pad_lo_y) && ((int64_t)B * Vz * V * V) % (V == 128 ? 16384 : 4096) == 0) {
     DPC_TRY(dpc_conv_xy_fast_launch(in, out, taps_x, taps_y, Kx, B, Vz, V, clip_in, mask_bits_out, mask_bits_in,
                                     rev, zero_ptr, hx, hy, stream));
@@ -184,6 +195,17 @@ static int launch_conv_z_fwd(const float* in, const float* taps_z, int Kz, int p
   if ((drc_probs || proj_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
   if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo_z < 0 || pad_lo_z >= Kz) return DPC_ERR_ARG;
+#ifndef DPC_EMU
+  if (dpc_tc_conv_z_supported(V, Vz, Kz, drc_probs != nullptr || proj_depth != nullptr)) {
+    DpcConvZArgs a;
+    dpc_set_taps_z(&a.ht, &a.use_ht, nullptr, 0, 0);
+    a.in = in; a.taps = taps_z; a.K = Kz; a.pl = pad_lo_z; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = clip_eps;
+    a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = 2;
+    a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = nullptr; a.depth = nullptr;
+    DPC_TRY(dpc_tc_conv_z_fwd_launch(a, stream));
+    return dpc_check_launch();
+  }
+#endif
   if (taps_z && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo_z, drc_probs != nullptr || proj_depth != nullptr)) {
     DPC_TRY(dpc_conv_z_fwd_fast_launch(in, taps_z, Kz, scale, mode, clip_eps, cam_dist, max_depth, flip_y, B, Vz, V,
                                        vox_out, mask2_out, proj, drc_probs, proj_depth, hz, stream));
@@ -215,6 +237,18 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
   if (!shape_ok(B, Vz, V) || Kz < 1 || Kz > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
   if (pad_lo < 0 || pad_lo >= Kz) return DPC_ERR_ARG;
   const bool lean_case = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
+#ifndef DPC_EMU
+  if (lean_case && dpc_tc_conv_z_supported(V, Vz, Kz, g_probs != nullptr || g_depth != nullptr)) {
+    DpcConvZBwdArgs a;
+    dpc_set_taps_z(&a.ht, &a.use_ht, nullptr, 0, 0);
+    a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps; a.K = Kz; a.pl = pad_lo; a.rev = rev;
+    a.mode = mode; a.eps = clip_eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
+    a.B = B; a.Vz = Vz; a.V = V; a.TY = 2;
+    a.g_proj = g_proj; a.g_vox = nullptr; a.g_probs = nullptr; a.g_depth = nullptr; a.d_in = d_in; a.d_scale = d_scale;
+    DPC_TRY(dpc_tc_conv_z_bwd_lean_launch(a, stream));
+    return dpc_check_launch();
+  }
+#endif
   if (taps && dpc_conv_z_fast_supported(V, Vz, Kz, pad_lo, g_probs != nullptr || g_depth != nullptr) &&
       (lean_case || dpc_conv_z_bwd_fast_general_ok(V))) {
     DPC_TRY(dpc_conv_z_bwd_fast_launch(vox, mask2, scale, taps, Kz, mode, clip_eps, cam_dist, max_depth, flip_y,

@@ -49,7 +49,7 @@
 // A and B K-major, N>>3 = 8 at bit 17, M>>4 = 8 at bit 24
 #define DPC_TC_IDESC 0x08100910u
 
-static int dpc_tc_enable = 1;     // dpc_debug_set key 8: 0 = FFMA2 kernels only
+static int dpc_tc_enable = 0;     // dpc_debug_set key 8: 1 = tensor-core kernels where supported
 
 DPC_DEV uint32_t dpc_tc_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,19 +100,20 @@ DPC_DEV void dpc_tc_ld32(uint32_t taddr, float* r) {
   for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
 }
 
-// v = hi + lo with hi, lo exactly representable in tf32 (round to nearest), |v - hi - lo| <= 2^-22 |v|
-DPC_DEV void dpc_tc_split(float v, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-  lo = __uint_as_float(l);
-}
+// v = hi + lo: hi = v rounded to tf32 (10 explicit mantissa bits; round to nearest, ties away, done on the
+// integer pipe -- cvt.rna.tf32.f32 is emulated with five instructions on sm_100a), lo = v - hi exactly (fp32).
+// The tensor core ignores the low 13 mantissa bits of lo, an error <= 2^-21 |v|.  No inf/nan handling:
+// an infinite voxel would poison its whole row through 0 * inf anyway.
+DPC_DEV float dpc_tc_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 
 // four consecutive K elements (k0 = 32*half + 4*chunk) of operand row `row`, hi and lo planes
 DPC_DEV void dpc_tc_store4(unsigned char* sm, int row, int half, int chunk, float a, float b, float c, float d) {
   float4 hi, lo;
-  dpc_tc_split(a, hi.x, lo.x); dpc_tc_split(b, hi.y, lo.y); dpc_tc_split(c, hi.z, lo.z); dpc_tc_split(d, hi.w, lo.w);
+  hi.x = dpc_tc_hi(a); hi.y = dpc_tc_hi(b); hi.z = dpc_tc_hi(c); hi.w = dpc_tc_hi(d);
+  const float2 m1 = make_float2(-1.0f, -1.0f);
+  const float2 l0 = __ffma2_rn(make_float2(hi.x, hi.y), m1, make_float2(a, b));     // v - hi, exact
+  const float2 l1 = __ffma2_rn(make_float2(hi.z, hi.w), m1, make_float2(c, d));
+  lo = make_float4(l0.x, l0.y, l1.x, l1.y);
   const uint32_t off = (uint32_t)half * DPC_TC_A_HALF + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
   *reinterpret_cast<float4*>(sm + off) = hi;
   *reinterpret_cast<float4*>(sm + DPC_TC_A_LO + off) = lo;
@@ -144,7 +145,9 @@ DPC_DEV void dpc_tc_build_toeplitz(unsigned char* sm, float* tp_hi, float* tp_lo
   for (int i = threadIdx.x; i < 192; i += DPC_TC_THREADS) {
     const int j = i - 64;
     const float t = (j >= 0 && j < K) ? dpc_tap(taps, K, j, rev) : 0.0f;
-    dpc_tc_split(t, tp_hi[i], tp_lo[i]);
+    const float th = dpc_tc_hi(t);
+    tp_hi[i] = th;
+    tp_lo[i] = dpc_tc_hi(t - th);
   }
   __syncthreads();
   const int n = threadIdx.x >> 1, h = threadIdx.x & 1;
@@ -201,9 +204,12 @@ DPC_DEV void dpc_tc_run(uint32_t sbase, uint32_t d_tmem, uint64_t* bar, unsigned
   unsigned char* sm = dpc_tc_dsm + (sbase - sraw)
 
 // ------------------------------------------------------------------------------ depth pass, forward
-// CTA = 128 rays (image rows y0, y0+1) x 64 depth levels; thread = ray.
+// CTA = 128 rays (image rows y0, y0+1) x 64 depth levels; thread = ray.  MODE = DPC_PROJ_*, HAS_S = occupancy
+// scale + clip stage present: compile-time, so the 64 unrolled levels carry no option tests.
+template <int MODE, bool HAS_S>
 __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_z_fwd_kernel(const __grid_constant__ DpcConvZArgs a) {
   constexpr int V = 64, Vz = 64;
+  constexpr bool CLAMPU = (MODE == DPC_PROJ_DRC);
   DPC_TC_SMEM_SETUP();
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t tmem = dpc_tc_prologue(sm, &bar, &tmem_slot, tp_hi, tp_lo, a.taps, a.K, a.pl, a.rev, 64);
@@ -218,8 +224,7 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_z_fwd_kernel(co
 #pragma unroll
     for (int q = 0; q < 16; ++q) dpc_tc_store4(sm, tid, q >> 3, q & 7, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
-  const bool has_s = a.scale != nullptr;
-  const float s = has_s ? a.scale[b] : 1.0f;
+  const float s = HAS_S ? a.scale[b] : 1.0f;
   const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
   dpc_tc_run(sbase, tmem, &bar, 0);
   float r[Vz];
@@ -235,26 +240,26 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_z_fwd_kernel(co
 #pragma unroll
   for (int z = 0; z < Vz; ++z) {
     float v = r[z];
-    if (has_s) {
+    if (HAS_S) {
       const float t = __fmul_rn(v, s);
-      v = dpc_clip01(t);
+      v = __saturatef(t);                        // clip to [0,1]; the clip passes the gradient iff it left t unchanged
       if (v == t) { if (z < 32) m0 |= 1u << z; else m1 |= 1u << (z - 32); }
     }
     vout[(size_t)z * V * V] = v;
-    if (a.mode == DPC_PROJ_MAX) {
+    if (MODE == DPC_PROJ_MAX) {
       mx = fmaxf(mx, v);
-    } else if (a.mode != DPC_PROJ_NONE) {
-      const float u = D.clampu ? fminf(fmaxf(v, D.lo), D.hi) : v;
+    } else if (MODE != DPC_PROJ_NONE) {
+      const float u = CLAMPU ? fminf(fmaxf(v, D.lo), D.hi) : v;
       float p = u * T[z >> 4];
       T[z >> 4] -= p;
       if (z == 0) p *= D.c0;
       S[z >> 4] += p;
     }
   }
-  if (a.mask2_out && has_s) *reinterpret_cast<uint2*>(a.mask2_out + (((size_t)b * V + y) * V + x) * 2) = make_uint2(m0, m1);
-  if (a.mode != DPC_PROJ_NONE) {
+  if (HAS_S && a.mask2_out) *reinterpret_cast<uint2*>(a.mask2_out + (((size_t)b * V + y) * V + x) * 2) = make_uint2(m0, m1);
+  if (MODE != DPC_PROJ_NONE) {
     float out = mx;
-    if (a.mode != DPC_PROJ_MAX) out = fmaf(T[0], fmaf(T[1], fmaf(T[2], S[3], S[2]), S[1]), S[0]);
+    if (MODE != DPC_PROJ_MAX) out = fmaf(T[0], fmaf(T[1], fmaf(T[2], S[3], S[2]), S[1]), S[0]);
     const int yo = a.flip_y ? (V - 1 - y) : y;
     a.proj[((size_t)b * V + yo) * V + x] = out;
   }
@@ -331,6 +336,7 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_z_bwd_lean_kern
 // ------------------------------------------------------------------------------ x and y passes
 // CTA = two depth slices (128 rows of 64 x).  [clip, pass bits] -> x pass -> y pass -> [* saved mask].
 // Both passes use the same Toeplitz operand (taps_x == taps_y, as smoothing_kernel builds them).
+template <bool CLIP, bool MOUT, bool MIN>
 __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, int K, int pl) {
   constexpr int V = 64;
   DPC_TC_SMEM_SETUP();
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_xy_kernel(const
   // saved clip mask of the OUTPUT voxels this thread will write (backward): thread = (slice, x), lane = x & 31,
   // word of row y = (base >> 5) + slice*128 + 2y + (x >> 5); lane l fetches rows l and l + 32.
   uint32_t mw0 = 0xffffffffu, mw1 = 0xffffffffu;
-  if (a.mask_in) {
+  if (MIN) {
     const uint32_t* mrow = a.mask_in + (base >> 5) + (size_t)(tid >> 6) * 128 + (warp & 1);
     mw0 = mrow[2 * lane];
     mw1 = mrow[2 * (lane + 32)];
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_xy_kernel(const
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int i = tid + DPC_TC_THREADS * k;       // float4 index within the two slices
-      if (a.mask_out) {
+      if (MOUT) {
         unsigned nib = ((v[k].x >= 0.0f && v[k].x <= 1.0f) ? 1u : 0u) | ((v[k].y >= 0.0f && v[k].y <= 1.0f) ? 2u : 0u) |
                        ((v[k].z >= 0.0f && v[k].z <= 1.0f) ? 4u : 0u) | ((v[k].w >= 0.0f && v[k].w <= 1.0f) ? 8u : 0u);
         unsigned word = nib << (4 * (tid & 7));
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_xy_kernel(const
         word |= __shfl_xor_sync(DPC_FULL, word, 4);
         if ((tid & 7) == 0) a.mask_out[(base >> 5) + (i >> 3)] = word;
       }
-      if (a.clip_in) { v[k].x = dpc_clip01(v[k].x); v[k].y = dpc_clip01(v[k].y); v[k].z = dpc_clip01(v[k].z); v[k].w = dpc_clip01(v[k].w); }
+      if (CLIP) { v[k].x = dpc_clip01(v[k].x); v[k].y = dpc_clip01(v[k].y); v[k].z = dpc_clip01(v[k].z); v[k].w = dpc_clip01(v[k].w); }
       const int row = i >> 4, c16 = i & 15;         // 16 float4 per row of 64
       dpc_tc_store4(sm, row, c16 >> 3, c16 & 7, v[k].x, v[k].y, v[k].z, v[k].w);
     }
@@ -382,8 +388,7 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_xy_kernel(const
     const int c = (yp & 31) >> 2;
 #pragma unroll
     for (int x = 0; x < V; ++x) {
-      float hi, lo;
-      dpc_tc_split(r[x], hi, lo);
+      const float hi = dpc_tc_hi(r[x]), lo = r[x] - hi;
       const uint32_t off = colb + (uint32_t)x * 128u + (uint32_t)((c ^ (x & 7)) << 4);
       *reinterpret_cast<float*>(sm + off) = hi;
       *reinterpret_cast<float*>(sm + DPC_TC_A_LO + off) = lo;
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_xy_kernel(const
 #pragma unroll
     for (int y = 0; y < V; ++y) {
       float v = r[y];
-      if (a.mask_in) {
+      if (MIN) {
         const uint32_t w = __shfl_sync(DPC_FULL, (y < 32) ? mw0 : mw1, y & 31);
         if (!((w >> lane) & 1u)) v = 0.0f;
       }
@@ -423,20 +428,43 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
   a.in = in; a.out = out; a.taps_x = taps; a.taps_y = taps; a.clip_in = clip_in; a.mask_out = mask_out; a.mask_in = mask_in;
   a.nslices = (int)nslices; a.rev = rev; a.zero_ptr = nullptr; a.dbg = 0;
   for (int i = 0; i < 24; ++i) { a.ht.px[i] = make_float2(0.f, 0.f); a.ht.dy[i] = make_float2(0.f, 0.f); }
-  if (cudaFuncSetAttribute(dpc_tc_conv_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess)
-    return DPC_ERR_CUDA;
-  DPC_LAUNCH(dpc_tc_conv_xy_kernel, dim3((unsigned)(nslices / 2)), dim3(DPC_TC_THREADS), DPC_TC_SMEM_BYTES, stream, a, K, pl);
-  return DPC_OK;
+#define DPC_TC_XY_GO(C, MO, MI) do { \
+    if (cudaFuncSetAttribute(dpc_tc_conv_xy_kernel<C, MO, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess) \
+      return DPC_ERR_CUDA; \
+    DPC_LAUNCH((dpc_tc_conv_xy_kernel<C, MO, MI>), dim3((unsigned)(nslices / 2)), dim3(DPC_TC_THREADS), DPC_TC_SMEM_BYTES, stream, a, K, pl); \
+    return DPC_OK; } while (0)
+  const int sel = (clip_in ? 4 : 0) | (mask_out ? 2 : 0) | (mask_in ? 1 : 0);
+  switch (sel) {
+    case 0: DPC_TC_XY_GO(false, false, false);
+    case 1: DPC_TC_XY_GO(false, false, true);
+    case 2: DPC_TC_XY_GO(false, true, false);
+    case 3: DPC_TC_XY_GO(false, true, true);
+    case 4: DPC_TC_XY_GO(true, false, false);
+    case 5: DPC_TC_XY_GO(true, false, true);
+    case 6: DPC_TC_XY_GO(true, true, false);
+    default: DPC_TC_XY_GO(true, true, true);
+  }
+#undef DPC_TC_XY_GO
 }
 
 static inline bool dpc_tc_conv_z_supported(int V, int Vz, int Kz, bool extras) {
   return dpc_tc_enable && V == 64 && Vz == 64 && Kz >= 1 && Kz <= DPC_MAX_TAPS && !extras;
 }
-static inline int dpc_tc_conv_z_fwd_launch(const DpcConvZArgs& a, void* stream) {
-  if (cudaFuncSetAttribute(dpc_tc_conv_z_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess)
+template <int MODE, bool HAS_S>
+static inline int dpc_tc_conv_z_fwd_go(const DpcConvZArgs& a, void* stream) {
+  if (cudaFuncSetAttribute(dpc_tc_conv_z_fwd_kernel<MODE, HAS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess)
     return DPC_ERR_CUDA;
-  DPC_LAUNCH(dpc_tc_conv_z_fwd_kernel, dim3(32, a.B), dim3(DPC_TC_THREADS), DPC_TC_SMEM_BYTES, stream, a);
+  DPC_LAUNCH((dpc_tc_conv_z_fwd_kernel<MODE, HAS_S>), dim3(32, a.B), dim3(DPC_TC_THREADS), DPC_TC_SMEM_BYTES, stream, a);
   return DPC_OK;
+}
+static inline int dpc_tc_conv_z_fwd_launch(const DpcConvZArgs& a, void* stream) {
+  const bool hs = a.scale != nullptr;
+  switch (a.mode) {
+    case DPC_PROJ_DRC: return hs ? dpc_tc_conv_z_fwd_go<DPC_PROJ_DRC, true>(a, stream) : dpc_tc_conv_z_fwd_go<DPC_PROJ_DRC, false>(a, stream);
+    case DPC_PROJ_MAX: return hs ? dpc_tc_conv_z_fwd_go<DPC_PROJ_MAX, true>(a, stream) : dpc_tc_conv_z_fwd_go<DPC_PROJ_MAX, false>(a, stream);
+    case DPC_PROJ_DRC_PROD: return hs ? dpc_tc_conv_z_fwd_go<DPC_PROJ_DRC_PROD, true>(a, stream) : dpc_tc_conv_z_fwd_go<DPC_PROJ_DRC_PROD, false>(a, stream);
+    default: return hs ? dpc_tc_conv_z_fwd_go<DPC_PROJ_NONE, true>(a, stream) : dpc_tc_conv_z_fwd_go<DPC_PROJ_NONE, false>(a, stream);
+  }
 }
 static inline int dpc_tc_conv_z_bwd_lean_launch(const DpcConvZBwdArgs& a, void* stream) {
   if (cudaFuncSetAttribute(dpc_tc_conv_z_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess)
