@@ -48,6 +48,8 @@ _SIGNATURES = {
     "dpc_is_cuda_build": (c_i, []),
     "dpc_debug_set": (c_i, [c_i, c_i]),
     "dpc_debug_stage_ms": (c_i, [c_p]),
+    "dpc_debug_trace_read": (c_i, [c_p]),
+    "dpc_debug_mma_bench": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
     "dpc_splat_fwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i,
                             c_p, c_p, c_p, c_p, c_p, c_p]),
     "dpc_splat_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i, c_i,
@@ -101,6 +103,8 @@ def lib():
                 "dpc_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
         _LIB = load_library(LIB_PATH)
+        if os.environ.get("DPC_TC"):      # experiment override of the smoothing-kernel family (dpc_debug_set key 8)
+            _LIB.dpc_debug_set(8, int(os.environ["DPC_TC"]))
     return _LIB
 
 

@@ -18,7 +18,7 @@ static int dpc_check_launch() {
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
 // Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
+static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
 // ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are
@@ -66,11 +66,33 @@ int dpc_debug_set(int key, int value) {
   if (key == 6) dpc_z_tile_cpasync = value ? 1 : 0;
   if (key == 7) dpc_xy_dbg = value;
 #ifndef DPC_EMU
-  if (key == 8) dpc_tc_enable = value ? 1 : 0;
+  if (key == 8) dpc_tc_enable = value;
+  if (key == 9) { int v = value; cudaMemcpyToSymbol(dpc_tcp_trace_on, &v, sizeof(int)); }
 #endif
   return DPC_OK;
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
+/* diagnostics: copy the 16 x 16 pipeline trace of CTA 0 (clock64 values) to host memory (synchronises) */
+int dpc_debug_trace_read(long long* host_out) {
+#ifndef DPC_EMU
+  if (!host_out) return DPC_ERR_NULL;
+  if (cudaMemcpyFromSymbol(host_out, dpc_tcp_trace, sizeof(long long) * 256) != cudaSuccess) return DPC_ERR_CUDA;
+  return cudaMemcpyFromSymbol(host_out + 256, dpc_tcp_cta_ns, sizeof(long long) * 480) == cudaSuccess ? DPC_OK : DPC_ERR_CUDA;
+#else
+  return DPC_ERR_ARG;
+#endif
+}
+/* diagnostics: tcgen05.mma micro-benchmark (see dpc_tc_mma_bench_kernel); out = 3 int64 per CTA (device memory) */
+int dpc_debug_mma_bench(long long* out, int nctas, int threads, int reps, int nmma, int spin, int M, int N, void* stream) {
+#ifndef DPC_EMU
+  if (!out || nctas < 1 || threads < 32 || threads > 512 || nmma < 1) return DPC_ERR_ARG;
+  if (cudaFuncSetAttribute(dpc_tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608) != cudaSuccess) return DPC_ERR_CUDA;
+  dpc_tc_mma_bench_kernel<<<nctas, threads, 196608, (cudaStream_t)stream>>>(out, reps, nmma, spin, M, N);
+  return dpc_check_launch();
+#else
+  return DPC_ERR_ARG;
+#endif
+}
 int dpc_is_cuda_build(void) {
 #ifdef DPC_EMU
   return 0;

@@ -49,7 +49,9 @@
 // A and B K-major, N>>3 = 8 at bit 17, M>>4 = 8 at bit 24
 #define DPC_TC_IDESC 0x08100910u
 
-static int dpc_tc_enable = 0;     // dpc_debug_set key 8: 1 = tensor-core kernels where supported
+// dpc_debug_set key 8: 0 = CUDA-core (FFMA2 / generic) kernels only, 1 = single-tile tensor-core kernels (this file;
+// kept as the simple reference form of the maths), 2 = persistent tensor-core pipelines (dpc_smooth_tcp.cuh; default)
+static int dpc_tc_enable = 2;
 
 DPC_DEV uint32_t dpc_tc_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -69,6 +71,14 @@ DPC_DEV void dpc_tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_
 }
 DPC_DEV void dpc_tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(dpc_tc_s32(bar)) : "memory");
+}
+// one lane of a converged warp (elect.sync): with a warp-uniform branch around it the compiler keeps the MMA
+// descriptors in uniform registers and emits the tcgen05.mma back to back; a divergent `lane == 0` branch costs
+// ~70 cycles of issue per MMA instead (R2UR / ELECT / BRA.U.ANY per instruction; measured, scripts/mma_bench.py)
+DPC_DEV uint32_t dpc_elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
+  return pred;
 }
 DPC_DEV void dpc_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 DPC_DEV void dpc_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -106,6 +116,65 @@ DPC_DEV void dpc_tc_ld32(uint32_t taddr, float* r) {
 // an infinite voxel would poison its whole row through 0 * inf anyway.
 DPC_DEV float dpc_tc_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 
+// this thread's TMEM lane, 32 consecutive columns <- r[0..31]
+DPC_DEV void dpc_tc_st32(uint32_t taddr, const float* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+      ::"r"(taddr),
+        "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
+        "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])),
+        "r"(__float_as_uint(r[8])), "r"(__float_as_uint(r[9])), "r"(__float_as_uint(r[10])), "r"(__float_as_uint(r[11])),
+        "r"(__float_as_uint(r[12])), "r"(__float_as_uint(r[13])), "r"(__float_as_uint(r[14])), "r"(__float_as_uint(r[15])),
+        "r"(__float_as_uint(r[16])), "r"(__float_as_uint(r[17])), "r"(__float_as_uint(r[18])), "r"(__float_as_uint(r[19])),
+        "r"(__float_as_uint(r[20])), "r"(__float_as_uint(r[21])), "r"(__float_as_uint(r[22])), "r"(__float_as_uint(r[23])),
+        "r"(__float_as_uint(r[24])), "r"(__float_as_uint(r[25])), "r"(__float_as_uint(r[26])), "r"(__float_as_uint(r[27])),
+        "r"(__float_as_uint(r[28])), "r"(__float_as_uint(r[29])), "r"(__float_as_uint(r[30])), "r"(__float_as_uint(r[31]))
+      : "memory");
+}
+DPC_DEV void dpc_tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// A operand from TMEM (row m in lane m, K element k in column a_tmem + k, 32 bits each), B from shared memory
+DPC_DEV void dpc_tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(DPC_TC_IDESC), "r"(accum) : "memory");
+}
+// 32 values of row-half `h` of this thread's operand row -> hi / lo planes in TMEM (columns a_hi + 32h .., a_lo + 32h ..)
+DPC_DEV void dpc_tc_split_st32(uint32_t a_hi_t, uint32_t a_lo_t, const float* v) {
+  float hi[32], lo[32];
+  const float2 m1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    hi[j] = dpc_tc_hi(v[j]); hi[j + 1] = dpc_tc_hi(v[j + 1]);
+    const float2 l = __ffma2_rn(make_float2(hi[j], hi[j + 1]), m1, make_float2(v[j], v[j + 1]));
+    lo[j] = l.x; lo[j + 1] = l.y;
+  }
+  dpc_tc_st32(a_hi_t, hi);
+  dpc_tc_st32(a_lo_t, lo);
+}
+// One elected thread: D = A * T with A = (a_hi, a_lo) planes of 64 TMEM columns each, T = (hi, lo) in shared memory
+DPC_DEV void dpc_tc_issue_ts(uint32_t a_hi_t, uint32_t a_lo_t, uint32_t t_base, uint32_t d_tmem, uint64_t* bar) {
+  const uint64_t dT = dpc_tc_desc(t_base);
+  uint32_t accum = 0;
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {          // a_lo*t_hi, a_hi*t_lo, a_hi*t_hi
+    const uint32_t at = (term == 0) ? a_lo_t : a_hi_t;
+    const uint32_t to = (term == 1) ? 2u * DPC_TC_T_HALF : 0u;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const uint64_t bd = dT + (uint64_t)((to + (uint32_t)(kk >> 2) * DPC_TC_T_HALF + (uint32_t)(kk & 3) * 32u) >> 4);
+      dpc_tc_mma_ts(d_tmem, at + (uint32_t)(8 * kk), bd, accum);
+      accum = 1;
+    }
+  }
+  dpc_tc_commit(bar);
+}
+
 // four consecutive K elements (k0 = 32*half + 4*chunk) of operand row `row`, hi and lo planes
 DPC_DEV void dpc_tc_store4(unsigned char* sm, int row, int half, int chunk, float a, float b, float c, float d) {
   float4 hi, lo;
@@ -121,28 +190,31 @@ DPC_DEV void dpc_tc_store4(unsigned char* sm, int row, int half, int chunk, floa
 
 // One elected thread: D[128 x 64] (TMEM columns d_tmem .. d_tmem+63) = A * T, three tf32 products, then
 // commit -> one arrival on `bar` once every MMA has completed (and has finished reading shared memory).
-DPC_DEV void dpc_tc_issue(uint32_t sbase, uint32_t d_tmem, uint64_t* bar) {
+// a_base: A_hi plane (A_lo 32 KiB above it); t_base: T_hi plane (T_lo 16 KiB above it); shared-window addresses.
+DPC_DEV void dpc_tc_issue2(uint32_t a_base, uint32_t t_base, uint32_t d_tmem, uint64_t* bar) {
+  const uint64_t dA = dpc_tc_desc(a_base), dT = dpc_tc_desc(t_base);
   uint32_t accum = 0;
 #pragma unroll
   for (int term = 0; term < 3; ++term) {          // small terms first: a_lo*t_hi, a_hi*t_lo, a_hi*t_hi
-    const uint32_t A = sbase + ((term == 0) ? DPC_TC_A_LO : 0u);
-    const uint32_t T = sbase + ((term == 1) ? DPC_TC_T_LO : DPC_TC_T_HI);
+    const uint32_t ao = (term == 0) ? DPC_TC_A_LO : 0u;
+    const uint32_t to = (term == 1) ? 2u * DPC_TC_T_HALF : 0u;
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {               // K = 64 in steps of 8 tf32 (32 bytes inside the 128-byte swizzle row)
-      const uint64_t ad = dpc_tc_desc(A + (uint32_t)(kk >> 2) * DPC_TC_A_HALF + (uint32_t)(kk & 3) * 32u);
-      const uint64_t bd = dpc_tc_desc(T + (uint32_t)(kk >> 2) * DPC_TC_T_HALF + (uint32_t)(kk & 3) * 32u);
+      const uint64_t ad = dA + (uint64_t)((ao + (uint32_t)(kk >> 2) * DPC_TC_A_HALF + (uint32_t)(kk & 3) * 32u) >> 4);
+      const uint64_t bd = dT + (uint64_t)((to + (uint32_t)(kk >> 2) * DPC_TC_T_HALF + (uint32_t)(kk & 3) * 32u) >> 4);
       dpc_tc_mma(d_tmem, ad, bd, accum);
       accum = 1;
     }
   }
   dpc_tc_commit(bar);
 }
+DPC_DEV void dpc_tc_issue(uint32_t sbase, uint32_t d_tmem, uint64_t* bar) { dpc_tc_issue2(sbase, sbase + DPC_TC_T_HI, d_tmem, bar); }
 
 // Toeplitz operand of a correlation with zero padding: out[n] = sum_j tap(j) in[n + j - pl]  =>
 // T[n][k] = tap(k - n + pl); rows n (the MMA's N), K-major.  tap(j) = taps[rev ? K-1-j : j] inside 0..K-1
 // (NULL taps = identity).  All 128 threads; contains a __syncthreads.
-DPC_DEV void dpc_tc_build_toeplitz(unsigned char* sm, float* tp_hi, float* tp_lo, const float* taps, int K, int pl, int rev) {
-  for (int i = threadIdx.x; i < 192; i += DPC_TC_THREADS) {
+DPC_DEV void dpc_tc_build_toeplitz(unsigned char* tbase, float* tp_hi, float* tp_lo, const float* taps, int K, int pl, int rev) {
+  for (int i = threadIdx.x; i < 192; i += (int)blockDim.x) {
     const int j = i - 64;
     const float t = (j >= 0 && j < K) ? dpc_tap(taps, K, j, rev) : 0.0f;
     const float th = dpc_tc_hi(t);
@@ -150,13 +222,15 @@ DPC_DEV void dpc_tc_build_toeplitz(unsigned char* sm, float* tp_hi, float* tp_lo
     tp_lo[i] = dpc_tc_hi(t - th);
   }
   __syncthreads();
-  const int n = threadIdx.x >> 1, h = threadIdx.x & 1;
+  if (threadIdx.x < 128) {
+    const int n = threadIdx.x >> 1, h = threadIdx.x & 1;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int i0 = 32 * h + 4 * c - n + pl + 64;    // in [1, 189]
-    const uint32_t off = (uint32_t)h * DPC_TC_T_HALF + (uint32_t)n * 128u + (uint32_t)((c ^ (n & 7)) << 4);
-    *reinterpret_cast<float4*>(sm + DPC_TC_T_HI + off) = make_float4(tp_hi[i0], tp_hi[i0 + 1], tp_hi[i0 + 2], tp_hi[i0 + 3]);
-    *reinterpret_cast<float4*>(sm + DPC_TC_T_LO + off) = make_float4(tp_lo[i0], tp_lo[i0 + 1], tp_lo[i0 + 2], tp_lo[i0 + 3]);
+    for (int c = 0; c < 8; ++c) {
+      const int i0 = 32 * h + 4 * c - n + pl + 64;    // in [1, 189]
+      const uint32_t off = (uint32_t)h * DPC_TC_T_HALF + (uint32_t)n * 128u + (uint32_t)((c ^ (n & 7)) << 4);
+      *reinterpret_cast<float4*>(tbase + off) = make_float4(tp_hi[i0], tp_hi[i0 + 1], tp_hi[i0 + 2], tp_hi[i0 + 3]);
+      *reinterpret_cast<float4*>(tbase + 2u * DPC_TC_T_HALF + off) = make_float4(tp_lo[i0], tp_lo[i0 + 1], tp_lo[i0 + 2], tp_lo[i0 + 3]);
+    }
   }
 }
 
@@ -166,7 +240,7 @@ DPC_DEV uint32_t dpc_tc_prologue(unsigned char* sm, uint64_t* bar, uint32_t* slo
                                  const float* taps, int K, int pl, int rev, uint32_t ncols) {
   if ((threadIdx.x >> 5) == 0) dpc_tc_alloc(slot, ncols);
   if (threadIdx.x == 0) dpc_mbar_init(bar, 1);
-  dpc_tc_build_toeplitz(sm, tp_hi, tp_lo, taps, K, pl, rev);
+  dpc_tc_build_toeplitz(sm + DPC_TC_T_HI, tp_hi, tp_lo, taps, K, pl, rev);
   dpc_fence_proxy_async();
   dpc_tc_fence_before();
   __syncthreads();
@@ -185,9 +259,12 @@ DPC_DEV void dpc_tc_run(uint32_t sbase, uint32_t d_tmem, uint64_t* bar, unsigned
   dpc_fence_proxy_async();
   dpc_tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    dpc_tc_fence_after();
-    dpc_tc_issue(sbase, d_tmem, bar);
+  if ((threadIdx.x >> 5) == 0) {
+    if (dpc_elect_one()) {
+      dpc_tc_fence_after();
+      dpc_tc_issue(sbase, d_tmem, bar);
+    }
+    __syncwarp();
   }
   dpc_mbar_wait(bar, phase);
   dpc_tc_fence_after();
@@ -415,10 +492,70 @@ __global__ void __launch_bounds__(DPC_TC_THREADS, 2) dpc_tc_conv_xy_kernel(const
   dpc_tc_epilogue(tmem, 128);
 }
 
+#include "dpc_smooth_tcp.cuh"
+
 // ------------------------------------------------------------------------------ dispatch
+// ---- 2-D tensor map of a [B,64,64,64] grid for the depth pass: inner dimension = the 4096 (y, x) positions of a
+// level, outer = the B*64 (b, level) rows; box = {128 positions, 64 levels} = one depth-pass tile.  The encoder is a
+// driver entry point fetched through the runtime (no link against libcuda).
+typedef CUresult (*DpcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static DpcEncodeTiledFn dpc_tc_encoder() {
+  static DpcEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<DpcEncodeTiledFn>(p);
+  }
+  return fn;
+}
+// effective kernel family: the pipelines need the tensor-map encoder of the driver; without it the single-tile kernels run
+static int dpc_tc_level() {
+  if (dpc_tc_enable >= 2) return dpc_tc_encoder() ? 2 : 1;
+  return dpc_tc_enable > 0 ? 1 : 0;
+}
+static int dpc_tc_make_zmap(CUtensorMap* m, const float* grid, int B) {
+  DpcEncodeTiledFn fn = dpc_tc_encoder();
+  if (!fn) return DPC_ERR_CUDA;
+  const cuuint64_t dims[2] = {4096, (cuuint64_t)B * 64};
+  const cuuint64_t strides[1] = {4096 * sizeof(float)};
+  const cuuint32_t box[2] = {128, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(grid), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DPC_OK : DPC_ERR_CUDA;
+}
+// 2-D view of nslices depth slices for the x / y passes: [nslices*64 rows (slice, y)][64 x], box {32 x, 128 rows},
+// 128-byte swizzle (16-byte chunk c of row r lands at chunk c ^ (r & 7))
+static int dpc_tc_make_xymap(CUtensorMap* m, const float* grid, int64_t nslices) {
+  DpcEncodeTiledFn fn = dpc_tc_encoder();
+  if (!fn) return DPC_ERR_CUDA;
+  const cuuint64_t dims[2] = {64, (cuuint64_t)nslices * 64};
+  const cuuint64_t strides[1] = {64 * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(grid), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DPC_OK : DPC_ERR_CUDA;
+}
+static int dpc_tc_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = 148;
+  }
+  return n;
+}
 static inline bool dpc_tc_conv_xy_supported(int V, int Kx, int plx, int Ky, int ply, const float* tx, const float* ty,
                                             int64_t nslices, const float* zero_ptr) {
-  return dpc_tc_enable && V == 64 && Kx == Ky && plx == ply && tx == ty && Kx >= 1 && Kx <= DPC_MAX_TAPS &&
+  return dpc_tc_level() && V == 64 && Kx == Ky && plx == ply && tx == ty && Kx >= 1 && Kx <= DPC_MAX_TAPS &&
          (nslices % 2) == 0 && !zero_ptr;
 }
 static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float* taps, int K, int pl, int64_t nslices,
@@ -434,6 +571,27 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
     DPC_LAUNCH((dpc_tc_conv_xy_kernel<C, MO, MI>), dim3((unsigned)(nslices / 2)), dim3(DPC_TC_THREADS), DPC_TC_SMEM_BYTES, stream, a, K, pl); \
     return DPC_OK; } while (0)
   const int sel = (clip_in ? 4 : 0) | (mask_out ? 2 : 0) | (mask_in ? 1 : 0);
+  if (dpc_tc_level() == 2) {
+    const int ntiles = (int)(nslices / 2), grid = ntiles < dpc_tc_sm_count() ? ntiles : dpc_tc_sm_count();
+    CUtensorMap xymap;
+    if (dpc_tc_make_xymap(&xymap, in, nslices) != DPC_OK) return DPC_ERR_CUDA;
+#define DPC_TCP_XY_GO(C, MO, MI) do { \
+    if (cudaFuncSetAttribute(dpc_tcp_conv_xy_kernel<C, MO, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess) \
+      return DPC_ERR_CUDA; \
+    DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, xymap, K, pl, ntiles); \
+    return DPC_OK; } while (0)
+    switch (sel) {
+      case 0: DPC_TCP_XY_GO(false, false, false);
+      case 1: DPC_TCP_XY_GO(false, false, true);
+      case 2: DPC_TCP_XY_GO(false, true, false);
+      case 3: DPC_TCP_XY_GO(false, true, true);
+      case 4: DPC_TCP_XY_GO(true, false, false);
+      case 5: DPC_TCP_XY_GO(true, false, true);
+      case 6: DPC_TCP_XY_GO(true, true, false);
+      default: DPC_TCP_XY_GO(true, true, true);
+    }
+#undef DPC_TCP_XY_GO
+  }
   switch (sel) {
     case 0: DPC_TC_XY_GO(false, false, false);
     case 1: DPC_TC_XY_GO(false, false, true);
@@ -448,7 +606,7 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
 }
 
 static inline bool dpc_tc_conv_z_supported(int V, int Vz, int Kz, bool extras) {
-  return dpc_tc_enable && V == 64 && Vz == 64 && Kz >= 1 && Kz <= DPC_MAX_TAPS && !extras;
+  return dpc_tc_level() && V == 64 && Vz == 64 && Kz >= 1 && Kz <= DPC_MAX_TAPS && !extras;
 }
 template <int MODE, bool HAS_S>
 static inline int dpc_tc_conv_z_fwd_go(const DpcConvZArgs& a, void* stream) {
@@ -457,8 +615,27 @@ static inline int dpc_tc_conv_z_fwd_go(const DpcConvZArgs& a, void* stream) {
   DPC_LAUNCH((dpc_tc_conv_z_fwd_kernel<MODE, HAS_S>), dim3(32, a.B), dim3(DPC_TC_THREADS), DPC_TC_SMEM_BYTES, stream, a);
   return DPC_OK;
 }
+template <int MODE, bool HAS_S>
+static inline int dpc_tcp_conv_z_fwd_go(const DpcConvZArgs& a, void* stream) {
+  if ((((uintptr_t)a.in) & 15u) != 0) return DPC_ERR_ARG;
+  CUtensorMap zmap;
+  if (dpc_tc_make_zmap(&zmap, a.in, a.B) != DPC_OK) return DPC_ERR_CUDA;
+  if (cudaFuncSetAttribute(dpc_tcp_conv_z_fwd_kernel<MODE, HAS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess)
+    return DPC_ERR_CUDA;
+  const int ntiles = 32 * a.B, grid = ntiles < dpc_tc_sm_count() ? ntiles : dpc_tc_sm_count();
+  DPC_LAUNCH((dpc_tcp_conv_z_fwd_kernel<MODE, HAS_S>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles);
+  return DPC_OK;
+}
 static inline int dpc_tc_conv_z_fwd_launch(const DpcConvZArgs& a, void* stream) {
   const bool hs = a.scale != nullptr;
+  if (dpc_tc_level() == 2) {
+    switch (a.mode) {
+      case DPC_PROJ_DRC: return hs ? dpc_tcp_conv_z_fwd_go<DPC_PROJ_DRC, true>(a, stream) : dpc_tcp_conv_z_fwd_go<DPC_PROJ_DRC, false>(a, stream);
+      case DPC_PROJ_MAX: return hs ? dpc_tcp_conv_z_fwd_go<DPC_PROJ_MAX, true>(a, stream) : dpc_tcp_conv_z_fwd_go<DPC_PROJ_MAX, false>(a, stream);
+      case DPC_PROJ_DRC_PROD: return hs ? dpc_tcp_conv_z_fwd_go<DPC_PROJ_DRC_PROD, true>(a, stream) : dpc_tcp_conv_z_fwd_go<DPC_PROJ_DRC_PROD, false>(a, stream);
+      default: return hs ? dpc_tcp_conv_z_fwd_go<DPC_PROJ_NONE, true>(a, stream) : dpc_tcp_conv_z_fwd_go<DPC_PROJ_NONE, false>(a, stream);
+    }
+  }
   switch (a.mode) {
     case DPC_PROJ_DRC: return hs ? dpc_tc_conv_z_fwd_go<DPC_PROJ_DRC, true>(a, stream) : dpc_tc_conv_z_fwd_go<DPC_PROJ_DRC, false>(a, stream);
     case DPC_PROJ_MAX: return hs ? dpc_tc_conv_z_fwd_go<DPC_PROJ_MAX, true>(a, stream) : dpc_tc_conv_z_fwd_go<DPC_PROJ_MAX, false>(a, stream);
@@ -467,6 +644,16 @@ static inline int dpc_tc_conv_z_fwd_launch(const DpcConvZArgs& a, void* stream) 
   }
 }
 static inline int dpc_tc_conv_z_bwd_lean_launch(const DpcConvZBwdArgs& a, void* stream) {
+  if (dpc_tc_level() == 2) {
+    if (cudaFuncSetAttribute(dpc_tcp_conv_z_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess)
+      return DPC_ERR_CUDA;
+    if ((((uintptr_t)a.vox) & 15u) != 0) return DPC_ERR_ARG;
+    CUtensorMap zmap;
+    if (dpc_tc_make_zmap(&zmap, a.vox, a.B) != DPC_OK) return DPC_ERR_CUDA;
+    const int ntiles = 32 * a.B, grid = ntiles < dpc_tc_sm_count() ? ntiles : dpc_tc_sm_count();
+    DPC_LAUNCH(dpc_tcp_conv_z_bwd_lean_kernel, dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles);
+    return DPC_OK;
+  }
   if (cudaFuncSetAttribute(dpc_tc_conv_z_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess)
     return DPC_ERR_CUDA;
   DPC_LAUNCH(dpc_tc_conv_z_bwd_lean_kernel, dim3(32, a.B), dim3(DPC_TC_THREADS), DPC_TC_SMEM_BYTES, stream, a);

@@ -61,6 +61,13 @@ int dpc_debug_set(int key, int value);
 /* key 3 = 1: record CUDA events around every stage of the fused forward/backward; this returns the
  * six stage durations (ms) of the last instrumented step (synchronises on the last event). */
 int dpc_debug_stage_ms(float* out6);
+/* diagnostics: tcgen05.mma issue/latency micro-benchmark; out = 3 int64 per CTA in device memory
+ * (cycles per repetition, cycles issuing, cycles waiting for completion). */
+int dpc_debug_mma_bench(long long* out, int nctas, int threads, int reps, int nmma, int spin, int M, int N, void* stream);
+/* diagnostics: dpc_debug_set(9, 1) makes CTA 0 of the persistent depth-pass kernel record clock64() at its
+ * pipeline hand-offs (16 events x 16 tiles), and every CTA of the persistent kernels its globaltimer at entry /
+ * after set-up / at exit (3 x 160); this copies both tables (256 + 480 int64) to host memory. */
+int dpc_debug_trace_read(long long* host_out);
 /* compiled for sm_100a?  1 = real CUDA build, 0 = the CPU emulation build used by tests/emu */
 int dpc_is_cuda_build(void);
 

@@ -13,6 +13,7 @@ from dpc_b200 import _capi  # noqa: E402
 
 L = _capi.lib()
 dev = torch.device("cuda:0")
+TC = int(os.environ.get("DPC_TC", "1"))
 P = _capi.ptr
 st = torch.cuda.current_stream().cuda_stream
 
@@ -78,57 +79,57 @@ def where(t, n=12):
 def main():
     torch.manual_seed(0)
     ok = True
-    B = 2
+    B = 6   # 192 depth-pass tiles: more than one per SM for the persistent kernels
     v = torch.rand(B, 64, 64, 64, device=dev)
     ident = torch.ones(1)
     # 1. identity taps: layouts only
-    o, _ = conv_z(v, ident, 1)
+    o, _ = conv_z(v, ident, TC)
     ok &= report("conv_z identity (tc)", o, v, 1e-6)
     if not torch.allclose(o, v, atol=1e-6):
-        d = torch.zeros(1, 64, 64, 64, device=dev); d[0, 5, 3, 7] = 1.0
-        od, _ = conv_z(d.repeat(2, 1, 1, 1), ident, 1)
+        d = torch.zeros(B, 64, 64, 64, device=dev); d[0, 5, 3, 7] = 1.0
+        od, _ = conv_z(d, ident, TC)
         print("  delta at (z5,y3,x7) lands at", where(od[0:1]))
-    o = conv_xy(v, ident, 1)
+    o = conv_xy(v, ident, TC)
     ok &= report("conv_xy identity (tc)", o, v, 1e-6)
     if not torch.allclose(o, v, atol=1e-6):
-        d = torch.zeros(2, 64, 64, 64, device=dev); d[0, 5, 3, 7] = 1.0
-        od = conv_xy(d, ident, 1)
+        d = torch.zeros(B, 64, 64, 64, device=dev); d[0, 5, 3, 7] = 1.0
+        od = conv_xy(d, ident, TC)
         print("  delta at (z5,y3,x7) lands at", where(od[0:1]))
     # 2. shift taps
     sh = torch.tensor([1.0, 0.0, 0.0])
-    o, _ = conv_z(v, sh, 1)
+    o, _ = conv_z(v, sh, TC)
     ok &= report("conv_z shift taps (tc)", o, ref_conv_axis(v, sh, 1, 1), 1e-6)
-    o = conv_xy(v, sh, 1)
+    o = conv_xy(v, sh, TC)
     ok &= report("conv_xy shift taps (tc)", o, ref_conv_axis(ref_conv_axis(v, sh, 3, 1), sh, 2, 1), 1e-6)
     # 3. Gaussians, odd / even K, against fp64 and against the CUDA-core kernels
     for K, sig in ((21, 3.0), (11, 1.5), (21, 0.2), (8, 2.0), (63, 9.0)):
         t = gauss(K, sig)
         pl = (K - 1) // 2
         want = ref_conv_axis(v, t, 1, pl)
-        o1, _ = conv_z(v, t, 1)
+        o1, _ = conv_z(v, t, TC)
         o0, _ = conv_z(v, t, 0)
         ok &= report("conv_z K=%d sig=%g (tc vs fp64)" % (K, sig), o1, want, 2e-6)
         report("conv_z K=%d sig=%g (cuda cores vs fp64)" % (K, sig), o0, want, 2e-6)
         want = ref_conv_axis(ref_conv_axis(v, t, 3, pl), t, 2, pl)
-        o1 = conv_xy(v, t, 1)
+        o1 = conv_xy(v, t, TC)
         o0 = conv_xy(v, t, 0)
         ok &= report("conv_xy K=%d sig=%g (tc vs fp64)" % (K, sig), o1, want, 2e-6)
         report("conv_xy K=%d sig=%g (cuda cores vs fp64)" % (K, sig), o0, want, 2e-6)
     # 4. scale + clip + DRC projection
     t = gauss(21, 3.0)
-    sc = torch.tensor([0.7, 1.9], device=dev)
+    sc = torch.tensor([0.7, 1.9, 1.0, 0.3, 2.5, 1.2], device=dev)
     for mode in (0, 1, 2):
-        o1, p1 = conv_z(v, t, 1, scale=sc, mode=mode)
+        o1, p1 = conv_z(v, t, TC, scale=sc, mode=mode)
         o0, p0 = conv_z(v, t, 0, scale=sc, mode=mode)
         ok &= report("conv_z+proj mode %d voxels (tc vs cuda cores)" % mode, o1, o0, 2e-6)
         ok &= report("conv_z+proj mode %d proj   (tc vs cuda cores)" % mode, p1, p0, 5e-6)
     # 5. large magnitudes (gradients): relative accuracy
     g = torch.randn(B, 64, 64, 64, device=dev) * 1e3
     want = ref_conv_axis(ref_conv_axis(g, t, 3, 10), t, 2, 10)
-    o1 = conv_xy(g, t, 1)
+    o1 = conv_xy(g, t, TC)
     ok &= report("conv_xy randn*1e3 (tc vs fp64, tol 2e-3)", o1, want, 2e-3)
-    L.dpc_debug_set(8, 1)
-    print("TC DIAG", "PASS" if ok else "FAIL", flush=True)
+    L.dpc_debug_set(8, 0)
+    print("TC DIAG level %d" % TC, "PASS" if ok else "FAIL", flush=True)
     return 0 if ok else 1
 
 
