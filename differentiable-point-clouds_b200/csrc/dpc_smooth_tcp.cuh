@@ -245,21 +245,31 @@ dpc_tcp_conv_z_fwd_kernel(const __grid_constant__ DpcConvZArgs a, const __grid_c
 
 // ------------------------------------------------------------------------------ depth pass, backward, lean
 // (DRC silhouette gradient only, occupancy scale present; see dpc_conv_z64_bwd_kernel for the quotient form)
+// Roles are mirrored here: the work is in front of the GEMM (two sweeps over the ray for the gradient of every
+// level), the back end only stores.  So EIGHT producer warps (thread = (ray, depth half); the two partial products of
+// a ray meet through smem) and FOUR consumer warps (thread = ray, all 64 levels).
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
 dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const __grid_constant__ CUtensorMap zmap, int ntiles) {
   constexpr int V = 64, Vz = 64;
+  __shared__ float pp[2][2][128];
   DPC_TCP_SETUP(a.taps, a.K, a.pl, a.rev);
-  if (warp < 4) {
-    // ---------------- producers: thread = ray: forward voxels -> DRC gradient of every level -> A planes
-    const int m = tid;
+  // barrier arrival counts differ from the forward's: 8 producer warps, 4 consumer warps
+  if (tid == 0) {
+    for (int q = 0; q < DPC_TCP_NS; ++q) dpc_mbar_init(&B.sfree[q], 8);
+    for (int q = 0; q < 2; ++q) { dpc_mbar_init(&B.opfull[q], 8); dpc_mbar_init(&B.accfree[q], 4); }
+  }
+  __syncthreads();
+  if (warp < 8) {
+    // ---------------- producers: forward voxels of a half ray -> DRC gradient -> A planes
+    const int m = tid & 127, h = tid >> 7;
     const DpcDrc D = dpc_drc_consts(a.mode, a.eps);
-    struct Extra { float gp, sc; uint2 mw; };
+    struct Extra { float gp, sc; uint32_t wbits; };
     auto fetch = [&](int tile) {
       Extra e;
       const int b = tile >> 5, y = (tile & 31) * 2 + (m >> 6), x = m & 63;
       const int yo = a.flip_y ? (V - 1 - y) : y;
       e.gp = a.g_proj[((size_t)b * V + yo) * V + x];
-      e.mw = *reinterpret_cast<const uint2*>(a.mask2 + (((size_t)b * V + y) * V + x) * 2);
+      e.wbits = a.mask2[(((size_t)b * V + y) * V + x) * 2 + h];
       e.sc = a.scale[b];
       return e;
     };
@@ -270,62 +280,65 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
       const Extra e = en;
       if (tile + step < ntiles) en = fetch(tile + step);      // the next tile's per-ray scalars, one iteration ahead
       dpc_mbar_wait(&B.sfull[slot], sph);
-      const float* stg = reinterpret_cast<const float*>(sm + DPC_TCP_S_OFF + (uint32_t)slot * DPC_TCP_SLOT) + m;
+      const float* stg = reinterpret_cast<const float*>(sm + DPC_TCP_S_OFF + (uint32_t)slot * DPC_TCP_SLOT) + (32 * h) * 128 + m;
+      float v[32];
+#pragma unroll
+      for (int z = 0; z < 32; ++z) v[z] = stg[z * 128];
+      dpc_tcp_warp_arrive(&B.sfree[slot]);
       const float gp = e.gp, sc = e.sc;
+      uint32_t wbits = e.wbits;
       const float inv_s = (sc != 0.0f) ? 1.0f / sc : 0.0f;
-      float P0 = 1.0f, P1 = 1.0f, P2 = 1.0f, P3 = 1.0f;      // first sweep over the staged ray: prod (1 - u)
-#pragma unroll 4
-      for (int z = 0; z < Vz; z += 4) {
-        P0 *= 1.0f - fminf(fmaxf(stg[(z + 0) * 128], D.lo), D.hi);
-        P1 *= 1.0f - fminf(fmaxf(stg[(z + 1) * 128], D.lo), D.hi);
-        P2 *= 1.0f - fminf(fmaxf(stg[(z + 2) * 128], D.lo), D.hi);
-        P3 *= 1.0f - fminf(fmaxf(stg[(z + 3) * 128], D.lo), D.hi);
+      float P0 = 1.0f, P1 = 1.0f, P2 = 1.0f, P3 = 1.0f;
+#pragma unroll
+      for (int z = 0; z < 32; z += 4) {
+        P0 *= 1.0f - fminf(fmaxf(v[z + 0], D.lo), D.hi);
+        P1 *= 1.0f - fminf(fmaxf(v[z + 1], D.lo), D.hi);
+        P2 *= 1.0f - fminf(fmaxf(v[z + 2], D.lo), D.hi);
+        P3 *= 1.0f - fminf(fmaxf(v[z + 3], D.lo), D.hi);
       }
-      const float gT = gp * ((P0 * P1) * (P2 * P3));
-      if (k >= 1) dpc_mbar_wait(&B.done[s], (k - 1) & 1);
+      pp[i & 1][h][m] = (P0 * P1) * (P2 * P3);
+      dpc_named_bar(2, 256);          // pp[i & 1] is rewritten two tiles later, behind the next tile's barrier
+      const float gT = gp * (pp[i & 1][0][m] * pp[i & 1][1][m]);
       float dsv = 0.0f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {                            // second sweep: 32 levels at a time -> gradient -> split -> TMEM
-        float v[32];
-        uint32_t wbits = h ? e.mw.y : e.mw.x;
-#pragma unroll
-        for (int z = 0; z < 32; ++z) {
-          const float vv = stg[(32 * h + z) * 128];
-          const float u = fminf(fmaxf(vv, D.lo), D.hi);
-          float dv = __fdividef(gT, 1.0f - u);
-          if (z == 0 && h == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
-          if ((u != vv) || !(wbits & 1u)) dv = 0.0f;
-          wbits >>= 1;
-          dsv = fmaf(dv, vv, dsv);
-          v[z] = dv * sc;
-        }
-        dpc_tcp_put_a(tmem, s, h, v);
+      for (int z = 0; z < 32; ++z) {
+        const float vv = v[z];
+        const float u = fminf(fmaxf(vv, D.lo), D.hi);
+        float dv = __fdividef(gT, 1.0f - u);
+        if (z == 0 && h == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
+        if ((u != vv) || !(wbits & 1u)) dv = 0.0f;
+        wbits >>= 1;
+        dsv = fmaf(dv, vv, dsv);
+        v[z] = dv * sc;
       }
-      dpc_tcp_warp_arrive(&B.sfree[slot]);
       if (a.d_scale) {
         const float w = dpc_warp_sum(dsv * inv_s);
         if (lane == 0) atomicAdd(a.d_scale + (tile >> 5), w);
       }
+      if (k >= 1) dpc_mbar_wait(&B.done[s], (k - 1) & 1);
+      dpc_tcp_put_a(tmem, s, h, v);
       dpc_tc_wait_st();
       dpc_tcp_warp_arrive(&B.opfull[s]);
       if (++slot == DPC_TCP_NS) { slot = 0; sph ^= 1; }
     }
   } else if (warp < DPC_TCP_ISSUER) {
-    // ---------------- consumers: dL/d(xy-smoothed) out
-    const int c = tid - DPC_TCP_NPROD, m = c & 127, ch = c >> 7;
+    // ---------------- consumers: thread = ray, dL/d(xy-smoothed) of all 64 levels out
+    const int m = tid - 256;
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += step, ++i) {
       const int s = i & 1, k = i >> 1;
       const int b = tile >> 5, y = (tile & 31) * 2 + (m >> 6), x = m & 63;
       dpc_mbar_wait(&B.done[s], k & 1);
       dpc_tc_fence_after();
-      float r[32];
-      dpc_tc_ld32(tmem + DPC_TCP_D1(s) + (uint32_t)(ch * 32) + ((uint32_t)((warp & 3) * 32) << 16), r);
+      float r[64];
+      const uint32_t taddr = tmem + DPC_TCP_D1(s) + ((uint32_t)((warp & 3) * 32) << 16);
+      dpc_tc_ld32(taddr, r);
+      dpc_tc_ld32(taddr + 32, r + 32);
       dpc_tc_wait_ld();
       dpc_tcp_warp_arrive(&B.accfree[s]);
-      float* dout = a.d_in + (((size_t)b * Vz + 32 * ch) * V + y) * V + x;
+      float* dout = a.d_in + ((size_t)b * Vz * V + y) * V + x;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) dout[(size_t)j * V * V] = r[j];
+      for (int j = 0; j < 64; ++j) dout[(size_t)j * V * V] = r[j];
     }
   } else {
     if (dpc_elect_one()) dpc_tcp_issuer_z(sm, sbase, tmem, B, &zmap, ntiles, step, false);
