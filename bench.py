@@ -34,6 +34,17 @@ G_BYTES = V * V * V * 4
 # algorithmic bytes per projection, SURVEY.md 8(d): full path 6g + 4n + 64N + 2s
 FULL_PATH_BYTES = 6 * G_BYTES + 4 * 12 * N + 64 * N + 2 * 4 * V * V
 # per-launch algorithmic bytes of each stage, per projection (DESIGN.md "kernels and rooflines")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at B=32, from the committed `ncu --set full` capture of this
+# very command (profiles/r01_i_tcgen05_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
+# previous kernel left in L2 are re-read from HBM, and the 32 MiB of output stays in L2 until a later kernel evicts it)
+NCU_TRAFFIC_B32 = {
+    "splat_fwd": 22.242048e6 + 0.010240e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
+    "conv_xy_fwd": 33.591552e6 + 0.604160e6,
+    "conv_z_fwd": 33.590272e6 + 0.952320e6,
+    "conv_z_bwd": 35.162624e6 + 0.555008e6,
+    "conv_xy_bwd": 34.638336e6 + 0.0,
+    "splat_bwd": 26.716160e6 + 0.0,
+}
 STAGE_BYTES = {
     "splat_fwd": G_BYTES + 2 * 12 * N + 32 * N,          # zero grid + read pc + write tr_pc + 8 corner RMW
     "conv_xy_fwd": 2 * G_BYTES + G_BYTES // 32,          # read raw, write xy-smoothed, clip-mask bits
@@ -538,7 +549,10 @@ def run_ours(args, rank, local_rank, world):
                     "serial_value": e2e_serial, "serial_ms_per_step": serial_ms},
             "gpu_launches": Pipeline.LAUNCHES_PER_STEP * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": (NCU_TRAFFIC_B32.get(dom) if (B == 32 and N == 8000 and V == 64) else None),
+                         "traffic_source": "ncu --set full, dram read+write per launch, profiles/r01_i_tcgen05_ncu_summary.md",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": STAGE_BYTES[dom] * B},
             "roofline_step": {"algorithmic_bytes_per_projection": FULL_PATH_BYTES, "achieved": step_gbs,
                               "frac": (step_gbs / peak) if step_gbs else None, "unit": "GB/s"},
