@@ -433,10 +433,16 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   const float* tx = p->K > 0 ? taps_xy : nullptr;
   const float* tz = p->Kz > 0 ? taps_z : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d_pose) DPC_CUDA(cudaMemsetAsync(d_pose, 0, (size_t)p->B * (p->pose_kind == DPC_POSE_MATRIX ? 16 : 4) * 4, st));
-  if (d_trans) DPC_CUDA(cudaMemsetAsync(d_trans, 0, (size_t)p->B * 3 * 4, st));
-  if (d_focal) DPC_CUDA(cudaMemsetAsync(d_focal, 0, (size_t)p->B * 4, st));
-  if (d_scale) DPC_CUDA(cudaMemsetAsync(d_scale, 0, (size_t)p->B * 4, st));
+  (void)st;
+  if (d_pose || d_trans || d_focal || d_scale) {     // the accumulation targets, zeroed in one launch
+    DpcZero4Args z;
+    z.p[0] = d_pose; z.n[0] = p->B * (p->pose_kind == DPC_POSE_MATRIX ? 16 : 4);
+    z.p[1] = d_trans; z.n[1] = p->B * 3;
+    z.p[2] = d_focal; z.n[2] = p->B;
+    z.p[3] = d_scale; z.n[3] = p->B;
+    DPC_LAUNCH(dpc_zero4_kernel, dim3(1), dim3(256), 0, stream, z);
+    DPC_TRY(dpc_check_launch());
+  }
   const bool any_grid_grad = g_proj || g_voxels || g_probs || g_depth;
   const float* d_raw = nullptr;
   stage_mark(4, stream);
