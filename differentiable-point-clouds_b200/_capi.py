@@ -49,6 +49,7 @@ _SIGNATURES = {
     "dpc_debug_set": (c_i, [c_i, c_i]),
     "dpc_debug_stage_ms": (c_i, [c_p]),
     "dpc_debug_trace_read": (c_i, [c_p]),
+    "dpc_debug_ktrace_read": (c_i, [c_p]),
     "dpc_debug_mma_bench": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
     "dpc_splat_fwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_p, c_i, c_i, c_i, c_i,
                             c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -105,6 +106,9 @@ def lib():
         _LIB = load_library(LIB_PATH)
         if os.environ.get("DPC_TC"):      # experiment override of the smoothing-kernel family (dpc_debug_set key 8)
             _LIB.dpc_debug_set(8, int(os.environ["DPC_TC"]))
+        for kv in filter(None, os.environ.get("DPC_KNOBS", "").split(",")):     # experiments: "10=0,11=1"
+            k, v = kv.split("=")
+            _LIB.dpc_debug_set(int(k), int(v))
     return _LIB
 
 

@@ -18,7 +18,9 @@ static int dpc_check_launch() {
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
 // Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
+static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 2, 0, 1, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
+// [10] 1 = the raw grid is zeroed by dpc_zero_kernel and the splats run their transform ahead of the grid dependency
+//      (0 = cudaMemsetAsync + wait-first splats); [11] 1 = red.v4 in the splat; [12] per-kernel timeline (dpc_kt)
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
 // ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are
@@ -35,6 +37,9 @@ static void stage_mark(int i, void* stream) {
 #else
 static void stage_mark(int, void*) {}
 #endif
+
+// set by the fused forward right before it calls dpc_splat_fwd: the stream predecessor is the grid-zeroing kernel
+static thread_local int g_splat_early_next = 0;
 
 static bool shape_ok(int B, int Vz, int V) {
   return B >= 1 && B <= 65535 && V >= 1 && V <= DPC_MAX_V && Vz >= 1 && Vz <= DPC_MAX_V;
@@ -68,6 +73,12 @@ int dpc_debug_set(int key, int value) {
 #ifndef DPC_EMU
   if (key == 8) dpc_tc_enable = value;
   if (key == 9) { int v = value; cudaMemcpyToSymbol(dpc_tcp_trace_on, &v, sizeof(int)); }
+  if (key == 12) {     // (re)arm the per-kernel timeline: minima to ~0, maxima to 0
+    unsigned long long init[64];
+    for (int i = 0; i < 64; ++i) init[i] = ((i & 3) < 2) ? ~0ull : 0ull;
+    cudaMemcpyToSymbol(dpc_kt, init, sizeof(init));
+    int v = value; cudaMemcpyToSymbol(dpc_kt_on, &v, sizeof(int));
+  }
 #endif
   return DPC_OK;
 }
@@ -79,6 +90,16 @@ int dpc_debug_trace_read(long long* host_out) {
   if (cudaMemcpyFromSymbol(host_out, dpc_tcp_trace, sizeof(long long) * 256) != cudaSuccess) return DPC_ERR_CUDA;
   return cudaMemcpyFromSymbol(host_out + 256, dpc_tcp_cta_ns, sizeof(long long) * 480) == cudaSuccess ? DPC_OK : DPC_ERR_CUDA;
 #else
+  return DPC_ERR_ARG;
+#endif
+}
+/* diagnostics: the per-kernel timeline (16 kernels x {first entry, first/last CTA past its dependency, last exit}, ns) */
+int dpc_debug_ktrace_read(unsigned long long* host_out) {
+#ifndef DPC_EMU
+  if (!host_out) return DPC_ERR_NULL;
+  return cudaMemcpyFromSymbol(host_out, dpc_kt, sizeof(unsigned long long) * 64) == cudaSuccess ? DPC_OK : DPC_ERR_CUDA;
+#else
+  (void)host_out;
   return DPC_ERR_ARG;
 #endif
 }
@@ -128,6 +149,8 @@ int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float
   a.pose_kind = pose_kind; a.focal_const = focal_const; a.cam_dist = cam_dist;
   a.B = B; a.N = N; a.Vz = Vz; a.V = V;
   a.tr_pc = tr_pc; a.vox = vox; a.vox_rgb = vox_rgb; a.idx_out = idx_out; a.valid_out = valid_out;
+  a.early = g_splat_early_next; g_splat_early_next = 0;
+  a.red4 = g_tune[11] ? 1 : 0;
   const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH(dpc_splat_fwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -154,6 +177,7 @@ int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float
   a.B = B; a.N = N; a.Vz = Vz; a.V = V;
   a.d_vox = d_vox; a.d_vox_rgb = d_vox_rgb; a.d_tr_pc_in = d_tr_pc_in;
   a.d_pc = d_pc; a.d_pose = d_pose; a.d_trans = d_trans; a.d_focal = d_focal; a.d_rgb = d_rgb;
+  a.early = g_tune[10] ? 1 : 0;
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH(dpc_splat_bwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -393,8 +417,23 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   const float* hz = (tz && p->taps_z_host) ? p->taps_z_host : nullptr;
   // cudaMemsetAsync beat a hand-written float4 zero kernel here (23.6 vs 28.4 us for memset + splat,
   // gpurun round 7), so the driver's memset stays.
-  if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO))
-    DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
+  // Round 8: a zeroing KERNEL again, now as the first half of a PDL pair -- it waits for everything older, lets the
+  // splat start, and the splat stages + transforms + writes tr_pc while the grid is being zeroed (knob 10).
+  if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO)) {
+    if (g_tune[10]) {
+      const size_t n4 = (size_t)g / 4;
+#ifdef DPC_EMU
+      const int zgrid = 2;
+#else
+      const int zgrid = 148 * 4;
+#endif
+      DPC_LAUNCH(dpc_zero_kernel, dim3(zgrid), dim3(256), 0, stream, (float4*)w.raw, n4, w.raw + n4 * 4, (int)(g - (int64_t)n4 * 4));
+      DPC_TRY(dpc_check_launch());
+      g_splat_early_next = 1;
+    } else {
+      DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
+    }
+  }
   DPC_TRY(dpc_splat_fwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
                         p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, stream));
   stage_mark(1, stream);

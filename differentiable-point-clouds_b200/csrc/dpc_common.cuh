@@ -59,6 +59,41 @@ DPC_DEV void dpc_grid_dep_sync() {
 #endif
 }
 
+// The two halves separately.  A kernel whose first phase reads nothing its stream predecessor wrote may
+// run that phase before the wait (the splat stages and transforms its points while the raw grid is being
+// zeroed).  The rule that keeps this safe transitively: a kernel whose OUTPUT a dependent may read early
+// (point data: the dropout gather) or that sits directly in front of such a dependent (the grid-zeroing
+// kernel) triggers only AFTER its own wait, so everything older than it has completed by then.
+DPC_DEV void dpc_grid_dep_trigger() {
+#ifndef DPC_EMU
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+DPC_DEV void dpc_grid_dep_wait() {
+#ifndef DPC_EMU
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+// ---- diagnostics: per-kernel timeline of one step (dpc_debug_set(12, 1); scripts/step_timeline.py).
+// Thread 0 of every CTA folds %globaltimer into [kernel][0] = first entry, [1] = first CTA past its grid
+// dependency, [2] = last CTA past it, [3] = last exit.
+#ifndef DPC_EMU
+__device__ unsigned long long dpc_kt[16 * 4];
+__device__ int dpc_kt_on = 0;
+DPC_DEV void dpc_kt_mark(int id, int slot) {
+  if (threadIdx.x == 0 && dpc_kt_on) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (slot < 2) atomicMin(&dpc_kt[id * 4 + slot], t); else atomicMax(&dpc_kt[id * 4 + slot], t);
+    if (slot == 1) atomicMax(&dpc_kt[id * 4 + 2], t);
+  }
+}
+#else
+DPC_DEV void dpc_kt_mark(int, int) {}
+#endif
+enum { DPC_KT_ZERO = 0, DPC_KT_SPLAT_F, DPC_KT_XY_F, DPC_KT_Z_F, DPC_KT_ZERO4, DPC_KT_Z_B, DPC_KT_XY_B, DPC_KT_SPLAT_B };
+
 // ------------------------------------------------------------------ small PTX wrappers
 // red.global.add.f32: fire-and-forget fp32 add at L2 (SASS REDG.E.ADD.F32).
 DPC_DEV void dpc_red_add(float* addr, float v) {
@@ -77,6 +112,15 @@ DPC_DEV void dpc_red_add2(float* addr, float a, float b) {
 #else
   atomicAdd(addr, a);
   atomicAdd(addr + 1, b);
+#endif
+}
+
+// red.global.add.v4.f32 (sm_90+): four adjacent floats in one L2 reduction.  addr must be 16-byte aligned.
+DPC_DEV void dpc_red_add4(float* addr, float a, float b, float c, float d) {
+#ifndef DPC_EMU
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+#else
+  atomicAdd(addr, a); atomicAdd(addr + 1, b); atomicAdd(addr + 2, c); atomicAdd(addr + 3, d);
 #endif
 }
 

@@ -87,6 +87,7 @@ DPC_DEV void dpc_tcp_put_a(uint32_t tmem, int s, int h, const float* v) {
 #define DPC_TCP_SETUP(TAPS, KK, PL, REV)                                            \
   extern __shared__ __align__(1024) unsigned char dpc_tcp_dsm[];                    \
   __shared__ __align__(8) DpcTcpBars B;                                             \
+  dpc_kt_mark(kt_id, 0);                                                            \
   const bool cta_trace = (dpc_tcp_trace_on != 0) && threadIdx.x == 0 && blockIdx.x < 160; \
   if (cta_trace) dpc_tcp_cta_ns[3 * blockIdx.x] = dpc_globaltimer();                \
   __shared__ uint32_t tmem_slot;                                                    \
@@ -115,12 +116,14 @@ DPC_DEV void dpc_tcp_put_a(uint32_t tmem, int s, int h, const float* v) {
   dpc_tc_fence_after();                                                             \
   const uint32_t tmem = tmem_slot;                                                  \
   dpc_grid_dep_sync();                                                              \
+  dpc_kt_mark(kt_id, 1);                                                            \
   if (cta_trace) dpc_tcp_cta_ns[3 * blockIdx.x + 1] = dpc_globaltimer()
 
 #define DPC_TCP_TEARDOWN()                                                          \
   dpc_tc_fence_before();                                                            \
   __syncthreads();                                                                  \
   if (cta_trace) dpc_tcp_cta_ns[3 * blockIdx.x + 2] = dpc_globaltimer();            \
+  dpc_kt_mark(kt_id, 3);                                                            \
   if (warp == 0) { __syncwarp(); dpc_tc_dealloc(tmem, 512); }
 
 // staging slot <- the 64 depth levels x 128 rays of depth-pass tile (b, image rows 2t, 2t+1): one TMA box; one thread.
@@ -157,6 +160,7 @@ dpc_tcp_conv_z_fwd_kernel(const __grid_constant__ DpcConvZArgs a, const __grid_c
   constexpr int V = 64, Vz = 64;
   constexpr bool CLAMPU = (MODE == DPC_PROJ_DRC);
   __shared__ __align__(8) float2 comb[128];
+  constexpr int kt_id = DPC_KT_Z_F;
   DPC_TCP_SETUP(a.taps, a.K, a.pl, a.rev);
   if (warp < 4) {
     // ---------------- producers: thread = ray
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
 dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const __grid_constant__ CUtensorMap zmap, int ntiles) {
   constexpr int V = 64, Vz = 64;
   __shared__ float pp[2][2][128];
+  constexpr int kt_id = DPC_KT_Z_B;
   DPC_TCP_SETUP(a.taps, a.K, a.pl, a.rev);
   // barrier arrival counts differ from the forward's: 8 producer warps, 4 consumer warps
   if (tid == 0) {
@@ -359,6 +364,7 @@ template <bool CLIP, bool MOUT, bool MIN>
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
 dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_constant__ CUtensorMap xymap, int K, int pl, int ntiles) {
   constexpr int V = 64;
+  constexpr int kt_id = MIN ? DPC_KT_XY_B : DPC_KT_XY_F;
   DPC_TCP_SETUP(a.taps_x, K, pl, a.rev);
   if (warp < 4) {
     // ---------------- producers: thread = row (slice, y)

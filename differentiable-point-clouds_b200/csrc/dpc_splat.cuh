@@ -20,6 +20,8 @@ struct DpcSplatArgs {
   int pose_kind; float focal_const; float cam_dist;
   int B, N, Vz, V;
   float* tr_pc; float* vox; float* vox_rgb; int32_t* idx_out; uint8_t* valid_out;
+  int early;   // the stream predecessor only zeroes `vox` (fused path): stage + transform + tr_pc before the grid dependency
+  int red4;    // x pairs go out as one 16-byte red.v4 when they do not straddle a 4-voxel group (experiment knob 11)
 };
 
 // Stage `n` points (3n floats) into smem: one TMA bulk copy when the 16-byte rules allow it
@@ -71,7 +73,9 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
   const int lane = tid & 31;
   const int V = a.V, Vz = a.Vz;
 
-  dpc_grid_dep_sync();
+  dpc_kt_mark(DPC_KT_SPLAT_F, 0);
+  dpc_grid_dep_trigger();
+  if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_F, 1); }
   dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
                    a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
@@ -97,6 +101,8 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
     __syncthreads();
     dpc_unstage_points(a.tr_pc + ((size_t)b * a.N + p_first) * 3, tile, n);
   }
+  // the grid is zero (and everything older than the zeroing kernel complete) from here on
+  if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_F, 1); }
 
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
@@ -176,6 +182,8 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
     if (leader) {
       float* g = a.vox + (size_t)b * Vz * V * V + base;
       const bool pair_ok = ((V & 1) == 0) && ((c.ix & 1) == 0) && ((((uintptr_t)a.vox) & 7u) == 0);
+      const int o4 = c.ix & 3;
+      const bool quad_ok = a.red4 && ((V & 3) == 0) && (o4 != 3) && ((((uintptr_t)a.vox) & 15u) == 0);
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (c.iz + k >= Vz) continue;  // only for a coordinate of exactly +0.5 (weight is 0): TF-GPU drops it
@@ -183,7 +191,11 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
         for (int jj = 0; jj < 2; ++jj) {
           if (c.iy + jj >= V) continue;
           float* row = g + (k * V + jj) * V;
-          if (pair_ok) {
+          if (quad_ok) {
+            const float w0 = w[k * 4 + jj * 2 + 0], w1 = w[k * 4 + jj * 2 + 1];
+            dpc_red_add4(row - o4, o4 == 0 ? w0 : 0.0f, o4 == 0 ? w1 : (o4 == 1 ? w0 : 0.0f),
+                         o4 == 1 ? w1 : (o4 == 2 ? w0 : 0.0f), o4 == 2 ? w1 : 0.0f);
+          } else if (pair_ok) {
             dpc_red_add2(row, w[k * 4 + jj * 2 + 0], w[k * 4 + jj * 2 + 1]);
           } else {
             dpc_red_add(row, w[k * 4 + jj * 2 + 0]);
@@ -193,6 +205,7 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
       }
     }
   }
+  dpc_kt_mark(DPC_KT_SPLAT_F, 3);
 }
 
 // ------------------------------------------------------------------------------ backward
@@ -202,6 +215,7 @@ struct DpcSplatBwdArgs {
   int B, N, Vz, V;
   const float* d_vox; const float* d_vox_rgb; const float* d_tr_pc_in;
   float* d_pc; float* d_pose; float* d_trans; float* d_focal; float* d_rgb;
+  int early;   // transform before the grid dependency (experiment knob 10)
 };
 
 template <int DPC_SPLAT_PPT>
@@ -223,7 +237,11 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   const int lane = tid & 31, warp = tid >> 5;
   const int V = a.V, Vz = a.Vz;
 
-  dpc_grid_dep_sync();
+  // The points and the camera are inputs of the forward (nothing in front of this kernel writes them), so they are
+  // staged and transformed while the x/y pass of the backward is still draining; the gathers wait for it.
+  dpc_kt_mark(DPC_KT_SPLAT_B, 0);
+  dpc_grid_dep_trigger();
+  if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
   dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
                    a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
@@ -251,6 +269,10 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     }
     cell[j] = dpc_cell(z, y, x, Vz, V);
     cell[j].valid = cell[j].valid && (i < n);
+  }
+  if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
+#pragma unroll
+  for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
     const int base = (cell[j].iz * V + cell[j].iy) * V + cell[j].ix;
 #pragma unroll
     for (int k = 0; k < 2; ++k)
@@ -319,6 +341,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     __syncthreads();
     dpc_unstage_points(a.d_pc + ((size_t)b * a.N + p_first) * 3, tile, n);
   }
+  dpc_kt_mark(DPC_KT_SPLAT_B, 3);
   if (a.pose_kind == DPC_POSE_NONE) return;
   const bool want_pose = a.d_pose != nullptr, want_t = a.d_trans != nullptr, want_f = a.d_focal != nullptr;
   if (!(want_pose || want_t || want_f)) return;
@@ -365,10 +388,19 @@ __global__ void __launch_bounds__(256)
 static void
 #endif
 dpc_zero_kernel(float4* dst, size_t n4, float* tail, int ntail) {
-  dpc_grid_dep_sync();
+  // wait FIRST, trigger second: the splat that follows reads its inputs before its own wait, so by the time it may
+  // start everything older than this kernel has to be complete (see dpc_grid_dep_trigger)
+  dpc_kt_mark(DPC_KT_ZERO, 0);
+  dpc_grid_dep_wait();
+  dpc_grid_dep_trigger();
+  dpc_kt_mark(DPC_KT_ZERO, 1);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; i + 3 * stride < n4; i += 4 * stride) { dst[i] = zz; dst[i + stride] = zz; dst[i + 2 * stride] = zz; dst[i + 3 * stride] = zz; }
+  for (; i < n4; i += stride) dst[i] = zz;
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.0f;
+  dpc_kt_mark(DPC_KT_ZERO, 3);
 }
 
 // Zeroes up to four small accumulation targets (pose / translation / focal / scale gradients) in ONE launch: every
@@ -380,7 +412,9 @@ __global__ void __launch_bounds__(256)
 static void
 #endif
 dpc_zero4_kernel(DpcZero4Args a) {
+  dpc_kt_mark(DPC_KT_ZERO4, 0);
   dpc_grid_dep_sync();
+  dpc_kt_mark(DPC_KT_ZERO4, 1);
   for (int k = 0; k < 4; ++k)
     if (a.p[k]) for (int i = threadIdx.x; i < a.n[k]; i += blockDim.x) a.p[k][i] = 0.0f;
 }
@@ -394,7 +428,7 @@ static void
 dpc_gather_kernel(const float* in, const int64_t* sel, int N, int n_keep, int C, float* out) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  dpc_grid_dep_sync();
+  dpc_grid_dep_wait();   // no early trigger: the output is point data, which a splat reads before its own wait
   if (i >= n_keep * C) return;
   const int r = i / C, ch = i - r * C;
   const int64_t s = sel[(size_t)b * n_keep + r];
@@ -409,7 +443,7 @@ static void
 dpc_gather_bwd_kernel(const float* g_out, const int64_t* sel, int N, int n_keep, int C, float* g_in) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  dpc_grid_dep_sync();
+  dpc_grid_dep_wait();
   if (i >= n_keep * C) return;
   const int r = i / C, ch = i - r * C;
   const int64_t s = sel[(size_t)b * n_keep + r];

@@ -56,8 +56,16 @@ int dpc_last_cuda_error(void);
  * not thread-safe).  key 0 / 1: points per thread of the forward / backward splat kernel (1|2|4);
  * key 3: stage events (see dpc_debug_stage_ms); key 5: 1 = ignore host taps (run the vector-register
  * smoothing kernels); key 6: 1 = cp.async tile load in the depth kernels; key 7: conv_xy diagnostics
- * (1 memory path only, 2 arithmetic only, 3 empty CTAs, 4/5 skip the x / y correlation). */
+ * (1 memory path only, 2 arithmetic only, 3 empty CTAs, 4/5 skip the x / y correlation); key 8: smoothing-kernel
+ * family at 64^3 (0 FFMA2, 1 single-tile tcgen05, 2 tcgen05 pipelines = default); key 10: 1 (default) = the fused
+ * forward zeroes the raw grid with a kernel the splat overlaps (transform ahead of the grid dependency), 0 =
+ * cudaMemsetAsync + wait-first splats; key 11: 1 = 16-byte red.v4 in the splat; key 12: 1 = arm the per-kernel
+ * timeline (dpc_debug_ktrace_read). */
 int dpc_debug_set(int key, int value);
+/* diagnostics: after dpc_debug_set(12, 1), every kernel of the fused path folds %globaltimer (ns) into
+ * out[4*k + {0: first CTA entry, 1: first CTA past its grid dependency, 2: last CTA past it, 3: last CTA exit}],
+ * k = 0 zero, 1 splat fwd, 2 x/y fwd, 3 depth fwd, 4 zero4, 5 depth bwd, 6 x/y bwd, 7 splat bwd; 64 uint64 to host. */
+int dpc_debug_ktrace_read(unsigned long long* host_out);
 /* key 3 = 1: record CUDA events around every stage of the fused forward/backward; this returns the
  * six stage durations (ms) of the last instrumented step (synchronises on the last event). */
 int dpc_debug_stage_ms(float* out6);

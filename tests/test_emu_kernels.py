@@ -40,6 +40,22 @@ def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
         emu.dpc_debug_set(1, 4)
 
 
+@pytest.mark.parametrize("knob,value", [(11, 1), (10, 0)])
+def test_splat_reduction_and_zeroing_variants(emu, knob, value):  # noqa: F811
+    """Knob 11: x pairs as one 16-byte reduction; knob 10 = 0: cudaMemsetAsync + wait-first splats."""
+    default = 1 if knob == 10 else 0
+    emu.dpc_debug_set(knob, value)
+    try:
+        for name in ("cfg1_drc_k11", "clustered_init", "v64_small", "edge_points"):
+            if name not in SMALL:
+                continue
+            fx = cases.load_golden(name)
+            outs, grads = cases.run_impl(Product, fx)
+            cases.assert_parity(fx, outs, grads)
+    finally:
+        emu.dpc_debug_set(knob, default)
+
+
 @pytest.mark.parametrize("name", ["v64_small", "v64_k11_max", "cfg1_drc_k21_sigma3", "cfg1_drc_k11", "vox_z"])
 def test_device_taps_kernels(emu, name):  # noqa: F811
     """On the CPU the taps are host tensors, so the tests above run the launch-parameter (uniform-register)

@@ -139,6 +139,23 @@ def test_full_benchmark_shape_clustered_and_translation():
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0, trans=tr, host_sigma=True))
 
 
+@pytest.mark.parametrize("knob,value", [(10, 0), (11, 1)])
+def test_splat_variants_full_shape(knob, value):
+    """Knob 10 = 0: cudaMemsetAsync + wait-first splats (default: zeroing kernel overlapped with the transform);
+    knob 11 = 1: 16-byte red.v4 rows.  Same results either way, spread and clustered clouds."""
+    from dpc_b200 import _capi
+    L = _capi.lib()
+    default = 1 if knob == 10 else 0
+    cfg = default_config(vox_size=64, pc_gauss_kernel_size=21)
+    L.dpc_debug_set(knob, value)
+    try:
+        for spread, seed in ((0.5, 1234), (0.025, 1235)):
+            pc, q, sc, gt = _bench_inputs(2, 8000, 64, spread, seed=seed)
+            _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
+    finally:
+        L.dpc_debug_set(knob, default)
+
+
 def test_max_projection_full_shape():
     cfg = default_config(vox_size=64, pc_gauss_kernel_size=21, ptn_max_projection=True)
     pc, q, sc, gt = _bench_inputs(2, 8000, 64, 0.5)
