@@ -6,6 +6,7 @@
 #include "dpc_smooth.cuh"
 #include "dpc_smooth_fast.cuh"
 #include "dpc_smooth_tc.cuh"
+#include "dpc_chamfer.cuh"
 
 static thread_local int g_last_cuda_error = 0;
 
@@ -522,6 +523,46 @@ int dpc_gather_points_bwd(const float* g_out, const int64_t* sel, int B, int N, 
   dim3 grid((n_keep * C + 255) / 256, B);
   DPC_LAUNCH(dpc_gather_bwd_kernel, grid, dim3(256), 0, stream, g_out, sel, N, n_keep, C, g_in);
   return dpc_check_launch();
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ f-4: nearest neighbours
+template <typename T>
+static int nn_launch(const T* vs, int ns, const T* vt, int nt, T* proj, T* min_dist, int32_t* idx,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!vs || !vt || !workspace) return DPC_ERR_NULL;
+  if (ns < 1 || nt < 1) return DPC_ERR_SHAPE;
+  const int splits = dpc_nn_splits(ns, nt);
+  const int64_t need = (int64_t)splits * ns * (int64_t)(sizeof(T) + sizeof(int32_t));
+  if (workspace_bytes < need || (((uintptr_t)workspace) & 7) != 0) return DPC_ERR_WORKSPACE;
+  T* part_s = (T*)workspace;
+  int32_t* part_i = (int32_t*)(part_s + (size_t)splits * ns);
+  int chunk = (nt + splits - 1) / splits;
+  chunk = ((chunk + DPC_NN_TILE - 1) / DPC_NN_TILE) * DPC_NN_TILE;
+  const int bx = (ns + DPC_NN_THREADS - 1) / DPC_NN_THREADS;
+  DPC_LAUNCH(dpc_nn_partial_kernel<T>, dim3(bx, splits), dim3(DPC_NN_THREADS), 0, stream, vs, ns, vt, nt, chunk, part_s, part_i);
+  DPC_TRY(dpc_check_launch());
+  DPC_LAUNCH(dpc_nn_final_kernel<T>, dim3(bx), dim3(DPC_NN_THREADS), 0, stream, vt, ns, splits, (const T*)part_s,
+             (const int32_t*)part_i, proj, min_dist, idx);
+  return dpc_check_launch();
+}
+
+extern "C" {
+
+int64_t dpc_point_cloud_distance_workspace_bytes(int ns, int nt, int elem_bytes) {
+  if (ns < 1 || nt < 1 || (elem_bytes != 4 && elem_bytes != 8)) return -1;
+  return (int64_t)dpc_nn_splits(ns, nt) * ns * (int64_t)(elem_bytes + 4);
+}
+
+int dpc_point_cloud_distance_f32(const float* vs, int ns, const float* vt, int nt, float* proj, float* min_dist,
+                                 int32_t* idx, void* workspace, int64_t workspace_bytes, void* stream) {
+  return nn_launch<float>(vs, ns, vt, nt, proj, min_dist, idx, workspace, workspace_bytes, stream);
+}
+
+int dpc_point_cloud_distance_f64(const double* vs, int ns, const double* vt, int nt, double* proj, double* min_dist,
+                                 int32_t* idx, void* workspace, int64_t workspace_bytes, void* stream) {
+  return nn_launch<double>(vs, ns, vt, nt, proj, min_dist, idx, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -23,6 +23,7 @@ import ctypes
 import torch
 
 from .. import _capi
+from .point_cloud_distance import point_cloud_distance  # noqa: F401  (re-exported like point_cloud.py:7 does)
 from .._capi import (POSE_MATRIX, POSE_NONE, POSE_QUAT, PROJ_DRC, PROJ_DRC_PROD, PROJ_MAX, PROJ_NONE,
                      ProjectParams, check, f32c, ptr, stream_of)
 

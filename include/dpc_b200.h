@@ -195,6 +195,19 @@ int dpc_gather_points(const float* in, const int64_t* sel, int B, int N, int n_k
 int dpc_gather_points_bwd(const float* g_out, const int64_t* sel, int B, int N, int n_keep, int C,
                           float* g_in /* zeroed by callee */, void* stream);
 
+/* ---- f-4: nearest-neighbour projection of the chamfer evaluation.  Replaces point_cloud_distance
+ * (util/point_cloud_distance.py:26-39; driver run/eval_chamfer.py:18-34): for every source point vs[i] the closest
+ * target: min_dist[i] = min_j sqrt(sum((vt[j] - vs[i])^2)), idx[i] = the FIRST j attaining it (tf.argmin over the
+ * rounded distances), proj[i,:] = vt[idx[i],:].  vs [ns,3], vt [nt,3] row-major, fp32 or fp64 (the evaluation feeds
+ * fp64).  Any of proj / min_dist / idx may be NULL.  workspace: dpc_point_cloud_distance_workspace_bytes(ns, nt,
+ * sizeof element) bytes of device memory, 8-byte aligned.  Nothing of size ns*nt is materialised, so the source
+ * need not be cut into pc_eval_chamfer_num_parts pieces. */
+int64_t dpc_point_cloud_distance_workspace_bytes(int ns, int nt, int elem_bytes);
+int dpc_point_cloud_distance_f32(const float* vs, int ns, const float* vt, int nt, float* proj, float* min_dist,
+                                 int32_t* idx, void* workspace, int64_t workspace_bytes, void* stream);
+int dpc_point_cloud_distance_f64(const double* vs, int ns, const double* vt, int nt, double* proj, double* min_dist,
+                                 int32_t* idx, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -319,3 +319,28 @@ def projection_loss(proj, gt):
     """sum((gt-proj)^2)/2 / B -- model_pc.py:414-415 (tf.nn.l2_loss / num_samples)."""
     d = gt - proj
     return (d * d).sum() / 2 / proj.shape[0]
+
+
+# ------------------------------------------------------------------ f-4: chamfer evaluation
+def point_cloud_distance(Vs, Vt, chunk=512):
+    """Restates util/point_cloud_distance.py:26-39: for every source point the closest target.
+    diff = Vt - Vs (`:33`), dist = sqrt(sum(diff**2, axis=2)) with the three squares added left to right
+    (`:34`; the order inside TF's reduce_sum is unpinned, like tf.norm), idx = first argmin over the ROUNDED
+    distances (`:35`), proj = Vt[idx] (`:36`), minDist = dist[i, idx] (`:37`).  numpy in the inputs' own
+    precision (np.sqrt is the correctly rounded hardware root); the [VsN, VtN] matrix is formed `chunk` sources
+    at a time.  Returns torch tensors (proj, minDist, idx int32)."""
+    vs = Vs.detach().cpu().numpy() if isinstance(Vs, torch.Tensor) else np.asarray(Vs)
+    vt = Vt.detach().cpu().numpy() if isinstance(Vt, torch.Tensor) else np.asarray(Vt)
+    assert vs.dtype == vt.dtype and vs.dtype in (np.float32, np.float64)
+    ns = vs.shape[0]
+    idx = np.empty(ns, dtype=np.int32)
+    md = np.empty(ns, dtype=vs.dtype)
+    for a in range(0, ns, chunk):
+        d = vt[None, :, :] - vs[a:a + chunk, None, :]
+        q = d * d
+        dist = np.sqrt((q[..., 0] + q[..., 1]) + q[..., 2])
+        j = np.argmin(dist, axis=1)
+        idx[a:a + chunk] = j
+        md[a:a + chunk] = dist[np.arange(dist.shape[0]), j]
+    return torch.from_numpy(vt[idx]), torch.from_numpy(md), torch.from_numpy(idx)
+

@@ -40,5 +40,6 @@ def load():
     ns.gauss_kernel = importlib.import_module("util.gauss_kernel")
     ns.quaternion = importlib.import_module("util.quaternion")
     ns.camera = importlib.import_module("util.camera")
+    ns.point_cloud_distance = importlib.import_module("util.point_cloud_distance")
     assert ns.point_cloud.__file__.startswith(REFERENCE_ROOT)
     return ns

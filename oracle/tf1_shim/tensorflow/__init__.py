@@ -307,7 +307,12 @@ def _bi(fn):
 def _sqrt_rn(t):
     # torch's CPU float32 sqrt is not correctly rounded (off by one ulp for ~0.7% of inputs);
     # TF/Eigen use sqrtps (IEEE).  float64 sqrt + one rounding is exact for float32.
-    return torch.sqrt(t.double()).float() if t.dtype == torch.float32 else torch.sqrt(t)
+    if t.dtype == torch.float32:
+        return torch.sqrt(t.double()).float()
+    if t.dtype == torch.float64:     # numpy's sqrt is the hardware (correctly rounded) one
+        import numpy as _np
+        return torch.from_numpy(_np.sqrt(t.detach().numpy())) if not t.requires_grad else torch.sqrt(t)
+    return torch.sqrt(t)
 
 
 exp = _un(torch.exp)

@@ -6,6 +6,10 @@ O=gpurun_out
 echo "== pytest (variants + benchmark shape)" | tee $O/status.txt
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "splat_variants or full_benchmark_shape or golden_fixture or properties or dropout" > $O/pytest_r8.log 2>&1; echo "pytest rc=$?" | tee -a $O/status.txt
 tail -4 $O/pytest_r8.log
+timeout 300 python -m pytest tests/test_chamfer.py -m gpu -x -q > $O/pytest_chamfer.log 2>&1; echo "pytest chamfer rc=$?" | tee -a $O/status.txt
+tail -4 $O/pytest_chamfer.log
+echo "== pcie probe" | tee -a $O/status.txt
+timeout 120 python scripts/pcie_probe.py > $O/pcie.log 2>&1; cat $O/pcie.log
 echo "== timeline" | tee -a $O/status.txt
 timeout 300 python scripts/step_timeline.py > $O/timeline.log 2>&1; echo "timeline rc=$?" | tee -a $O/status.txt
 cat $O/timeline.log
