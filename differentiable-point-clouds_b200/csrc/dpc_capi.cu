@@ -19,9 +19,14 @@ static int dpc_check_launch() {
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
 // Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 2, 0, 1, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
-// [10] 1 = the raw grid is zeroed by dpc_zero_kernel and the splats run their transform ahead of the grid dependency
-//      (0 = cudaMemsetAsync + wait-first splats); [11] 1 = red.v4 in the splat; [12] per-kernel timeline (dpc_kt)
+static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1};   // [0] points/thread splat fwd, [1] splat bwd
+// [10] 1 = the raw grid is zeroed by dpc_zero_kernel and the forward splat runs its transform ahead of the grid
+//      dependency (default 0 = cudaMemsetAsync + wait-first splat: the reductions run ~4 us faster behind the driver's
+//      memset than behind a store kernel, profiles/r01_k_step_timeline.txt); [11] 1 = 16-byte red.v4 / gathers in the
+//      splats; [12] per-kernel timeline (dpc_kt); [13] 1 = keep the zeroing launch + dL/dscale atomics in the fused
+//      backward (0 = folded partials, no launch); [14] 1 = the backward splat transforms ahead of its grid dependency;
+//      [15] 1 = the fused path smooths x/y IN PLACE and runs the backward in the same grid (two 32 MiB grids per step
+//      instead of three)
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
 // ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are
@@ -160,12 +165,15 @@ int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float
   return dpc_check_launch();
 }
 
-int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float* trans,
-                  const float* focal, float focal_const, float cam_dist, const float* rgb,
-                  int rgb_stop_grad, int B, int N, int Vz, int V,
-                  const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
-                  float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
-                  void* stream) {
+}  // extern "C"
+
+// the public entry point plus the fused backward's extra: fold the depth pass's dL/dscale partials
+static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, const float* trans,
+                            const float* focal, float focal_const, float cam_dist, const float* rgb,
+                            int rgb_stop_grad, int B, int N, int Vz, int V,
+                            const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
+                            float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
+                            const float* d_scale_part, int n_part, float* d_scale_out, void* stream) {
   if (!pc) return DPC_ERR_NULL;
   if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
   if (pose_kind < DPC_POSE_NONE || pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
@@ -178,7 +186,9 @@ int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float
   a.B = B; a.N = N; a.Vz = Vz; a.V = V;
   a.d_vox = d_vox; a.d_vox_rgb = d_vox_rgb; a.d_tr_pc_in = d_tr_pc_in;
   a.d_pc = d_pc; a.d_pose = d_pose; a.d_trans = d_trans; a.d_focal = d_focal; a.d_rgb = d_rgb;
-  a.early = g_tune[10] ? 1 : 0;
+  a.early = g_tune[14] ? 1 : 0;
+  a.gather4 = g_tune[11] ? 1 : 0;
+  a.d_scale_part = d_scale_part; a.n_part = n_part; a.d_scale_out = d_scale_out;
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH(dpc_splat_bwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -187,7 +197,17 @@ int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float
   return dpc_check_launch();
 }
 
-}  // extern "C" (internal launchers below have C++ linkage)
+extern "C" int dpc_splat_bwd(const float* pc, const float* pose, int pose_kind, const float* trans,
+                             const float* focal, float focal_const, float cam_dist, const float* rgb,
+                             int rgb_stop_grad, int B, int N, int Vz, int V,
+                             const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
+                             float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
+                             void* stream) {
+  return splat_bwd_launch(pc, pose, pose_kind, trans, focal, focal_const, cam_dist, rgb, rgb_stop_grad, B, N, Vz, V,
+                          d_vox, d_vox_rgb, d_tr_pc_in, d_pc, d_pose, d_trans, d_focal, d_rgb, nullptr, 0, nullptr, stream);
+}
+
+// (internal launchers below have C++ linkage)
 
 // ---- internal launchers: like the public entry points plus `rev` (read the taps back to front:
 // the transposed correlation, so the backward needs no reversed copy of the taps), NULL taps =
@@ -277,7 +297,8 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
                              int mode, float clip_eps, float cam_dist, float max_depth, int flip_y,
                              int B, int Vz, int V,
                              const float* g_proj, const float* g_vox, const float* g_probs, const float* g_depth,
-                             float* d_in, float* d_scale, void* stream, const float* hz = nullptr) {
+                             float* d_in, float* d_scale, void* stream, const float* hz = nullptr,
+                             float* d_scale_part = nullptr, const DpcZero4Args* zero = nullptr) {
   if (!vox || !d_in) return DPC_ERR_NULL;
   if (mode < DPC_PROJ_NONE || mode > DPC_PROJ_DRC_PROD) return DPC_ERR_ARG;
   if ((g_probs || g_depth) && (mode == DPC_PROJ_NONE || mode == DPC_PROJ_MAX)) return DPC_ERR_ARG;
@@ -286,12 +307,13 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
   const bool lean_case = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
 #ifndef DPC_EMU
   if (lean_case && dpc_tc_conv_z_supported(V, Vz, Kz, g_probs != nullptr || g_depth != nullptr)) {
-    DpcConvZBwdArgs a;
+    DpcConvZBwdArgs a = {};
     dpc_set_taps_z(&a.ht, &a.use_ht, nullptr, 0, 0);
     a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps; a.K = Kz; a.pl = pad_lo; a.rev = rev;
     a.mode = mode; a.eps = clip_eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
     a.B = B; a.Vz = Vz; a.V = V; a.TY = 2;
     a.g_proj = g_proj; a.g_vox = nullptr; a.g_probs = nullptr; a.g_depth = nullptr; a.d_in = d_in; a.d_scale = d_scale;
+    if (d_scale_part && dpc_tc_level() == 2) { a.d_scale_part = d_scale_part; if (zero) a.zero = *zero; }
     DPC_TRY(dpc_tc_conv_z_bwd_lean_launch(a, stream));
     return dpc_check_launch();
   }
@@ -302,7 +324,7 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
                                        B, Vz, V, g_proj, g_vox, g_probs, g_depth, d_in, d_scale, rev, hz, stream));
     return dpc_check_launch();
   }
-  DpcConvZBwdArgs a;
+  DpcConvZBwdArgs a = {};
   dpc_set_taps_z(&a.ht, &a.use_ht, nullptr, 0, 0);
   a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps; a.K = Kz; a.pl = pad_lo; a.rev = rev;
   a.mode = mode; a.eps = clip_eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
@@ -351,7 +373,7 @@ int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
 // ------------------------------------------------------------------------------------ fused path
 static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-struct DpcScratch { float* raw; float* tmp; int64_t total; };
+struct DpcScratch { float* raw; float* tmp; float* part; int64_t total; };
 struct DpcSaved { uint32_t* mask1; uint32_t* mask2; int64_t total; };
 
 static DpcScratch scratch_layout(const dpc_project_params* p, void* base) {
@@ -360,7 +382,8 @@ static DpcScratch scratch_layout(const dpc_project_params* p, void* base) {
   char* c = (char*)base;
   w.raw = (float*)c;
   w.tmp = (float*)(c + align256(g * 4));
-  w.total = 2 * align256(g * 4);
+  w.part = (float*)(c + 2 * align256(g * 4));      // dL/dscale partials of the depth-pass backward: [B, 32 tiles x 8 warps]
+  w.total = 2 * align256(g * 4) + align256((int64_t)p->B * 256 * 4);
   return w;
 }
 
@@ -442,12 +465,15 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   // all-zero (so the next forward needs no memset).  Measured on B200 (profiles/r01_d): not a win --
   // the memset doubles as an L2 warm-up for the splat's reductions, which otherwise miss to HBM --
   // so the default path keeps the memset and leaves the flag to callers that want it.
-  DPC_TRY(launch_conv_xy(w.raw, w.tmp, tx, K, (K - 1) / 2, tx, K, (K - 1) / 2,
+  // In place unless the caller wants the raw grid handed back zeroed: every x/y tile is a pair of whole depth slices,
+  // read completely before it is written, so the pass can overwrite its input -- one 32 MiB grid less per step in L2.
+  float* xy_out = ((p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) || !g_tune[15]) ? w.tmp : w.raw;
+  DPC_TRY(launch_conv_xy(w.raw, xy_out, tx, K, (K - 1) / 2, tx, K, (K - 1) / 2,
                          p->B, p->Vz, p->V, /*clip_in=*/1, sv.mask1, nullptr, /*rev=*/0,
                          /*zero_in=*/(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) ? 1 : 0, stream, hxy, hxy));
   stage_mark(2, stream);
   const bool want_probs = (p->mode != DPC_PROJ_MAX);
-  DPC_TRY(launch_conv_z_fwd(w.tmp, tz, Kz, (Kz - 1) / 2, scale, p->mode, p->clip_eps, p->cam_dist,
+  DPC_TRY(launch_conv_z_fwd(xy_out, tz, Kz, (Kz - 1) / 2, scale, p->mode, p->clip_eps, p->cam_dist,
                             p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V, voxels, scale ? sv.mask2 : nullptr, proj,
                             want_probs ? drc_probs : nullptr, want_probs ? proj_depth : nullptr, stream, hz));
   stage_mark(3, stream);
@@ -474,34 +500,48 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   const float* tz = p->Kz > 0 ? taps_z : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   (void)st;
-  if (d_pose || d_trans || d_focal || d_scale) {     // the accumulation targets, zeroed in one launch
-    DpcZero4Args z;
-    z.p[0] = d_pose; z.n[0] = p->B * (p->pose_kind == DPC_POSE_MATRIX ? 16 : 4);
-    z.p[1] = d_trans; z.n[1] = p->B * 3;
-    z.p[2] = d_focal; z.n[2] = p->B;
-    z.p[3] = d_scale; z.n[3] = p->B;
+  const bool any_grid_grad = g_proj || g_voxels || g_probs || g_depth;
+  DpcZero4Args z;
+  z.p[0] = d_pose; z.n[0] = p->B * (p->pose_kind == DPC_POSE_MATRIX ? 16 : 4);
+  z.p[1] = d_trans; z.n[1] = p->B * 3;
+  z.p[2] = d_focal; z.n[2] = p->B;
+  z.p[3] = d_scale; z.n[3] = p->B;
+  // Training case on the tcgen05 pipelines: no zeroing launch at all.  The depth-pass backward (first kernel) zeroes
+  // the splat backward's targets and leaves dL/dscale as per-warp partials, which the splat backward (last kernel)
+  // folds.  Otherwise: one launch zeroes the (up to) four accumulation targets.
+  bool fold_scale = false;
+#ifndef DPC_EMU
+  fold_scale = g_tune[13] == 0 && any_grid_grad && scale && d_scale && g_proj && !g_voxels && !g_probs && !g_depth &&
+               p->mode == DPC_PROJ_DRC && dpc_tc_level() == 2 && dpc_tc_conv_z_supported(p->V, p->Vz, Kz, false);
+#endif
+  if (fold_scale) {
+    z.p[3] = nullptr;
+  } else if (d_pose || d_trans || d_focal || d_scale) {
     DPC_LAUNCH(dpc_zero4_kernel, dim3(1), dim3(256), 0, stream, z);
     DPC_TRY(dpc_check_launch());
   }
-  const bool any_grid_grad = g_proj || g_voxels || g_probs || g_depth;
   const float* d_raw = nullptr;
   stage_mark(4, stream);
   const float* hxy = (tx && p->taps_xy_host) ? p->taps_xy_host : nullptr;
   const float* hz = (tz && p->taps_z_host) ? p->taps_z_host : nullptr;
   if (any_grid_grad) {
-    // voxels/proj -> dL/d(xy-smoothed) in tmp -> dL/d(raw) in tmp again (per-slice in place; the saved
-    // clip mask applied).  `raw` is not touched: it stays all-zero for the next forward.
+    // voxels/proj -> dL/d(xy-smoothed) in G -> dL/d(raw) in G again (per-slice in place; the saved clip mask
+    // applied).  G is the raw grid's storage (dead after the forward, and the forward zeroes it again) unless the
+    // caller keeps `raw` all-zero between calls (DPC_FLAG_SCRATCH_RAW_ZERO): then G = tmp.
+    float* G = ((p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) || !g_tune[15]) ? w.tmp : w.raw;
     DPC_TRY(launch_conv_z_bwd(voxels, scale ? sv.mask2 : nullptr, scale, tz, Kz, Kz - 1 - (Kz - 1) / 2, /*rev=*/1,
                               p->mode, p->clip_eps, p->cam_dist, p->max_depth, /*flip_y=*/1, p->B, p->Vz, p->V,
-                              g_proj, g_voxels, g_probs, g_depth, w.tmp, d_scale, stream, hz));
+                              g_proj, g_voxels, g_probs, g_depth, G, d_scale, stream, hz,
+                              fold_scale ? w.part : nullptr, fold_scale ? &z : nullptr));
     stage_mark(5, stream);
-    DPC_TRY(launch_conv_xy(w.tmp, w.tmp, tx, K, K - 1 - (K - 1) / 2, tx, K, K - 1 - (K - 1) / 2,
+    DPC_TRY(launch_conv_xy(G, G, tx, K, K - 1 - (K - 1) / 2, tx, K, K - 1 - (K - 1) / 2,
                            p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, sv.mask1, /*rev=*/1, /*zero_in=*/0, stream, hxy, hxy));
-    d_raw = w.tmp;
+    d_raw = G;
   }
   stage_mark(6, stream);
-  DPC_TRY(dpc_splat_bwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
-                        p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr, stream));
+  DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
+                           p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr,
+                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream));
   stage_mark(7, stream);
   return DPC_OK;
 }

@@ -196,6 +196,11 @@ struct DpcConvZBwdArgs {
   const float* g_proj; const float* g_vox; const float* g_probs; const float* g_depth;
   float* d_in; float* d_scale;
   DpcTapsZ ht; int use_ht;   // fast kernels: host-provided taps in the launch parameters
+  // tcgen05 pipeline only: dL/dscale as per-warp partial sums [B * 32 tiles * 8 warps] (folded by the splat backward)
+  // instead of atomics, and the small accumulation targets of the splat backward zeroed by CTA 0 -- together they
+  // remove the zeroing launch in front of the backward (every stream node costs ~3 us)
+  float* d_scale_part;
+  DpcZero4Args zero;
 };
 
 #ifndef DPC_EMU

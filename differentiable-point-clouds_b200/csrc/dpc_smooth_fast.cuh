@@ -773,7 +773,7 @@ static inline int dpc_conv_z_bwd_fast_launch(const float* vox, const uint32_t* m
                                              float max_depth, int flip_y, int B, int Vz, int V, const float* g_proj,
                                              const float* g_vox, const float* g_probs, const float* g_depth, float* d_in,
                                              float* d_scale, int rev, const float* hz, void* stream) {
-  DpcConvZBwdArgs a;
+  DpcConvZBwdArgs a = {};
   a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps_rev; a.K = Kz; a.pl = (Kz - 1) / 2; a.rev = rev;
   a.mode = mode; a.eps = eps; a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y;
   a.B = B; a.Vz = Vz; a.V = V; a.TY = DPC_ZF_TY;

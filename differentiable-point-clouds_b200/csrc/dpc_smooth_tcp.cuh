@@ -316,7 +316,10 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
         dsv = fmaf(dv, vv, dsv);
         v[z] = dv * sc;
       }
-      if (a.d_scale) {
+      if (a.d_scale_part) {
+        const float w = dpc_warp_sum(dsv * inv_s);
+        if (lane == 0) a.d_scale_part[(size_t)tile * 8 + warp] = w;
+      } else if (a.d_scale) {
         const float w = dpc_warp_sum(dsv * inv_s);
         if (lane == 0) atomicAdd(a.d_scale + (tile >> 5), w);
       }
@@ -329,6 +332,10 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
   } else if (warp < DPC_TCP_ISSUER) {
     // ---------------- consumers: thread = ray, dL/d(xy-smoothed) of all 64 levels out
     const int m = tid - 256;
+    if (blockIdx.x == 0) {     // the splat backward's accumulation targets (it runs two kernels from now)
+      for (int q = 0; q < 4; ++q)
+        if (a.zero.p[q]) for (int e = m; e < a.zero.n[q]; e += 128) a.zero.p[q][e] = 0.0f;
+    }
     int i = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += step, ++i) {
       const int s = i & 1, k = i >> 1;

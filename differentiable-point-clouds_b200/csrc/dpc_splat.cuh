@@ -215,7 +215,11 @@ struct DpcSplatBwdArgs {
   int B, N, Vz, V;
   const float* d_vox; const float* d_vox_rgb; const float* d_tr_pc_in;
   float* d_pc; float* d_pose; float* d_trans; float* d_focal; float* d_rgb;
-  int early;   // transform before the grid dependency (experiment knob 10)
+  int early;   // transform before the grid dependency (experiment knob 14)
+  int gather4; // 16-byte gathers of x pairs (experiment knob 11)
+  // per-warp partial sums of dL/dscale left by the depth-pass backward ([B, n_part]); CTA (0, b) folds them into
+  // d_scale_out[b], so the fused backward needs neither atomics on d_scale nor a launch that zeroes it
+  const float* d_scale_part; int n_part; float* d_scale_out;
 };
 
 template <int DPC_SPLAT_PPT>
@@ -271,18 +275,42 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     cell[j].valid = cell[j].valid && (i < n);
   }
   if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
+  if (a.d_scale_part && blockIdx.x == 0 && warp == DPC_SPLAT_THREADS / 32 - 1) {
+    float v = 0.0f;
+    for (int q = lane; q < a.n_part; q += 32) v += a.d_scale_part[(size_t)b * a.n_part + q];
+    v = dpc_warp_sum(v);
+    if (lane == 0) a.d_scale_out[b] = v;
+  }
+  // An uncoalesced warp load costs one L1 wavefront per lane, and the gathers are what this kernel waits for: the x
+  // pair of a row comes in ONE 16-byte load whenever it does not straddle a 4-voxel group (3 of 4 points): 5
+  // wavefronts per point on average instead of 8.
+  const bool quad = a.gather4 && dv && ((V & 3) == 0) && ((((uintptr_t)dv) & 15u) == 0);
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
     const int base = (cell[j].iz * V + cell[j].iy) * V + cell[j].ix;
+    const int o4 = cell[j].ix & 3;
+    if (quad && o4 != 3) {        // ix + 1 < V is implied
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < 2; ++k)
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          const bool inb = cell[j].valid && dv && (cell[j].iz + k < Vz) && (cell[j].iy + jj < V) && (cell[j].ix + ii < V);
-          dw[j][k * 4 + jj * 2 + ii] = inb ? __ldg(dv + base + (k * V + jj) * V + ii) : 0.0f;
+        for (int jj = 0; jj < 2; ++jj) {
+          const bool inb = cell[j].valid && (cell[j].iz + k < Vz) && (cell[j].iy + jj < V);
+          float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (inb) q4 = __ldg(reinterpret_cast<const float4*>(dv + base + (k * V + jj) * V - o4));
+          dw[j][k * 4 + jj * 2 + 0] = o4 == 0 ? q4.x : (o4 == 1 ? q4.y : q4.z);
+          dw[j][k * 4 + jj * 2 + 1] = o4 == 0 ? q4.y : (o4 == 1 ? q4.z : q4.w);
         }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii) {
+            const bool inb = cell[j].valid && dv && (cell[j].iz + k < Vz) && (cell[j].iy + jj < V) && (cell[j].ix + ii < V);
+            dw[j][k * 4 + jj * 2 + ii] = inb ? __ldg(dv + base + (k * V + jj) * V + ii) : 0.0f;
+          }
+    }
   }
   __syncthreads();  // every thread has read its points: the tile can take the results
 

@@ -50,15 +50,7 @@ with torch.cuda.stream(s):
     torch.cuda.synchronize()
     with torch.cuda.graph(g, stream=s):
         pipe.step()
-for rep in range(2):
-    one("graph replay, default knobs (#%d)" % rep, g)
-one("eager, default knobs")
-L.dpc_debug_set(10, 0)
-g2 = torch.cuda.CUDAGraph()
-with torch.cuda.stream(s):
-    pipe.step()
-    torch.cuda.synchronize()
-    with torch.cuda.graph(g2, stream=s):
-        pipe.step()
-one("graph replay, knob 10 = 0 (memset + wait-first splats)", g2)
-L.dpc_debug_set(10, 1)
+knobs = os.environ.get("DPC_KNOBS", "defaults")
+for rep in range(3):
+    one("graph replay, knobs %s (#%d)" % (knobs, rep), g)
+one("eager, knobs %s" % knobs)

@@ -40,10 +40,14 @@ def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
         emu.dpc_debug_set(1, 4)
 
 
-@pytest.mark.parametrize("knob,value", [(11, 1), (10, 0)])
+KNOB_DEFAULTS = {10: 0, 11: 1, 13: 0, 14: 1, 15: 1}
+
+
+@pytest.mark.parametrize("knob,value", [(11, 0), (10, 1), (15, 0)])
 def test_splat_reduction_and_zeroing_variants(emu, knob, value):  # noqa: F811
-    """Knob 11: x pairs as one 16-byte reduction; knob 10 = 0: cudaMemsetAsync + wait-first splats."""
-    default = 1 if knob == 10 else 0
+    """Knob 11 = 0: 8-byte / scalar reductions and gathers instead of 16-byte ones; knob 10 = 1: zeroing kernel +
+    transform ahead of the grid dependency; knob 15 = 0: x/y pass out of place, backward in the second grid."""
+    default = KNOB_DEFAULTS[knob]
     emu.dpc_debug_set(knob, value)
     try:
         for name in ("cfg1_drc_k11", "clustered_init", "v64_small", "edge_points"):
