@@ -414,7 +414,6 @@ def e2e_graphed(pipe, steps, nbuf=4):
         pipe._e2e_setup()
     s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     d_in = [torch.empty_like(pipe.d_in) for _ in range(nbuf)]
-    d_out = [torch.empty_like(pipe.d_out) for _ in range(nbuf)]
     h_out = [torch.empty_like(pipe.h_out).pin_memory() for _ in range(nbuf)]
     for k in range(nbuf):
         d_in[k].copy_(pipe.h_in)
@@ -424,10 +423,10 @@ def e2e_graphed(pipe, steps, nbuf=4):
         pc, q, sc, gt = [p.reshape(sh) for p, sh in zip(parts, pipe.in_shapes)]
         pc, q, sc = pc.detach().requires_grad_(True), q.detach().requires_grad_(True), sc.detach().requires_grad_(True)
         out = pcm.pointcloud_project_fast(pipe.cfg, pc, q, None, None, pipe.kernel, sc)
-        l = ((gt - out["proj"]) ** 2).sum() / 2 / B
+        l = torch.nn.functional.mse_loss(out["proj"], gt, reduction="sum") / (2 * B)      # = sum((gt - proj)^2) / 2 / B
         gpc, gq, gsc = torch.autograd.grad(l, (pc, q, sc))
-        for d, t in zip(torch.split(d_out[k], pipe.out_sizes), (l.detach(), out["proj"].detach(), gpc, gq, gsc)):
-            d.copy_(t.reshape(-1))
+        # the results stay where the step left them (static tensors of the graph's pool); D2H reads them in place
+        return [t.reshape(-1) for t in (l.detach(), out["proj"].detach(), gpc, gq, gsc)]
 
     graphs = []
     torch.cuda.synchronize()
@@ -436,11 +435,13 @@ def e2e_graphed(pipe, steps, nbuf=4):
             for k in range(nbuf):
                 step_fn(k)
     torch.cuda.synchronize()
+    results = []
     for k in range(nbuf):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s_cmp):
-            step_fn(k)
+            results.append(step_fn(k))
         graphs.append(g)
+    h_parts = [torch.split(h, pipe.out_sizes) for h in h_out]
     torch.cuda.synchronize()
 
     ev_in = [torch.cuda.Event() for _ in range(nbuf)]
@@ -469,13 +470,14 @@ def e2e_graphed(pipe, steps, nbuf=4):
             h2d(i + lag)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[k])
-            s_cmp.wait_event(ev_out[k])            # d_out[k] has been drained by the copy of step i - nbuf
+            s_cmp.wait_event(ev_out[k])            # the results of step i - nbuf (same graph) have been copied out
             graphs[k].replay()
             ev_free[k].record(s_cmp)
             ev_cmp[k].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[k])
-            h_out[k].copy_(d_out[k], non_blocking=True)
+            for h, t in zip(h_parts[k], results[k]):
+                h.copy_(t, non_blocking=True)
             ev_out[k].record(s_out)
         if i >= lag:
             ev_out[(i - lag) % nbuf].synchronize()     # the host consumes step i - lag's results

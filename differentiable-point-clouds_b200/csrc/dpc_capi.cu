@@ -109,6 +109,16 @@ int dpc_debug_ktrace_read(unsigned long long* host_out) {
   return DPC_ERR_ARG;
 #endif
 }
+/* diagnostics: per-CTA phase stamps of the splat kernels (2 kernels x 512 CTAs x 8 slots, ns) */
+int dpc_debug_phase_read(unsigned long long* host_out) {
+#ifndef DPC_EMU
+  if (!host_out) return DPC_ERR_NULL;
+  return cudaMemcpyFromSymbol(host_out, dpc_ph, sizeof(unsigned long long) * 2 * 512 * 8) == cudaSuccess ? DPC_OK : DPC_ERR_CUDA;
+#else
+  (void)host_out;
+  return DPC_ERR_ARG;
+#endif
+}
 /* diagnostics: tcgen05.mma micro-benchmark (see dpc_tc_mma_bench_kernel); out = 3 int64 per CTA (device memory) */
 int dpc_debug_mma_bench(long long* out, int nctas, int threads, int reps, int nmma, int spin, int M, int N, void* stream) {
 #ifndef DPC_EMU
@@ -225,6 +235,7 @@ static int launch_conv_xy(const float* in, float* out, const float* taps_x, int 
 #ifndef DPC_EMU
   // tensor-core path (dpc_smooth_tc.cuh): 64^3 grids, any tap count, same taps along x and y
   if (dpc_tc_conv_xy_supported(V, Kx, pad_lo_x, Ky, pad_lo_y, taps_x, taps_y, (int64_t)B * Vz, zero_ptr)) {
+    dpc_tcp_host_taps_next = hx;
     DPC_TRY(dpc_tc_conv_xy_launch(in, out, taps_x, Kx, pad_lo_x, (int64_t)B * Vz, clip_in, mask_bits_out, mask_bits_in, rev, stream));
     return dpc_check_launch();
   }
@@ -269,6 +280,7 @@ static int launch_conv_z_fwd(const float* in, const float* taps_z, int Kz, int p
     a.in = in; a.taps = taps_z; a.K = Kz; a.pl = pad_lo_z; a.rev = 0; a.scale = scale; a.mode = mode; a.eps = clip_eps;
     a.cam_dist = cam_dist; a.max_depth = max_depth; a.flip_y = flip_y; a.B = B; a.Vz = Vz; a.V = V; a.TY = 2;
     a.vox_out = vox_out; a.mask2_out = mask2_out; a.proj = proj; a.probs = nullptr; a.depth = nullptr;
+    dpc_tcp_host_taps_next = hz;
     DPC_TRY(dpc_tc_conv_z_fwd_launch(a, stream));
     return dpc_check_launch();
   }
@@ -314,6 +326,7 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
     a.B = B; a.Vz = Vz; a.V = V; a.TY = 2;
     a.g_proj = g_proj; a.g_vox = nullptr; a.g_probs = nullptr; a.g_depth = nullptr; a.d_in = d_in; a.d_scale = d_scale;
     if (d_scale_part && dpc_tc_level() == 2) { a.d_scale_part = d_scale_part; if (zero) a.zero = *zero; }
+    dpc_tcp_host_taps_next = hz;
     DPC_TRY(dpc_tc_conv_z_bwd_lean_launch(a, stream));
     return dpc_check_launch();
   }

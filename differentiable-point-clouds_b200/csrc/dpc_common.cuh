@@ -89,8 +89,19 @@ DPC_DEV void dpc_kt_mark(int id, int slot) {
     if (slot == 1) atomicMax(&dpc_kt[id * 4 + 2], t);
   }
 }
+// per-CTA phase stamps of the two splat kernels (same switch): [which][cta < 512][8 slots]
+__device__ unsigned long long dpc_ph[2 * 512 * 8];
+DPC_DEV void dpc_ph_mark(int which, int slot) {
+  if (threadIdx.x == 0 && dpc_kt_on) {
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory");
+    if (cta < 512u) dpc_ph[((unsigned)which * 512u + cta) * 8u + (unsigned)slot] = t;
+  }
+}
 #else
 DPC_DEV void dpc_kt_mark(int, int) {}
+DPC_DEV void dpc_ph_mark(int, int) {}
 #endif
 enum { DPC_KT_ZERO = 0, DPC_KT_SPLAT_F, DPC_KT_XY_F, DPC_KT_Z_F, DPC_KT_ZERO4, DPC_KT_Z_B, DPC_KT_XY_B, DPC_KT_SPLAT_B };
 

@@ -213,6 +213,7 @@ DPC_DEV void dpc_tc_issue(uint32_t sbase, uint32_t d_tmem, uint64_t* bar) { dpc_
 // Toeplitz operand of a correlation with zero padding: out[n] = sum_j tap(j) in[n + j - pl]  =>
 // T[n][k] = tap(k - n + pl); rows n (the MMA's N), K-major.  tap(j) = taps[rev ? K-1-j : j] inside 0..K-1
 // (NULL taps = identity).  All 128 threads; contains a __syncthreads.
+DPC_DEV void dpc_tc_build_toeplitz_from(unsigned char* tbase, const float* tp_hi, const float* tp_lo, int pl);
 DPC_DEV void dpc_tc_build_toeplitz(unsigned char* tbase, float* tp_hi, float* tp_lo, const float* taps, int K, int pl, int rev) {
   for (int i = threadIdx.x; i < 192; i += (int)blockDim.x) {
     const int j = i - 64;
@@ -222,6 +223,10 @@ DPC_DEV void dpc_tc_build_toeplitz(unsigned char* tbase, float* tp_hi, float* tp
     tp_lo[i] = dpc_tc_hi(t - th);
   }
   __syncthreads();
+  dpc_tc_build_toeplitz_from(tbase, tp_hi, tp_lo, pl);
+}
+// second half: the padded tap rows (hi / lo, 192 entries, tap j at 64 + j) -> the operand in the MMA's smem layout
+DPC_DEV void dpc_tc_build_toeplitz_from(unsigned char* tbase, const float* tp_hi, const float* tp_lo, int pl) {
   if (threadIdx.x < 128) {
     const int n = threadIdx.x >> 1, h = threadIdx.x & 1;
 #pragma unroll
@@ -553,6 +558,18 @@ static int dpc_tc_sm_count() {
   }
   return n;
 }
+// Host copy of the taps for the NEXT pipeline launch on this thread (set by the C-ABI layer right before it calls a
+// launcher below, consumed and cleared there); NULL = the kernel reads the device taps.
+static thread_local const float* dpc_tcp_host_taps_next = nullptr;
+static inline DpcTcpTaps dpc_tcp_take_host_taps(int K) {
+  DpcTcpTaps ht;
+  const float* h = dpc_tcp_host_taps_next;
+  dpc_tcp_host_taps_next = nullptr;
+  ht.valid = (h != nullptr && K >= 1 && K <= DPC_MAX_TAPS && !dpc_ignore_host_taps) ? 1 : 0;
+  for (int i = 0; i <= DPC_MAX_TAPS; ++i) ht.t[i] = (ht.valid && i < K) ? h[i] : 0.0f;
+  return ht;
+}
+
 static inline bool dpc_tc_conv_xy_supported(int V, int Kx, int plx, int Ky, int ply, const float* tx, const float* ty,
                                             int64_t nslices, const float* zero_ptr) {
   return dpc_tc_level() && V == 64 && Kx == Ky && plx == ply && tx == ty && Kx >= 1 && Kx <= DPC_MAX_TAPS &&
@@ -575,10 +592,11 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
     const int ntiles = (int)(nslices / 2), grid = ntiles < dpc_tc_sm_count() ? ntiles : dpc_tc_sm_count();
     CUtensorMap xymap;
     if (dpc_tc_make_xymap(&xymap, in, nslices) != DPC_OK) return DPC_ERR_CUDA;
+    const DpcTcpTaps ht = dpc_tcp_take_host_taps(taps ? K : 0);
 #define DPC_TCP_XY_GO(C, MO, MI) do { \
     if (cudaFuncSetAttribute(dpc_tcp_conv_xy_kernel<C, MO, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess) \
       return DPC_ERR_CUDA; \
-    DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, xymap, K, pl, ntiles); \
+    DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, xymap, K, pl, ntiles, ht); \
     return DPC_OK; } while (0)
     switch (sel) {
       case 0: DPC_TCP_XY_GO(false, false, false);
@@ -623,7 +641,8 @@ static inline int dpc_tcp_conv_z_fwd_go(const DpcConvZArgs& a, void* stream) {
   if (cudaFuncSetAttribute(dpc_tcp_conv_z_fwd_kernel<MODE, HAS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess)
     return DPC_ERR_CUDA;
   const int ntiles = 32 * a.B, grid = ntiles < dpc_tc_sm_count() ? ntiles : dpc_tc_sm_count();
-  DPC_LAUNCH((dpc_tcp_conv_z_fwd_kernel<MODE, HAS_S>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles);
+  const DpcTcpTaps ht = dpc_tcp_take_host_taps(a.taps ? a.K : 0);
+  DPC_LAUNCH((dpc_tcp_conv_z_fwd_kernel<MODE, HAS_S>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles, ht);
   return DPC_OK;
 }
 static inline int dpc_tc_conv_z_fwd_launch(const DpcConvZArgs& a, void* stream) {
@@ -651,7 +670,8 @@ static inline int dpc_tc_conv_z_bwd_lean_launch(const DpcConvZBwdArgs& a, void* 
     CUtensorMap zmap;
     if (dpc_tc_make_zmap(&zmap, a.vox, a.B) != DPC_OK) return DPC_ERR_CUDA;
     const int ntiles = 32 * a.B, grid = ntiles < dpc_tc_sm_count() ? ntiles : dpc_tc_sm_count();
-    DPC_LAUNCH(dpc_tcp_conv_z_bwd_lean_kernel, dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles);
+    const DpcTcpTaps ht = dpc_tcp_take_host_taps(a.taps ? a.K : 0);
+    DPC_LAUNCH(dpc_tcp_conv_z_bwd_lean_kernel, dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles, ht);
     return DPC_OK;
   }
   if (cudaFuncSetAttribute(dpc_tc_conv_z_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess)

@@ -84,6 +84,11 @@ DPC_DEV void dpc_tcp_put_a(uint32_t tmem, int s, int h, const float* v) {
   dpc_tc_split_st32(lane_t + DPC_TCP_AHI(s) + 32u * (uint32_t)h, lane_t + DPC_TCP_ALO(s) + 32u * (uint32_t)h, v);
 }
 
+// The taps as launch parameters when the host knows them (sigma is a host value in the reference's schedule): the
+// prologue then builds the Toeplitz operand from the constant bank instead of waiting ~1 us for a global load that
+// misses L2 -- the prologue of these 226 KB CTAs cannot overlap the previous kernel, so it is on the critical path.
+struct DpcTcpTaps { float t[DPC_MAX_TAPS + 1]; int valid; };
+
 #define DPC_TCP_SETUP(TAPS, KK, PL, REV)                                            \
   extern __shared__ __align__(1024) unsigned char dpc_tcp_dsm[];                    \
   __shared__ __align__(8) DpcTcpBars B;                                             \
@@ -108,7 +113,19 @@ DPC_DEV void dpc_tcp_put_a(uint32_t tmem, int s, int h, const float* v) {
   }                                                                                 \
   {                                                                                 \
     float* tp_hi = reinterpret_cast<float*>(sm + DPC_TCP_S_OFF);      /* prologue scratch inside the staging ring */ \
-    dpc_tc_build_toeplitz(sm + DPC_TCP_T_OFF, tp_hi, tp_hi + 192, TAPS, KK, PL, REV); \
+    if (ht.valid) {                                                                 \
+      for (int i_ = tid; i_ < 192; i_ += DPC_TCP_THREADS) {                         \
+        const int j_ = i_ - 64;                                                     \
+        const float t_ = (j_ >= 0 && j_ < (KK)) ? ht.t[(REV) ? ((KK) - 1 - j_) : j_] : 0.0f; \
+        const float th_ = dpc_tc_hi(t_);                                            \
+        tp_hi[i_] = th_;                                                            \
+        tp_hi[192 + i_] = dpc_tc_hi(t_ - th_);                                      \
+      }                                                                             \
+      __syncthreads();                                                              \
+      dpc_tc_build_toeplitz_from(sm + DPC_TCP_T_OFF, tp_hi, tp_hi + 192, PL);       \
+    } else {                                                                        \
+      dpc_tc_build_toeplitz(sm + DPC_TCP_T_OFF, tp_hi, tp_hi + 192, TAPS, KK, PL, REV); \
+    }                                                                               \
   }                                                                                 \
   dpc_fence_proxy_async();                                                          \
   dpc_tc_fence_before();                                                            \
@@ -156,7 +173,8 @@ DPC_DEV void dpc_tcp_issuer_z(unsigned char* sm, uint32_t sbase, uint32_t tmem, 
 // tile = (sample b, image rows 2t, 2t+1): 128 rays x 64 levels.
 template <int MODE, bool HAS_S>
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
-dpc_tcp_conv_z_fwd_kernel(const __grid_constant__ DpcConvZArgs a, const __grid_constant__ CUtensorMap zmap, int ntiles) {
+dpc_tcp_conv_z_fwd_kernel(const __grid_constant__ DpcConvZArgs a, const __grid_constant__ CUtensorMap zmap, int ntiles,
+                          const __grid_constant__ DpcTcpTaps ht) {
   constexpr int V = 64, Vz = 64;
   constexpr bool CLAMPU = (MODE == DPC_PROJ_DRC);
   __shared__ __align__(8) float2 comb[128];
@@ -253,7 +271,8 @@ dpc_tcp_conv_z_fwd_kernel(const __grid_constant__ DpcConvZArgs a, const __grid_c
 // level), the back end only stores.  So EIGHT producer warps (thread = (ray, depth half); the two partial products of
 // a ray meet through smem) and FOUR consumer warps (thread = ray, all 64 levels).
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
-dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const __grid_constant__ CUtensorMap zmap, int ntiles) {
+dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const __grid_constant__ CUtensorMap zmap, int ntiles,
+                               const __grid_constant__ DpcTcpTaps ht) {
   constexpr int V = 64, Vz = 64;
   __shared__ float pp[2][2][128];
   constexpr int kt_id = DPC_KT_Z_B;
@@ -369,7 +388,8 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
 //              overlaps GEMM 2 of the next tile.
 template <bool CLIP, bool MOUT, bool MIN>
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
-dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_constant__ CUtensorMap xymap, int K, int pl, int ntiles) {
+dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_constant__ CUtensorMap xymap, int K, int pl, int ntiles,
+                       const __grid_constant__ DpcTcpTaps ht) {
   constexpr int V = 64;
   constexpr int kt_id = MIN ? DPC_KT_XY_B : DPC_KT_XY_F;
   DPC_TCP_SETUP(a.taps_x, K, pl, a.rev);

@@ -74,11 +74,13 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
   const int V = a.V, Vz = a.Vz;
 
   dpc_kt_mark(DPC_KT_SPLAT_F, 0);
+  dpc_ph_mark(0, 0);
   dpc_grid_dep_trigger();
   if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_F, 1); }
   dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
                    a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
+  dpc_ph_mark(0, 1);
 
   float z[DPC_SPLAT_PPT], y[DPC_SPLAT_PPT], x[DPC_SPLAT_PPT];
 #pragma unroll
@@ -90,6 +92,7 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
       dpc_transform_point(P, tile[i * 3 + 0], tile[i * 3 + 1], tile[i * 3 + 2], z[j], y[j], x[j], cam);
     }
   }
+  dpc_ph_mark(0, 2);
   if (a.tr_pc) {
     __syncthreads();  // everyone has read its points
 #pragma unroll
@@ -102,7 +105,9 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
     dpc_unstage_points(a.tr_pc + ((size_t)b * a.N + p_first) * 3, tile, n);
   }
   // the grid is zero (and everything older than the zeroing kernel complete) from here on
+  dpc_ph_mark(0, 3);
   if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_F, 1); }
+  dpc_ph_mark(0, 4);
 
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
@@ -205,6 +210,7 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
       }
     }
   }
+  dpc_ph_mark(0, 5);
   dpc_kt_mark(DPC_KT_SPLAT_F, 3);
 }
 
@@ -244,11 +250,13 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   // The points and the camera are inputs of the forward (nothing in front of this kernel writes them), so they are
   // staged and transformed while the x/y pass of the backward is still draining; the gathers wait for it.
   dpc_kt_mark(DPC_KT_SPLAT_B, 0);
+  dpc_ph_mark(1, 0);
   dpc_grid_dep_trigger();
   if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
   dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
                    a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
+  dpc_ph_mark(1, 1);
 
   float acc[12];
 #pragma unroll
@@ -274,7 +282,9 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     cell[j] = dpc_cell(z, y, x, Vz, V);
     cell[j].valid = cell[j].valid && (i < n);
   }
+  dpc_ph_mark(1, 2);
   if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
+  dpc_ph_mark(1, 3);
   if (a.d_scale_part && blockIdx.x == 0 && warp == DPC_SPLAT_THREADS / 32 - 1) {
     float v = 0.0f;
     for (int q = lane; q < a.n_part; q += 32) v += a.d_scale_part[(size_t)b * a.n_part + q];
@@ -312,6 +322,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
           }
     }
   }
+  dpc_ph_mark(1, 4);   // gathers issued
   __syncthreads();  // every thread has read its points: the tile can take the results
 
   // pass 2: weights' derivative, chain rule through the camera
@@ -364,11 +375,13 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
       if (a.d_pc) { tile[i * 3 + 0] = d0; tile[i * 3 + 1] = d1; tile[i * 3 + 2] = d2; }
     }
   }
+  dpc_ph_mark(1, 5);   // gathers consumed, chain rule done
   if (a.d_pc) {
     dpc_fence_proxy_async();
     __syncthreads();
     dpc_unstage_points(a.d_pc + ((size_t)b * a.N + p_first) * 3, tile, n);
   }
+  dpc_ph_mark(1, 6);
   dpc_kt_mark(DPC_KT_SPLAT_B, 3);
   if (a.pose_kind == DPC_POSE_NONE) return;
   const bool want_pose = a.d_pose != nullptr, want_t = a.d_trans != nullptr, want_f = a.d_focal != nullptr;

@@ -66,6 +66,10 @@ int dpc_debug_set(int key, int value);
  * out[4*k + {0: first CTA entry, 1: first CTA past its grid dependency, 2: last CTA past it, 3: last CTA exit}],
  * k = 0 zero, 1 splat fwd, 2 x/y fwd, 3 depth fwd, 4 zero4, 5 depth bwd, 6 x/y bwd, 7 splat bwd; 64 uint64 to host. */
 int dpc_debug_ktrace_read(unsigned long long* host_out);
+/* same switch: thread 0 of every CTA (first 512) of the splat kernels stamps its phases; out[((which * 512 + cta) * 8 + slot],
+ * which 0 = forward {entry, points staged, transformed, tr_pc stored, past the dependency, reductions issued},
+ * 1 = backward {entry, staged, transformed, past the dependency, gathers issued, chain rule done, d_pc stored}. */
+int dpc_debug_phase_read(unsigned long long* host_out);
 /* key 3 = 1: record CUDA events around every stage of the fused forward/backward; this returns the
  * six stage durations (ms) of the last instrumented step (synchronises on the last event). */
 int dpc_debug_stage_ms(float* out6);
