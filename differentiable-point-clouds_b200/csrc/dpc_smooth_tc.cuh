@@ -561,6 +561,7 @@ static int dpc_tc_sm_count() {
 // Host copy of the taps for the NEXT pipeline launch on this thread (set by the C-ABI layer right before it calls a
 // launcher below, consumed and cleared there); NULL = the kernel reads the device taps.
 static thread_local const float* dpc_tcp_host_taps_next = nullptr;
+static int dpc_tcp_pdrain = 0;      // experiment knob 2: the producer warps of the x/y pipeline store the tiles
 static inline DpcTcpTaps dpc_tcp_take_host_taps(int K) {
   DpcTcpTaps ht;
   const float* h = dpc_tcp_host_taps_next;
@@ -593,11 +594,12 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
     CUtensorMap xymap;
     if (dpc_tc_make_xymap(&xymap, in, nslices) != DPC_OK) return DPC_ERR_CUDA;
     const DpcTcpTaps ht = dpc_tcp_take_host_taps(taps ? K : 0);
-#define DPC_TCP_XY_GO(C, MO, MI) do { \
-    if (cudaFuncSetAttribute(dpc_tcp_conv_xy_kernel<C, MO, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess) \
+#define DPC_TCP_XY_GO1(C, MO, MI, PD) do { \
+    if (cudaFuncSetAttribute(dpc_tcp_conv_xy_kernel<C, MO, MI, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess) \
       return DPC_ERR_CUDA; \
-    DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, xymap, K, pl, ntiles, ht); \
+    DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI, PD>), dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, xymap, K, pl, ntiles, ht); \
     return DPC_OK; } while (0)
+#define DPC_TCP_XY_GO(C, MO, MI) do { if (dpc_tcp_pdrain) DPC_TCP_XY_GO1(C, MO, MI, true); else DPC_TCP_XY_GO1(C, MO, MI, false); } while (0)
     switch (sel) {
       case 0: DPC_TCP_XY_GO(false, false, false);
       case 1: DPC_TCP_XY_GO(false, false, true);
@@ -609,6 +611,7 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
       default: DPC_TCP_XY_GO(true, true, true);
     }
 #undef DPC_TCP_XY_GO
+#undef DPC_TCP_XY_GO1
   }
   switch (sel) {
     case 0: DPC_TC_XY_GO(false, false, false);

@@ -386,16 +386,50 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
 //   consumers: D1[s] row (slice, y') -> transposed into smem X[s] (raw fp32, same chunk swizzle) -> row (slice, x)
 //              half -> split -> A[s] again -> GEMM 2 -> D2[s] -> store (slice, y, x), one tile late so that it
 //              overlaps GEMM 2 of the next tile.
-template <bool CLIP, bool MOUT, bool MIN>
+// PDRAIN (knob 2): the four PRODUCER warps store the finished tiles instead of the consumers.  The consumers' chain per
+// tile is  D1 -> transpose through smem -> split -> A planes  and then  D2 -> global; the producers only split one
+// staged row each.  With the store moved over, a stage's critical path is  P -> GEMM 1 -> transpose -> GEMM 2  and the
+// store of tile i-2 runs under it (accfree[s] tells the issuer that D2[s] has been drained before GEMM 2 of tile i).
+template <bool CLIP, bool MOUT, bool MIN, bool PDRAIN>
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
 dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_constant__ CUtensorMap xymap, int K, int pl, int ntiles,
                        const __grid_constant__ DpcTcpTaps ht) {
   constexpr int V = 64;
   constexpr int kt_id = MIN ? DPC_KT_XY_B : DPC_KT_XY_F;
   DPC_TCP_SETUP(a.taps_x, K, pl, a.rev);
+  if (PDRAIN) {           // accfree[s]: 4 producer warps -> issuer, D2[s] drained
+    if (tid == 0) { dpc_mbar_init(&B.accfree[0], 4); dpc_mbar_init(&B.accfree[1], 4); }
+    __syncthreads();
+  }
   if (warp < 4) {
     // ---------------- producers: thread = row (slice, y)
     const int m = tid;
+    // PDRAIN: store of tile j (D2[s] ready: done2 of tile j has been waited for): thread = (slice, x), all 64 rows y
+    auto pdrain = [&](int j, int tile) {
+      const int s = j & 1;
+      const size_t base = (size_t)tile * (2 * V * V);
+      const int sl = m >> 6, rx = m & 63;
+      dpc_tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t mw = 0xffffffffu;
+        if (MIN) mw = a.mask_in[(base >> 5) + (size_t)sl * 128 + 2 * (32 * h + lane) + ((m >> 5) & 1)];
+        float r[32];
+        dpc_tc_ld32(tmem + DPC_TCP_D2(s) + (uint32_t)(h * 32) + ((uint32_t)(warp * 32) << 16), r);
+        dpc_tc_wait_ld();
+        float* dst = a.out + base + (size_t)sl * V * V + (size_t)(32 * h) * V + rx;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          float v = r[q];
+          if (MIN) {
+            const uint32_t w = __shfl_sync(DPC_FULL, mw, q);
+            if (!((w >> lane) & 1u)) v = 0.0f;
+          }
+          dst[q * V] = v;
+        }
+      }
+      dpc_tcp_warp_arrive(&B.accfree[s]);
+    };
     int i = 0, slot = 0, sph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += step, ++i) {
       const int s = i & 1, k = i >> 1;
@@ -426,7 +460,14 @@ dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_c
       dpc_tcp_warp_arrive(&B.sfree[slot]);
       dpc_tc_wait_st();
       dpc_tcp_warp_arrive(&B.opfull[s]);
+      if (PDRAIN && k >= 1) pdrain(i - 2, tile - 2 * step);    // its done2 was waited for above
       if (++slot == DPC_TCP_NS) { slot = 0; sph ^= 1; }
+    }
+    if (PDRAIN) {          // the last two tiles of this CTA
+      for (int j = (i >= 2 ? i - 2 : 0); j < i; ++j) {
+        dpc_mbar_wait(&B.done2[j & 1], (j >> 1) & 1);
+        pdrain(j, (int)blockIdx.x + j * step);
+      }
     }
   } else if (warp < DPC_TCP_ISSUER) {
     // ---------------- consumers
@@ -484,10 +525,10 @@ dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_c
       dpc_tcp_put_a(tmem, s, h, r);                    // A planes of stage s: GEMM 1 of this tile has finished reading them
       dpc_tc_wait_st();
       dpc_tcp_warp_arrive(&B.opfull2[s]);
-      if (prev_tile >= 0) drain(i - 1, prev_tile);      // overlaps GEMM 2 of tile i
+      if (!PDRAIN && prev_tile >= 0) drain(i - 1, prev_tile);      // overlaps GEMM 2 of tile i
       prev_tile = tile;
     }
-    if (prev_tile >= 0) drain(i - 1, prev_tile);
+    if (!PDRAIN && prev_tile >= 0) drain(i - 1, prev_tile);
   } else {
     // ---------------- issuing / loading lane
     if (dpc_elect_one()) {
@@ -511,6 +552,7 @@ dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_c
       auto gemm2 = [&](int j) {                // D2[s] drained: every consumer stored tile j-2 before it published tile j
         const int s = j & 1, k = j >> 1;
         dpc_mbar_wait(&B.opfull2[s], k & 1);
+        if (PDRAIN && k >= 1) dpc_mbar_wait(&B.accfree[s], (k - 1) & 1);     // the producers have stored tile j-2 (D2[s])
         dpc_tc_fence_after();
         dpc_tc_issue_ts(tmem + DPC_TCP_AHI(s), tmem + DPC_TCP_ALO(s), sbase + DPC_TCP_T_OFF, tmem + DPC_TCP_D2(s), &B.done2[s]);
       };
