@@ -401,88 +401,63 @@ def e2e_pipelined(pipe, steps):
 
 
 def e2e_graphed(pipe, steps, nbuf=4):
-    """As e2e_pipelined, but the step a user builds with the public API (pointcloud_project_fast ->
-    loss -> autograd) is captured once per buffer set in a CUDA graph and replayed: the ~25 small
-    launches and the Python/autograd time of a step collapse into one graph launch, which is what
-    bounds the eager path (the GPU work is ~0.12 ms, the eager host time ~0.5 ms).
-    `nbuf` buffer sets are in flight: the host reads the results of step i - (nbuf - 1) while the copies and the
-    compute of the later steps proceed, so neither the host's enqueue time (~0.1 ms per step) nor a copy
-    (H2D 3.6 MB: ~0.11 ms, D2H ~0.07 ms, scripts/pcie_probe.py) sits on the critical path of the next step."""
+    """End to end with HOST buffers, the way a throughput-minded caller would run it: ONE CUDA graph per buffer set holds
+    the whole step -- H2D of the step's inputs from pinned memory, the step a user builds with the public API
+    (pointcloud_project_fast -> loss -> autograd), D2H of loss + silhouettes + gradients into pinned memory -- and
+    `nbuf` such graphs are in flight, each on its own stream.  Per step the host does one graph launch and (nbuf - 1
+    steps later) one event wait; the copies of one step run under the kernels of its neighbours.  The eager path is
+    bounded by ~0.5 ms of Python/autograd time per step, separate copy/compute streams with per-step event bookkeeping
+    by ~0.15 ms of host time (profiles/r01_k_pcie_probe.txt: H2D 3.6 MB 0.11 ms, D2H 0.07 ms, bookkeeping 0.03 ms)."""
     from dpc_b200.util import point_cloud as pcm
     dev = pipe.dev
     if not hasattr(pipe, "h_in"):
         pipe._e2e_setup()
-    s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    pcm.release_scratch()            # scratch grids are cached per stream: drop those of streams that are gone
+    streams = [torch.cuda.Stream(dev) for _ in range(nbuf)]
     d_in = [torch.empty_like(pipe.d_in) for _ in range(nbuf)]
     h_out = [torch.empty_like(pipe.h_out).pin_memory() for _ in range(nbuf)]
-    for k in range(nbuf):
-        d_in[k].copy_(pipe.h_in)
+    h_parts = [torch.split(h, pipe.out_sizes) for h in h_out]
 
     def step_fn(k):
+        d_in[k].copy_(pipe.h_in, non_blocking=True)                                   # H2D, 3.6 MB
         parts = torch.split(d_in[k], pipe.in_sizes)
         pc, q, sc, gt = [p.reshape(sh) for p, sh in zip(parts, pipe.in_shapes)]
         pc, q, sc = pc.detach().requires_grad_(True), q.detach().requires_grad_(True), sc.detach().requires_grad_(True)
         out = pcm.pointcloud_project_fast(pipe.cfg, pc, q, None, None, pipe.kernel, sc)
         l = torch.nn.functional.mse_loss(out["proj"], gt, reduction="sum") / (2 * B)      # = sum((gt - proj)^2) / 2 / B
         gpc, gq, gsc = torch.autograd.grad(l, (pc, q, sc))
-        # the results stay where the step left them (static tensors of the graph's pool); D2H reads them in place
-        return [t.reshape(-1) for t in (l.detach(), out["proj"].detach(), gpc, gq, gsc)]
+        for h, t in zip(h_parts[k], (l.detach(), out["proj"].detach(), gpc, gq, gsc)):    # D2H, 3.6 MB
+            h.copy_(t.reshape(-1), non_blocking=True)
 
     graphs = []
     torch.cuda.synchronize()
-    with torch.cuda.stream(s_cmp):
-        for _ in range(3):
-            for k in range(nbuf):
+    for k in range(nbuf):
+        with torch.cuda.stream(streams[k]):
+            for _ in range(3):
                 step_fn(k)
     torch.cuda.synchronize()
-    results = []
     for k in range(nbuf):
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s_cmp):
-            results.append(step_fn(k))
+        with torch.cuda.graph(g, stream=streams[k]):
+            step_fn(k)
         graphs.append(g)
-    h_parts = [torch.split(h, pipe.out_sizes) for h in h_out]
     torch.cuda.synchronize()
-
-    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
-    ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
-    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
-    ev_free = [torch.cuda.Event() for _ in range(nbuf)]
-    for k in range(nbuf):
-        ev_free[k].record(s_cmp)
-        ev_out[k].record(s_out)
-    torch.cuda.synchronize()
-
-    def h2d(i):
-        k = i % nbuf
-        with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_free[k])
-            d_in[k].copy_(pipe.h_in, non_blocking=True)
-            ev_in[k].record(s_in)
+    done = [torch.cuda.Event() for _ in range(nbuf)]
 
     lag = nbuf - 1
+    loss = 0.0
     t0 = time.perf_counter()
-    for j in range(min(lag, steps)):
-        h2d(j)
     for i in range(steps):
         k = i % nbuf
-        if i + lag < steps:
-            h2d(i + lag)
-        with torch.cuda.stream(s_cmp):
-            s_cmp.wait_event(ev_in[k])
-            s_cmp.wait_event(ev_out[k])            # the results of step i - nbuf (same graph) have been copied out
+        if i >= nbuf:
+            done[k].synchronize()                 # the host consumes step i - nbuf's results before its buffers are reused
+            loss = float(h_out[k][0])
+        with torch.cuda.stream(streams[k]):
             graphs[k].replay()
-            ev_free[k].record(s_cmp)
-            ev_cmp[k].record(s_cmp)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_cmp[k])
-            for h, t in zip(h_parts[k], results[k]):
-                h.copy_(t, non_blocking=True)
-            ev_out[k].record(s_out)
-        if i >= lag:
-            ev_out[(i - lag) % nbuf].synchronize()     # the host consumes step i - lag's results
-    for i in range(max(0, steps - lag), steps):
-        ev_out[i % nbuf].synchronize()
+            done[k].record(streams[k])
+    for i in range(max(0, steps - nbuf), steps):
+        done[i % nbuf].synchronize()
     loss = float(h_out[(steps - 1) % nbuf][0])
     dt = time.perf_counter() - t0
     torch.cuda.synchronize()
@@ -574,9 +549,9 @@ def run_ours(args, rank, local_rank, world):
         t_g = D.reduce_scalar(t_g, "max", dev)
         if abs(loss_g - loss) <= 1e-3 * max(1.0, abs(loss)):
             e2e_value, t_e2e, n_e2e_used = world * B * n_g / t_g, t_g, n_g
-            e2e_mode = ("the API-built step (pointcloud_project_fast -> loss -> autograd) captured in a CUDA graph and "
-                        "replayed; H2D/D2H of neighbouring steps overlap compute (3 streams, 4 buffer sets in flight: the host "
-                        "reads step i-3's results while steps i-2..i are copied/computed)")
+            e2e_mode = ("one CUDA graph per buffer set = H2D of the inputs + the API-built step (pointcloud_project_fast -> loss -> "
+                        "autograd) + D2H of loss/silhouettes/gradients; 4 graphs in flight on 4 streams, the host reads step "
+                        "i-4's results before relaunching its graph")
             n_e2e = n_g
     except Exception as exc:  # capture not possible: keep the eager number
         print("graph capture failed: %r" % (exc,), file=sys.stderr)

@@ -19,7 +19,7 @@ static int dpc_check_launch() {
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
 // Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1};   // [0] points/thread splat fwd, [1] splat bwd
+static int g_tune[16] = {4, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1};   // [0] points/thread splat fwd, [1] splat bwd
 // [10] 1 = the raw grid is zeroed by dpc_zero_kernel and the forward splat runs its transform ahead of the grid
 //      dependency (default 0 = cudaMemsetAsync + wait-first splat: the reductions run ~4 us faster behind the driver's
 //      memset than behind a store kernel, profiles/r01_k_step_timeline.txt); [11] 1 = 16-byte red.v4 / gathers in the
@@ -27,6 +27,8 @@ static int g_tune[16] = {4, 4, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1};   // [
 //      backward (0 = folded partials, no launch); [14] 1 = the backward splat transforms ahead of its grid dependency;
 //      [15] 1 = the fused path smooths x/y IN PLACE and runs the backward in the same grid (two 32 MiB grids per step
 //      instead of three)
+// measured after the 16-byte gathers (profiles/r01_m_*): forward 4 / 2 / 1 points per thread = 10.2 / 10.7 / 13.9 us,
+// backward 21.5 / 28.5 / 20.6 us -> forward 4 (250 CTAs), backward 1 (1000 CTAs)
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
 // ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are

@@ -306,8 +306,8 @@ def _scratch_for(device, stream, nbytes):
     key = (device.index if device.type == "cuda" else -1, stream, nbytes)
     buf = _SCRATCH.get(key)
     if buf is None:
-        if len(_SCRATCH) >= 8:
-            _SCRATCH.clear()
+        if len(_SCRATCH) >= 32:       # streams come and go; a captured CUDA graph keeps using its stream's buffer,
+            _SCRATCH.clear()          # so the cache is only dropped when it is clearly stale (see release_scratch)
         buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
     return key, buf

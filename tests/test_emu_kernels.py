@@ -26,7 +26,7 @@ def test_emulated_kernels_match_golden(emu, name):  # noqa: F811
     cases.assert_parity(fx, outs, grads)
 
 
-@pytest.mark.parametrize("ppt", [1, 2])
+@pytest.mark.parametrize("ppt", [1, 2, 4])
 def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
     emu.dpc_debug_set(0, ppt)
     emu.dpc_debug_set(1, ppt)
@@ -37,7 +37,7 @@ def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
             cases.assert_parity(fx, outs, grads)
     finally:
         emu.dpc_debug_set(0, 4)
-        emu.dpc_debug_set(1, 4)
+        emu.dpc_debug_set(1, 1)
 
 
 KNOB_DEFAULTS = {10: 0, 11: 1, 13: 0, 14: 1, 15: 1}
