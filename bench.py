@@ -35,16 +35,17 @@ G_BYTES = V * V * V * 4
 FULL_PATH_BYTES = 6 * G_BYTES + 4 * 12 * N + 64 * N + 2 * 4 * V * V
 # per-launch algorithmic bytes of each stage, per projection (DESIGN.md "kernels and rooflines")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B=32, from the committed `ncu --set full` capture of this
-# very command (profiles/r01_i_tcgen05_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
+# very command (profiles/r01_l_inplace_v4_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
 # previous kernel left in L2 are re-read from HBM, and the 32 MiB of output stays in L2 until a later kernel evicts it)
 NCU_TRAFFIC_B32 = {
-    "splat_fwd": 22.242048e6 + 0.010240e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
-    "conv_xy_fwd": 33.591552e6 + 0.604160e6,
-    "conv_z_fwd": 33.590272e6 + 0.952320e6,
-    "conv_z_bwd": 35.162624e6 + 0.555008e6,
-    "conv_xy_bwd": 34.638336e6 + 0.0,
-    "splat_bwd": 26.716160e6 + 0.0,
+    "splat_fwd": 22.242048e6 + 0.038656e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
+    "conv_xy_fwd": 33.592832e6 + 0.006400e6,
+    "conv_z_fwd": 33.590272e6 + 0.717312e6,
+    "conv_z_bwd": 35.164416e6 + 0.601600e6,
+    "conv_xy_bwd": 34.638592e6 + 0.015872e6,
+    "splat_bwd": 26.755584e6 + 0.0,
 }
+NCU_TRAFFIC_SOURCE = "ncu --set full, dram read+write per launch, profiles/r01_l_inplace_v4_ncu_summary.md"
 STAGE_BYTES = {
     "splat_fwd": G_BYTES + 2 * 12 * N + 32 * N,          # zero grid + read pc + write tr_pc + 8 corner RMW
     "conv_xy_fwd": 2 * G_BYTES + G_BYTES // 32,          # read raw, write xy-smoothed, clip-mask bits
@@ -570,6 +571,16 @@ def run_ours(args, rank, local_rank, world):
         dom = max((k for k in stages if k in STAGE_BYTES), key=stages.get)
         achieved = STAGE_BYTES[dom] * B / (stages[dom] * 1e-3) / 1e9
         step_gbs = FULL_PATH_BYTES * B / ((ms_total / args.steps) * 1e-3) / 1e9 if world == 1 else None
+        busy = pipe.kernel_timeline(graph, flush)
+        roofline_busy = None
+        if busy:
+            # the same ratio with each kernel's duration taken INSIDE the timed step (globaltimer stamps of its own CTAs,
+            # first CTA past its grid dependency -> last exit; PDL chaining and graph replay intact)
+            per = {k: {"busy_us": busy[k], "achieved": STAGE_BYTES[k] * B / (busy[k] * 1e-6) / 1e9,
+                       "frac": STAGE_BYTES[k] * B / (busy[k] * 1e-6) / 1e9 / peak} for k in STAGE_BYTES if k in busy}
+            slow = max(per, key=lambda k: per[k]["busy_us"])
+            roofline_busy = {"bound": "hbm", "unit": "GB/s", "peak": peak, "dominant_kernel": slow,
+                             "achieved": per[slow]["achieved"], "frac": per[slow]["frac"], "per_kernel": per}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -590,13 +601,16 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_B32.get(dom) if (B == 32 and N == 8000 and V == 64) else None),
-                         "traffic_source": "ncu --set full, dram read+write per launch, profiles/r01_i_tcgen05_ncu_summary.md",
+                         "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "duration_source": "CUDA events recorded by the library around the stage on the launch stream "
+                                            "(serialises the kernels: includes the launch gap and the un-overlapped prologue)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": STAGE_BYTES[dom] * B},
             "roofline_step": {"algorithmic_bytes_per_projection": FULL_PATH_BYTES, "achieved": step_gbs,
                               "frac": (step_gbs / peak) if step_gbs else None, "unit": "GB/s"},
             "stages_ms": stages,
-            "kernel_busy_us": pipe.kernel_timeline(graph, flush),
+            "kernel_busy_us": busy,
+            "roofline_in_step": roofline_busy,
         }
         if not args.no_cpu_baseline and world == 1:
             threads = pick_threads()

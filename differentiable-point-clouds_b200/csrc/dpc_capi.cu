@@ -460,6 +460,13 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   // Round 8: a zeroing KERNEL again, now as the first half of a PDL pair -- it waits for everything older, lets the
   // splat start, and the splat stages + transforms + writes tr_pc while the grid is being zeroed (knob 10).
   if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO)) {
+#ifndef DPC_EMU
+    if (g_tune[10] == 2 && ((size_t)g * 4) % 16384 == 0) {
+      DPC_LAUNCH(dpc_zero_bulk_kernel, dim3(148 * 2), dim3(128), 0, stream, (unsigned char*)w.raw, (size_t)g * 4);
+      DPC_TRY(dpc_check_launch());
+      g_splat_early_next = 1;
+    } else
+#endif
     if (g_tune[10]) {
       const size_t n4 = (size_t)g / 4;
 #ifdef DPC_EMU

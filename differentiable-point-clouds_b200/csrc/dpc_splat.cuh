@@ -444,6 +444,30 @@ dpc_zero_kernel(float4* dst, size_t n4, float* tail, int ntail) {
   dpc_kt_mark(DPC_KT_ZERO, 3);
 }
 
+// Same role, zeros written by the TMA engine (bulk stores from a zeroed 16 KiB of shared memory) instead of by the
+// SMs' store path: experiment knob 10 = 2 (does the placement of the zero lines in L2 matter to the reductions?).
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(128)
+dpc_zero_bulk_kernel(unsigned char* dst, size_t bytes) {
+  __shared__ __align__(128) unsigned char z[16384];
+  dpc_kt_mark(DPC_KT_ZERO, 0);
+  dpc_grid_dep_wait();
+  dpc_grid_dep_trigger();
+  dpc_kt_mark(DPC_KT_ZERO, 1);
+  for (int i = threadIdx.x; i < 16384 / 16; i += blockDim.x) reinterpret_cast<float4*>(z)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  dpc_fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(z);
+    for (size_t off = (size_t)blockIdx.x * 16384; off < bytes; off += (size_t)gridDim.x * 16384)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(sa), "r"(16384u) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  dpc_kt_mark(DPC_KT_ZERO, 3);
+}
+#endif
+
 // Zeroes up to four small accumulation targets (pose / translation / focal / scale gradients) in ONE launch: every
 // stream operation costs ~2.5 us of dependency latency on B200, four cudaMemsetAsync of a few bytes each cost 10 us.
 struct DpcZero4Args { float* p[4]; int n[4]; };

@@ -139,7 +139,7 @@ def test_full_benchmark_shape_clustered_and_translation():
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0, trans=tr, host_sigma=True))
 
 
-@pytest.mark.parametrize("knob,value", [(2, 1), (10, 1), (11, 0), (13, 1), (14, 0), (15, 0)])
+@pytest.mark.parametrize("knob,value", [(2, 1), (10, 1), (10, 2), (11, 0), (13, 1), (14, 0), (15, 0)])
 def test_splat_variants_full_shape(knob, value):
     """The experiment knobs of the fused path give the same results as the defaults, spread and clustered clouds:
     10 = 1 zeroing kernel + forward transform ahead of the grid dependency (default: cudaMemsetAsync); 11 = 0 8-byte /
