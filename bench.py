@@ -125,7 +125,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -618,7 +618,7 @@ def run_ours(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": args.ref_batch * n / total, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d fwd+bwd steps of a B=%d batch of the same workload (oracle, torch-CPU)"
                                               % (n, args.ref_batch)}
-        print(json.dumps(line))
+        emit(line)
     D.barrier()
 
 
@@ -651,7 +651,7 @@ def run_train(args, rank, local_rank, world):
     ms = D.reduce_scalar(e0.elapsed_time(e1), "max", dev)
     views = cfg.batch_size * cfg.step_size
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "train step: object-views/sec (%s)" % name, "value": world * views * args.steps / (ms / 1000.0),
             "unit": "object-views/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -664,8 +664,33 @@ def run_train(args, rank, local_rank, world):
     D.barrier()
 
 
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with
+    printf when the box sets NCCL_DEBUG, whatever NCCL_DEBUG_FILE says), so file descriptor 1 points at stderr for the
+    whole run and is put back only for the JSON line (emit())."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line))
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(2, 1)
+
+
 def main():
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner must not share stdout with the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="projection", choices=["projection", "train_supervised", "train_unsupervised"])
     ap.add_argument("--objects-per-rank", type=int, default=0)
