@@ -25,6 +25,7 @@ static int g_tune[16] = {4, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1};   // [
 //      memset than behind a store kernel, profiles/r01_k_step_timeline.txt); [11] 1 = 16-byte red.v4 / gathers in the
 //      splats; [12] per-kernel timeline (dpc_kt); [13] 1 = keep the zeroing launch + dL/dscale atomics in the fused
 //      backward (0 = folded partials, no launch); [14] 1 = the backward splat transforms ahead of its grid dependency;
+//      [4] 1 = the splat backward runs co-resident with the x/y pass of the backward (per-sample counters);
 //      [15] 1 = the fused path smooths x/y IN PLACE and runs the backward in the same grid (two 32 MiB grids per step
 //      instead of three)
 // measured after the 16-byte gathers (profiles/r01_m_*): forward 4 / 2 / 1 points per thread = 10.2 / 10.7 / 13.9 us,
@@ -186,7 +187,8 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
                             int rgb_stop_grad, int B, int N, int Vz, int V,
                             const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
                             float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
-                            const float* d_scale_part, int n_part, float* d_scale_out, void* stream) {
+                            const float* d_scale_part, int n_part, float* d_scale_out, void* stream,
+                            const unsigned* sample_cnt = nullptr, int cnt_target = 0) {
   if (!pc) return DPC_ERR_NULL;
   if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
   if (pose_kind < DPC_POSE_NONE || pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
@@ -202,11 +204,26 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.early = g_tune[14] ? 1 : 0;
   a.gather4 = g_tune[11] ? 1 : 0;
   a.d_scale_part = d_scale_part; a.n_part = n_part; a.d_scale_out = d_scale_out;
+  a.sample_cnt = sample_cnt; a.cnt_target = cnt_target;
+#ifndef DPC_EMU
+  if (sample_cnt) {
+    // co-resident with the x/y pipeline (416 threads x 128 registers, 197 KB): 128-thread CTAs at one point per thread
+    // (64 registers) fit beside it; same shared-memory carve-out as the pipeline so the two can share an SM
+    static bool carve_set = false;
+    if (!carve_set) {
+      DPC_CUDA(cudaFuncSetAttribute(dpc_splat_bwd_kernel<1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve_set = true;
+    }
+    dim3 grid128((N + 127) / 128, B);
+    DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128>), grid128, dim3(128), 0, stream, a);
+    return dpc_check_launch();
+  }
+#endif
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
-  if (ppt == 4) { DPC_LAUNCH(dpc_splat_bwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
-  else if (ppt == 2) { DPC_LAUNCH(dpc_splat_bwd_kernel<2>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
-  else { DPC_LAUNCH(dpc_splat_bwd_kernel<1>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  if (ppt == 4) { DPC_LAUNCH((dpc_splat_bwd_kernel<4, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  else if (ppt == 2) { DPC_LAUNCH((dpc_splat_bwd_kernel<2, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  else { DPC_LAUNCH((dpc_splat_bwd_kernel<1, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
   return dpc_check_launch();
 }
 
@@ -389,7 +406,7 @@ int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
 // ------------------------------------------------------------------------------------ fused path
 static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-struct DpcScratch { float* raw; float* tmp; float* part; int64_t total; };
+struct DpcScratch { float* raw; float* tmp; float* part; unsigned* cnt; int64_t total; };
 struct DpcSaved { uint32_t* mask1; uint32_t* mask2; int64_t total; };
 
 static DpcScratch scratch_layout(const dpc_project_params* p, void* base) {
@@ -399,7 +416,8 @@ static DpcScratch scratch_layout(const dpc_project_params* p, void* base) {
   w.raw = (float*)c;
   w.tmp = (float*)(c + align256(g * 4));
   w.part = (float*)(c + 2 * align256(g * 4));      // dL/dscale partials of the depth-pass backward: [B, 32 tiles x 8 warps]
-  w.total = 2 * align256(g * 4) + align256((int64_t)p->B * 256 * 4);
+  w.cnt = (unsigned*)(c + 2 * align256(g * 4) + align256((int64_t)p->B * 256 * 4));   // per-sample completion counters (knob 4)
+  w.total = 2 * align256(g * 4) + align256((int64_t)p->B * 256 * 4) + align256((int64_t)p->B * 4);
   return w;
 }
 
@@ -537,8 +555,11 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   fold_scale = g_tune[13] == 0 && any_grid_grad && scale && d_scale && g_proj && !g_voxels && !g_probs && !g_depth &&
                p->mode == DPC_PROJ_DRC && dpc_tc_level() == 2 && dpc_tc_conv_z_supported(p->V, p->Vz, Kz, false);
 #endif
+  // knob 4: the splat backward runs co-resident with the x/y pass and starts on a sample as soon as that pass has
+  // stored it (per-sample counters, zeroed by the depth pass like the other targets) instead of after the whole pass
+  bool coresident = fold_scale && g_tune[4] && p->N >= 128;
   if (fold_scale) {
-    z.p[3] = nullptr;
+    z.p[3] = coresident ? (float*)w.cnt : nullptr; z.n[3] = p->B;     // all-zero bits either way
   } else if (d_pose || d_trans || d_focal || d_scale) {
     DPC_LAUNCH(dpc_zero4_kernel, dim3(1), dim3(256), 0, stream, z);
     DPC_TRY(dpc_check_launch());
@@ -557,14 +578,21 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                               g_proj, g_voxels, g_probs, g_depth, G, d_scale, stream, hz,
                               fold_scale ? w.part : nullptr, fold_scale ? &z : nullptr));
     stage_mark(5, stream);
+#ifndef DPC_EMU
+    dpc_tcp_xy_cnt_next = coresident ? w.cnt : nullptr;
+#endif
     DPC_TRY(launch_conv_xy(G, G, tx, K, K - 1 - (K - 1) / 2, tx, K, K - 1 - (K - 1) / 2,
                            p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, sv.mask1, /*rev=*/1, /*zero_in=*/0, stream, hxy, hxy));
+#ifndef DPC_EMU
+    if (dpc_tcp_xy_cnt_next) { dpc_tcp_xy_cnt_next = nullptr; coresident = false; }   // not the pipeline kernel: nobody signals
+#endif
     d_raw = G;
   }
   stage_mark(6, stream);
   DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
                            p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr,
-                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream));
+                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream,
+                           coresident ? w.cnt : nullptr, 256));
   stage_mark(7, stream);
   return DPC_OK;
 }

@@ -393,7 +393,10 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
 template <bool CLIP, bool MOUT, bool MIN, bool PDRAIN>
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
 dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_constant__ CUtensorMap xymap, int K, int pl, int ntiles,
-                       const __grid_constant__ DpcTcpTaps ht) {
+                       const __grid_constant__ DpcTcpTaps ht, int ns, unsigned* sample_cnt) {
+  // ns: staging slots in use (at most 4; 3 leaves shared memory for a co-resident splat CTA).  sample_cnt: when
+  // not NULL, every consumer warp adds 1 to sample_cnt[tile / 32] once its part of a tile is stored and visible, so a
+  // dependent kernel can start on a sample (256 arrivals) while this one is still working on later samples.
   constexpr int V = 64;
   constexpr int kt_id = MIN ? DPC_KT_XY_B : DPC_KT_XY_F;
   DPC_TCP_SETUP(a.taps_x, K, pl, a.rev);
@@ -461,7 +464,7 @@ dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_c
       dpc_tc_wait_st();
       dpc_tcp_warp_arrive(&B.opfull[s]);
       if (PDRAIN && k >= 1) pdrain(i - 2, tile - 2 * step);    // its done2 was waited for above
-      if (++slot == DPC_TCP_NS) { slot = 0; sph ^= 1; }
+      if (++slot == ns) { slot = 0; sph ^= 1; }
     }
     if (PDRAIN) {          // the last two tiles of this CTA
       for (int j = (i >= 2 ? i - 2 : 0); j < i; ++j) {
@@ -495,6 +498,11 @@ dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_c
           if (!((w >> lane) & 1u)) v = 0.0f;
         }
         dst[q * V] = v;
+      }
+      if (sample_cnt) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(sample_cnt + (tile >> 5), 1u);
       }
     };
     int i = 0, prev_tile = -1;
@@ -538,16 +546,16 @@ dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_c
         dpc_tma_load_2d(dst, &xymap, 0, tile * 128, &B.sfull[slot]);
         dpc_tma_load_2d(dst + 16384, &xymap, 32, tile * 128, &B.sfull[slot]);
       };
-      for (int j = 0; j < DPC_TCP_NS; ++j) { const int t = (int)blockIdx.x + j * step; if (t < ntiles) fill(j, t); }
+      for (int j = 0; j < ns; ++j) { const int t = (int)blockIdx.x + j * step; if (t < ntiles) fill(j, t); }
       int slot = 0, sph = 0;
       auto gemm1 = [&](int j, int tile) {      // D1[s] drained: implied by done2[s] of tile j-2, which the producers waited for
         const int s = j & 1, k = j >> 1;
         dpc_mbar_wait(&B.opfull[s], k & 1);
         dpc_tc_fence_after();
         dpc_tc_issue_ts(tmem + DPC_TCP_AHI(s), tmem + DPC_TCP_ALO(s), sbase + DPC_TCP_T_OFF, tmem + DPC_TCP_D1(s), &B.done[s]);
-        const int nt = tile + DPC_TCP_NS * step;
+        const int nt = tile + ns * step;
         if (nt < ntiles) { dpc_mbar_wait(&B.sfree[slot], sph); fill(slot, nt); }
-        if (++slot == DPC_TCP_NS) { slot = 0; sph ^= 1; }
+        if (++slot == ns) { slot = 0; sph ^= 1; }
       };
       auto gemm2 = [&](int j) {                // D2[s] drained: every consumer stored tile j-2 before it published tile j
         const int s = j & 1, k = j >> 1;

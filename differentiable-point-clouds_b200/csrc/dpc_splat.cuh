@@ -226,20 +226,38 @@ struct DpcSplatBwdArgs {
   // per-warp partial sums of dL/dscale left by the depth-pass backward ([B, n_part]); CTA (0, b) folds them into
   // d_scale_out[b], so the fused backward needs neither atomics on d_scale nor a launch that zeroes it
   const float* d_scale_part; int n_part; float* d_scale_out;
+  const unsigned* sample_cnt; int cnt_target;   // co-resident mode (knob 4): per-sample completion counters of the x/y pass
 };
 
-template <int DPC_SPLAT_PPT>
+// gathers of dL/d(raw): through the read-only path normally; past L1 (ld.global.cg) when the producer kernel is still
+// running on other samples (co-resident mode)
+DPC_DEV float dpc_ld_gather(const float* p, bool coherent) {
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(DPC_SPLAT_THREADS)
+  return coherent ? __ldcg(p) : __ldg(p);
+#else
+  (void)coherent; return *p;
+#endif
+}
+DPC_DEV float4 dpc_ld_gather4(const float4* p, bool coherent) {
+#ifndef DPC_EMU
+  return coherent ? __ldcg(p) : __ldg(p);
+#else
+  (void)coherent; return *p;
+#endif
+}
+
+template <int DPC_SPLAT_PPT, int NT>
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(NT)
 #else
 static void
 #endif
 dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
-  constexpr int DPC_SPLAT_TILE = DPC_SPLAT_THREADS * DPC_SPLAT_PPT;
+  constexpr int DPC_SPLAT_TILE = NT * DPC_SPLAT_PPT;
   __shared__ __align__(128) float tile[DPC_SPLAT_TILE * 3];
   __shared__ __align__(8) uint64_t bar;
   __shared__ DpcPose pose_sm;
-  __shared__ float red[DPC_SPLAT_THREADS / 32][12];
+  __shared__ float red[NT / 32][12];
   const int b = blockIdx.y;
   const int p_first = blockIdx.x * DPC_SPLAT_TILE;
   const int n = min(DPC_SPLAT_TILE, a.N - p_first);
@@ -271,7 +289,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   // gathers of all four points before anything consumes them
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
-    const int i = j * DPC_SPLAT_THREADS + tid;
+    const int i = j * NT + tid;
     p0[j] = p1[j] = p2[j] = 0.0f;
     float z = 0.f, y = 0.f, x = 0.f;
     cam[j].xs = cam[j].ys = 0.f; cam[j].zs = 1.f;
@@ -283,9 +301,23 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     cell[j].valid = cell[j].valid && (i < n);
   }
   dpc_ph_mark(1, 2);
-  if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
+  if (a.sample_cnt) {
+    // co-resident with the x/y pass of the backward (knob 4): no grid dependency -- wait until that pass has stored
+    // this sample's 32 tiles (8 consumer warps each), then read dL/d(raw) past L1 (ld.global.cg)
+    if (tid == 0) {
+#ifndef DPC_EMU
+      unsigned seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sample_cnt + b) : "memory");
+        if (seen < (unsigned)a.cnt_target) __nanosleep(200);
+      } while (seen < (unsigned)a.cnt_target);
+#endif
+    }
+    __syncthreads();
+    dpc_kt_mark(DPC_KT_SPLAT_B, 1);
+  } else if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
   dpc_ph_mark(1, 3);
-  if (a.d_scale_part && blockIdx.x == 0 && warp == DPC_SPLAT_THREADS / 32 - 1) {
+  if (a.d_scale_part && blockIdx.x == 0 && warp == NT / 32 - 1) {
     float v = 0.0f;
     for (int q = lane; q < a.n_part; q += 32) v += a.d_scale_part[(size_t)b * a.n_part + q];
     v = dpc_warp_sum(v);
@@ -294,6 +326,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   // An uncoalesced warp load costs one L1 wavefront per lane, and the gathers are what this kernel waits for: the x
   // pair of a row comes in ONE 16-byte load whenever it does not straddle a 4-voxel group (3 of 4 points): 5
   // wavefronts per point on average instead of 8.
+  const bool coherent = a.sample_cnt != nullptr;
   const bool quad = a.gather4 && dv && ((V & 3) == 0) && ((((uintptr_t)dv) & 15u) == 0);
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
@@ -306,7 +339,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
         for (int jj = 0; jj < 2; ++jj) {
           const bool inb = cell[j].valid && (cell[j].iz + k < Vz) && (cell[j].iy + jj < V);
           float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (inb) q4 = __ldg(reinterpret_cast<const float4*>(dv + base + (k * V + jj) * V - o4));
+          if (inb) q4 = dpc_ld_gather4(reinterpret_cast<const float4*>(dv + base + (k * V + jj) * V - o4), coherent);
           dw[j][k * 4 + jj * 2 + 0] = o4 == 0 ? q4.x : (o4 == 1 ? q4.y : q4.z);
           dw[j][k * 4 + jj * 2 + 1] = o4 == 0 ? q4.y : (o4 == 1 ? q4.z : q4.w);
         }
@@ -318,7 +351,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
 #pragma unroll
           for (int ii = 0; ii < 2; ++ii) {
             const bool inb = cell[j].valid && dv && (cell[j].iz + k < Vz) && (cell[j].iy + jj < V) && (cell[j].ix + ii < V);
-            dw[j][k * 4 + jj * 2 + ii] = inb ? __ldg(dv + base + (k * V + jj) * V + ii) : 0.0f;
+            dw[j][k * 4 + jj * 2 + ii] = inb ? dpc_ld_gather(dv + base + (k * V + jj) * V + ii, coherent) : 0.0f;
           }
     }
   }
@@ -328,7 +361,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   // pass 2: weights' derivative, chain rule through the camera
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
-    const int i = j * DPC_SPLAT_THREADS + tid;
+    const int i = j * NT + tid;
     const bool live = i < n;
     const DpcCell c = cell[j];
     const size_t pi = (size_t)b * a.N + p_first + i;
@@ -395,7 +428,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   __syncthreads();
   if (tid < 12) {
     float v = 0.f;
-    for (int wgi = 0; wgi < DPC_SPLAT_THREADS / 32; ++wgi) v += red[wgi][tid];
+    for (int wgi = 0; wgi < NT / 32; ++wgi) v += red[wgi][tid];
     red[0][tid] = v;
   }
   __syncthreads();

@@ -45,7 +45,7 @@ def test_argument_validation_needs_no_gpu(lib):
     import ctypes
     assert lib.dpc_project_fast_scratch_bytes(ctypes.byref(p)) == -1
     p.Vz = 64
-    assert lib.dpc_project_fast_scratch_bytes(ctypes.byref(p)) == 2 * 64 ** 3 * 4 + 1024   # two grids + dL/dscale partials
+    assert lib.dpc_project_fast_scratch_bytes(ctypes.byref(p)) == 2 * 64 ** 3 * 4 + 1024 + 256   # two grids + dL/dscale partials + counters
     assert lib.dpc_project_fast_saved_bytes(ctypes.byref(p)) >= 2 * 64 ** 3 // 8
 
 
