@@ -35,17 +35,17 @@ G_BYTES = V * V * V * 4
 FULL_PATH_BYTES = 6 * G_BYTES + 4 * 12 * N + 64 * N + 2 * 4 * V * V
 # per-launch algorithmic bytes of each stage, per projection (DESIGN.md "kernels and rooflines")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B=32, from the committed `ncu --set full` capture of this
-# very command (profiles/r01_l_inplace_v4_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
+# very command (profiles/r01_p_final_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
 # previous kernel left in L2 are re-read from HBM, and the 32 MiB of output stays in L2 until a later kernel evicts it)
 NCU_TRAFFIC_B32 = {
-    "splat_fwd": 22.242048e6 + 0.038656e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
-    "conv_xy_fwd": 33.592832e6 + 0.006400e6,
-    "conv_z_fwd": 33.590272e6 + 0.717312e6,
-    "conv_z_bwd": 35.164416e6 + 0.601600e6,
-    "conv_xy_bwd": 34.638592e6 + 0.015872e6,
-    "splat_bwd": 26.755584e6 + 0.0,
+    "splat_fwd": 22.190848e6 + 0.075264e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
+    "conv_xy_fwd": 33.596416e6 + 0.002560e6,
+    "conv_z_fwd": 33.591808e6 + 1.078016e6,
+    "conv_z_bwd": 35.166464e6 + 0.500224e6,
+    "conv_xy_bwd": 34.642432e6 + 0.003840e6,
+    "splat_bwd": 26.721536e6 + 0.0,
 }
-NCU_TRAFFIC_SOURCE = "ncu --set full, dram read+write per launch, profiles/r01_l_inplace_v4_ncu_summary.md"
+NCU_TRAFFIC_SOURCE = "ncu --set full, dram read+write per launch, profiles/r01_p_final_ncu_summary.md"
 STAGE_BYTES = {
     "splat_fwd": G_BYTES + 2 * 12 * N + 32 * N,          # zero grid + read pc + write tr_pc + 8 corner RMW
     "conv_xy_fwd": 2 * G_BYTES + G_BYTES // 32,          # read raw, write xy-smoothed, clip-mask bits
@@ -202,12 +202,13 @@ class L2Flush:
 class Pipeline:
     """Device buffers + C-ABI calls for one rank (B samples)."""
 
-    def __init__(self, dev, seed_shift):
+    def __init__(self, dev, seed_shift, clustered=False, sigma=None, max_projection=False):
         from dpc_b200 import _capi
         from dpc_b200.util import gauss_kernel as gk
         self.capi, self.L, self.dev = _capi, _capi.lib(), dev
         self.cfg = bench_cfg()
-        host = make_inputs(B, seed_shift)
+        sigma = SIGMA if sigma is None else sigma
+        host = make_inputs(B, seed_shift, clustered)
         self.host = [t.pin_memory() for t in host]
         self.pc, self.q, self.sc, self.gt = [t.to(dev) for t in host]
         self.sc1 = self.sc.reshape(-1).contiguous()
@@ -215,9 +216,10 @@ class Pipeline:
         self.neg_gt_over_b = (-self.gt3 / B).contiguous()
         # sigma is a host value (the reference's schedule is a function of the step count, model_pc.py:35-40):
         # the kernel object holds the taps on the host and on the device
-        self.kernel = gk.smoothing_kernel(self.cfg, SIGMA)
+        self.kernel = gk.smoothing_kernel(self.cfg, sigma)
         self.taps = self.kernel.device_taps(dev)[0]
-        self.p = _capi.ProjectParams(B=B, N=N, Vz=V, V=V, pose_kind=_capi.POSE_QUAT, mode=_capi.PROJ_DRC, K=K, Kz=K,
+        self.p = _capi.ProjectParams(B=B, N=N, Vz=V, V=V, pose_kind=_capi.POSE_QUAT,
+                                     mode=_capi.PROJ_MAX if max_projection else _capi.PROJ_DRC, K=K, Kz=K,
                                      focal_const=float(self.cfg.focal_length), cam_dist=float(self.cfg.camera_distance),
                                      clip_eps=float(self.cfg.drc_logsum_clip_val), max_depth=float(self.cfg.max_depth))
         self.p.flags = 0
@@ -465,6 +467,40 @@ def e2e_graphed(pipe, steps, nbuf=4):
     return dt, loss
 
 
+def variant_rows(dev, steps, flush):
+    """SURVEY 8(d)'s other rows of the same workload, timed like the headline (graph replay, in-graph events, L2
+    evicted between steps): init-clustered cloud (decoder init, stddev 0.025: every point of a sample in ~27 voxels,
+    worst-case contention), the end of the sigma schedule (0.2), max projection instead of DRC; plus the fraction of
+    points that land inside the cube."""
+    rows = {}
+    for name, kw in (("spread_sigma3_drc", {}), ("clustered_init", {"clustered": True}), ("sigma_0.2", {"sigma": 0.2}),
+                     ("max_projection", {"max_projection": True})):
+        pipe = Pipeline(dev, 0, **kw)
+        for _ in range(3):
+            pipe.step()
+        torch.cuda.synchronize()
+        tr = pipe.tr_pc
+        valid = float(((tr >= -0.5) & (tr <= 0.5)).all(dim=-1).float().mean())
+        e0 = torch.cuda.Event(enable_timing=True, external=True)
+        e1 = torch.cuda.Event(enable_timing=True, external=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            e0.record()
+            pipe.step()
+            e1.record()
+        total = 0.0
+        for it in range(steps + 2):
+            if flush is not None:
+                flush.fill_(it & 0xff)
+            g.replay()
+            e1.synchronize()
+            if it >= 2:
+                total += e0.elapsed_time(e1)
+        rows[name] = {"ms_per_step": total / steps, "projections_per_s": B * steps / (total / 1000.0), "valid_point_fraction": valid}
+        del g, pipe
+    return rows
+
+
 def run_ours(args, rank, local_rank, world):
     from dpc_b200 import distributed as D
     if not torch.cuda.is_available():
@@ -643,6 +679,11 @@ def run_ours(args, rank, local_rank, world):
             "kernel_busy_us": busy,
             "roofline_in_step": roofline_busy,
         }
+        if world == 1 and g_ev0 is not None:
+            try:
+                line["variants"] = variant_rows(dev, min(args.steps, 20), flush)
+            except Exception as exc:
+                print("variant rows failed: %r" % (exc,), file=sys.stderr)
         if not args.no_cpu_baseline and world == 1:
             threads = pick_threads()
             total, n = time_oracle(args.ref_batch, 3, 1, threads)
