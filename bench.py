@@ -232,6 +232,9 @@ class Pipeline:
         self.saved = torch.empty(self.saved_bytes, dtype=torch.uint8, device=dev)
         self.tr_pc, self.vox, self.proj, self.g_proj = f(B, N, 3), f(B, V, V, V), f(B, V, V), f(B, V, V)
         self.d_pc, self.d_q, self.d_sc = f(B, N, 3), f(B, 4), f(B)
+        self.loss = f(1)
+        self.loss_ws_bytes = int(self.L.dpc_proj_l2_loss_workspace_bytes())
+        self.loss_ws = torch.zeros((self.loss_ws_bytes + 3) // 4, dtype=torch.int32, device=dev)
 
     @property
     def stream(self):
@@ -243,15 +246,17 @@ class Pipeline:
                                  self.taps.data_ptr(), self.taps.data_ptr(), self.tr_pc.data_ptr(), self.vox.data_ptr(),
                                  self.proj.data_ptr(), None, None, self.scratch.data_ptr(), self.scratch_bytes,
                                  self.saved.data_ptr(), self.saved_bytes, self.stream))
-        # dL/dproj of sum((gt-proj)^2)/2/B  (model_pc.py:414-415) -- loss side, plain torch
-        torch.add(self.neg_gt_over_b, self.proj, alpha=1.0 / B, out=self.g_proj)      # (proj - gt) / B, one launch
+        # loss = sum((gt-proj)^2)/2/B and dL/dproj = (proj - gt)/B  (model_pc.py:414-415): one launch of the library's
+        # loss kernel (PDL-aware, so the first backward kernel starts up underneath it)
+        c(L.dpc_proj_l2_loss(self.proj.data_ptr(), self.gt3.data_ptr(), B * V * V, 1.0 / B, self.loss.data_ptr(),
+                             self.g_proj.data_ptr(), self.loss_ws.data_ptr(), self.loss_ws_bytes, self.stream))
         c(L.dpc_project_fast_bwd(ctypes.byref(p), self.pc.data_ptr(), self.q.data_ptr(), None, None, self.sc1.data_ptr(),
                                  self.taps.data_ptr(), self.taps.data_ptr(), self.vox.data_ptr(), self.g_proj.data_ptr(),
                                  None, None, None, None, self.d_pc.data_ptr(), self.d_q.data_ptr(), None, None,
                                  self.d_sc.data_ptr(), self.scratch.data_ptr(), self.scratch_bytes,
                                  self.saved.data_ptr(), self.saved_bytes, self.stream))
 
-    LAUNCHES_PER_STEP = 6  # splat_fwd, conv_xy, conv_z_fwd | conv_z_bwd, conv_xy, splat_bwd (the loss op between them is torch's)
+    LAUNCHES_PER_STEP = 7  # splat_fwd, conv_xy, conv_z_fwd | proj_l2_loss | conv_z_bwd, conv_xy, splat_bwd (+ the driver's memset node)
 
     KT_NAMES = ("zero", "splat_fwd", "conv_xy_fwd", "conv_z_fwd", "zero4", "conv_z_bwd", "conv_xy_bwd", "splat_bwd")
 
@@ -412,6 +417,7 @@ def e2e_graphed(pipe, steps, nbuf=4):
     bounded by ~0.5 ms of Python/autograd time per step, separate copy/compute streams with per-step event bookkeeping
     by ~0.15 ms of host time (profiles/r01_k_pcie_probe.txt: H2D 3.6 MB 0.11 ms, D2H 0.07 ms, bookkeeping 0.03 ms)."""
     from dpc_b200.util import point_cloud as pcm
+    from dpc_b200.util.losses import proj_l2_loss
     dev = pipe.dev
     if not hasattr(pipe, "h_in"):
         pipe._e2e_setup()
@@ -428,7 +434,7 @@ def e2e_graphed(pipe, steps, nbuf=4):
         pc, q, sc, gt = [p.reshape(sh) for p, sh in zip(parts, pipe.in_shapes)]
         pc, q, sc = pc.detach().requires_grad_(True), q.detach().requires_grad_(True), sc.detach().requires_grad_(True)
         out = pcm.pointcloud_project_fast(pipe.cfg, pc, q, None, None, pipe.kernel, sc)
-        l = torch.nn.functional.mse_loss(out["proj"], gt, reduction="sum") / (2 * B)      # = sum((gt - proj)^2) / 2 / B
+        l = proj_l2_loss(gt, out["proj"], B)              # sum((gt - proj)^2) / 2 / B, model_pc.py:414-415
         gpc, gq, gsc = torch.autograd.grad(l, (pc, q, sc))
         for h, t in zip(h_parts[k], (l.detach(), out["proj"].detach(), gpc, gq, gsc)):    # D2H, 3.6 MB
             h.copy_(t.reshape(-1), non_blocking=True)

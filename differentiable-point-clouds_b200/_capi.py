@@ -52,6 +52,8 @@ _SIGNATURES = {
     "dpc_debug_ktrace_read": (c_i, [c_p]),
     "dpc_debug_phase_read": (c_i, [c_p]),
     "dpc_debug_mma_bench": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "dpc_proj_l2_loss_workspace_bytes": (c_i64, []),
+    "dpc_proj_l2_loss": (c_i, [c_p, c_p, c_i64, c_f, c_p, c_p, c_p, c_i64, c_p]),
     "dpc_point_cloud_distance_workspace_bytes": (c_i64, [c_i, c_i, c_i]),
     "dpc_point_cloud_distance_f32": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64, c_p]),
     "dpc_point_cloud_distance_f64": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64, c_p]),

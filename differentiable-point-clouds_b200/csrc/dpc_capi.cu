@@ -7,6 +7,7 @@
 #include "dpc_smooth_fast.cuh"
 #include "dpc_smooth_tc.cuh"
 #include "dpc_chamfer.cuh"
+#include "dpc_loss.cuh"
 
 static thread_local int g_last_cuda_error = 0;
 
@@ -640,6 +641,23 @@ static int nn_launch(const T* vs, int ns, const T* vt, int nt, T* proj, T* min_d
 }
 
 extern "C" {
+
+int64_t dpc_proj_l2_loss_workspace_bytes(void) { return (int64_t)(DPC_LOSS_MAX_CTAS + 1) * 4; }
+
+int dpc_proj_l2_loss(const float* pred, const float* gt, int64_t n, float inv_count, float* loss, float* g_pred,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!pred || !gt || !loss || !workspace) return DPC_ERR_NULL;
+  if (n < 1) return DPC_ERR_SHAPE;
+  if (workspace_bytes < dpc_proj_l2_loss_workspace_bytes() || (((uintptr_t)workspace) & 3) != 0) return DPC_ERR_WORKSPACE;
+  int64_t ctas = (n / 4 + DPC_LOSS_THREADS - 1) / DPC_LOSS_THREADS;      // one float4 per thread where that is enough
+  if (ctas < 1) ctas = 1;
+  if (ctas > 148 * 2) ctas = 148 * 2;
+  float* partial = (float*)workspace;
+  unsigned* counter = (unsigned*)(partial + DPC_LOSS_MAX_CTAS);
+  DPC_LAUNCH(dpc_proj_l2_loss_kernel, dim3((unsigned)ctas), dim3(DPC_LOSS_THREADS), 0, stream, pred, gt, (long long)n, inv_count,
+             loss, g_pred, partial, counter);
+  return dpc_check_launch();
+}
 
 int64_t dpc_point_cloud_distance_workspace_bytes(int ns, int nt, int elem_bytes) {
   if (ns < 1 || nt < 1 || (elem_bytes != 4 && elem_bytes != 8)) return -1;

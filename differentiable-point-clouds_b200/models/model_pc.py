@@ -164,7 +164,11 @@ class ModelPointCloud(nn.Module):
             if cfg.pose_predictor_student:
                 total = total + self.add_student_loss(outputs, winner)
         else:
-            proj_loss = ((gt - pred) ** 2).sum() / 2 / pred.shape[0]
+            if pred.is_cuda:      # model_pc.py:414-415 as one kernel (value + gradient), util/losses.py
+                from ..util.losses import proj_l2_loss
+                proj_loss = proj_l2_loss(gt.contiguous(), pred, pred.shape[0])
+            else:                 # CPU tensors only occur in the CPU test-suite (emulated kernels)
+                proj_loss = ((gt - pred) ** 2).sum() / 2 / pred.shape[0]
         return (total + proj_loss) * cfg.proj_weight
 
     def get_loss(self, inputs, outputs):

@@ -199,6 +199,16 @@ int dpc_gather_points(const float* in, const int64_t* sel, int B, int N, int n_k
 int dpc_gather_points_bwd(const float* g_out, const int64_t* sel, int B, int N, int n_keep, int C,
                           float* g_in /* zeroed by callee */, void* stream);
 
+/* ---- f-1 (loss row): the silhouette loss of the training step and its gradient in one pass.  Replaces
+ * `tf.nn.l2_loss(gt - pred) / num_samples` (models/model_pc.py:414-415) and its autodiff:
+ *   *loss = sum((gt - pred)^2) / 2 * inv_count,   g_pred[i] = (pred[i] - gt[i]) * inv_count   (g_pred may be NULL).
+ * pred / gt / g_pred: n floats.  workspace: dpc_proj_l2_loss_workspace_bytes() bytes of device memory, 4-byte aligned,
+ * ZEROED ONCE by the caller before its first use (per-CTA partial sums + a self-resetting completion counter; calls on
+ * one stream may share it).  Deterministic (fixed summation order). */
+int64_t dpc_proj_l2_loss_workspace_bytes(void);
+int dpc_proj_l2_loss(const float* pred, const float* gt, int64_t n, float inv_count, float* loss, float* g_pred,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- f-4: nearest-neighbour projection of the chamfer evaluation.  Replaces point_cloud_distance
  * (util/point_cloud_distance.py:26-39; driver run/eval_chamfer.py:18-34): for every source point vs[i] the closest
  * target: min_dist[i] = min_j sqrt(sum((vt[j] - vs[i])^2)), idx[i] = the FIRST j attaining it (tf.argmin over the
