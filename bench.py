@@ -246,10 +246,11 @@ class Pipeline:
                                  self.taps.data_ptr(), self.taps.data_ptr(), self.tr_pc.data_ptr(), self.vox.data_ptr(),
                                  self.proj.data_ptr(), None, None, self.scratch.data_ptr(), self.scratch_bytes,
                                  self.saved.data_ptr(), self.saved_bytes, self.stream))
-        # loss = sum((gt-proj)^2)/2/B and dL/dproj = (proj - gt)/B  (model_pc.py:414-415): one launch of the library's
-        # loss kernel (PDL-aware, so the first backward kernel starts up underneath it)
-        c(L.dpc_proj_l2_loss(self.proj.data_ptr(), self.gt3.data_ptr(), B * V * V, 1.0 / B, self.loss.data_ptr(),
-                             self.g_proj.data_ptr(), self.loss_ws.data_ptr(), self.loss_ws_bytes, self.stream))
+        # dL/dproj = (proj - gt)/B of loss = sum((gt-proj)^2)/2/B  (model_pc.py:414-415): one launch of the library's loss
+        # kernel in its gradient-only form (the device-only step never read the loss VALUE; the e2e step, which returns
+        # it to the host, runs the full form through util/losses.proj_l2_loss)
+        c(L.dpc_proj_l2_loss(self.proj.data_ptr(), self.gt3.data_ptr(), B * V * V, 1.0 / B, None,
+                             self.g_proj.data_ptr(), None, 0, self.stream))
         c(L.dpc_project_fast_bwd(ctypes.byref(p), self.pc.data_ptr(), self.q.data_ptr(), None, None, self.sc1.data_ptr(),
                                  self.taps.data_ptr(), self.taps.data_ptr(), self.vox.data_ptr(), self.g_proj.data_ptr(),
                                  None, None, None, None, self.d_pc.data_ptr(), self.d_q.data_ptr(), None, None,

@@ -646,9 +646,10 @@ int64_t dpc_proj_l2_loss_workspace_bytes(void) { return (int64_t)(DPC_LOSS_MAX_C
 
 int dpc_proj_l2_loss(const float* pred, const float* gt, int64_t n, float inv_count, float* loss, float* g_pred,
                      void* workspace, int64_t workspace_bytes, void* stream) {
-  if (!pred || !gt || !loss || !workspace) return DPC_ERR_NULL;
+  if (!pred || !gt || (!loss && !g_pred)) return DPC_ERR_NULL;
+  if (loss && !workspace) return DPC_ERR_NULL;
   if (n < 1) return DPC_ERR_SHAPE;
-  if (workspace_bytes < dpc_proj_l2_loss_workspace_bytes() || (((uintptr_t)workspace) & 3) != 0) return DPC_ERR_WORKSPACE;
+  if (loss && (workspace_bytes < dpc_proj_l2_loss_workspace_bytes() || (((uintptr_t)workspace) & 3) != 0)) return DPC_ERR_WORKSPACE;
   int64_t ctas = (n / 4 + DPC_LOSS_THREADS - 1) / DPC_LOSS_THREADS;      // one float4 per thread where that is enough
   if (ctas < 1) ctas = 1;
   if (ctas > 148 * 2) ctas = 148 * 2;

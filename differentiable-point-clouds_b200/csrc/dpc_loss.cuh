@@ -41,6 +41,7 @@ dpc_proj_l2_loss_kernel(const float* pred, const float* gt, long long n, float i
       if (g_pred) g_pred[i] = -d * inv_count;
     }
   }
+  if (!loss) return;        // gradient only (uniform): no reduction, no fence, no counter
   acc = dpc_warp_sum(acc);
   if (lane == 0) red[warp] = acc;
   __syncthreads();

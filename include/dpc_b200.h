@@ -202,7 +202,7 @@ int dpc_gather_points_bwd(const float* g_out, const int64_t* sel, int B, int N, 
 /* ---- f-1 (loss row): the silhouette loss of the training step and its gradient in one pass.  Replaces
  * `tf.nn.l2_loss(gt - pred) / num_samples` (models/model_pc.py:414-415) and its autodiff:
  *   *loss = sum((gt - pred)^2) / 2 * inv_count,   g_pred[i] = (pred[i] - gt[i]) * inv_count   (g_pred may be NULL).
- * pred / gt / g_pred: n floats.  workspace: dpc_proj_l2_loss_workspace_bytes() bytes of device memory, 4-byte aligned,
+ * pred / gt / g_pred: n floats.  loss may be NULL as well (gradient only: no reduction, workspace unused).  workspace: dpc_proj_l2_loss_workspace_bytes() bytes of device memory, 4-byte aligned,
  * ZEROED ONCE by the caller before its first use (per-CTA partial sums + a self-resetting completion counter; calls on
  * one stream may share it).  Deterministic (fixed summation order). */
 int64_t dpc_proj_l2_loss_workspace_bytes(void);

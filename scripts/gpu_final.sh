@@ -18,7 +18,7 @@ echo "== ncu launch list" | tee -a $O/status.txt
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_bench.log 2>&1; echo "ncu-list rc=$?" | tee -a $O/status.txt
 echo "== ncu full" | tee -a $O/status.txt
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:dpc_ -s 12 -c 6 -o $O/prof_full \
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:dpc_ -s 14 -c 7 -o $O/prof_full \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_full.log 2>&1; echo "ncu-full rc=$?" | tee -a $O/status.txt
 echo "== sanitizer" | tee -a $O/status.txt
 timeout -s KILL 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $O/sanitizer.log 2>&1; echo "memcheck rc=$?" | tee -a $O/status.txt

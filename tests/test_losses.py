@@ -25,6 +25,13 @@ def _check(device):
         assert float((p.grad.cpu() - 2.0 * want_g).abs().max()) <= 1e-6
         again = proj_l2_loss(gt.to(device), p.detach(), n)     # the workspace is reusable and the sum deterministic
         assert float(again) == float(loss)
+        # gradient-only form of the C-ABI entry point (loss = NULL, no workspace)
+        from dpc_b200 import _capi
+        pd, gd = pred.to(device).contiguous(), gt.to(device).contiguous()
+        gp = torch.empty_like(pd)
+        _capi.check(_capi.lib().dpc_proj_l2_loss(_capi.ptr(pd), _capi.ptr(gd), pd.numel(), 1.0 / n, None, _capi.ptr(gp), None, 0,
+                                                 _capi.stream_of(pd)))
+        assert float((gp.cpu() - want_g).abs().max()) <= 1e-6
 
 
 def test_emulated_loss_kernel():
