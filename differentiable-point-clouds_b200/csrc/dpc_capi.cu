@@ -339,7 +339,9 @@ static int launch_conv_z_bwd(const float* vox, const uint32_t* mask2, const floa
   if (pad_lo < 0 || pad_lo >= Kz) return DPC_ERR_ARG;
   const bool lean_case = (mode == DPC_PROJ_DRC) && scale && mask2 && g_proj && !g_vox;
 #ifndef DPC_EMU
-  if (lean_case && dpc_tc_conv_z_supported(V, Vz, Kz, g_probs != nullptr || g_depth != nullptr)) {
+  // the persistent tcgen05 pipeline also has the max-projection form of the silhouette-only backward
+  const bool lean_tcp = (mode == DPC_PROJ_DRC || mode == DPC_PROJ_MAX) && scale && mask2 && g_proj && !g_vox && dpc_tc_level() == 2;
+  if ((lean_case || lean_tcp) && dpc_tc_conv_z_supported(V, Vz, Kz, g_probs != nullptr || g_depth != nullptr)) {
     DpcConvZBwdArgs a = {};
     dpc_set_taps_z(&a.ht, &a.use_ht, nullptr, 0, 0);
     a.vox = vox; a.mask2 = mask2; a.scale = scale; a.taps = taps; a.K = Kz; a.pl = pad_lo; a.rev = rev;
@@ -554,7 +556,8 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   bool fold_scale = false;
 #ifndef DPC_EMU
   fold_scale = g_tune[13] == 0 && any_grid_grad && scale && d_scale && g_proj && !g_voxels && !g_probs && !g_depth &&
-               p->mode == DPC_PROJ_DRC && dpc_tc_level() == 2 && dpc_tc_conv_z_supported(p->V, p->Vz, Kz, false);
+               (p->mode == DPC_PROJ_DRC || p->mode == DPC_PROJ_MAX) && dpc_tc_level() == 2 &&
+               dpc_tc_conv_z_supported(p->V, p->Vz, Kz, false);
 #endif
   // knob 4: the splat backward runs co-resident with the x/y pass and starts on a sample as soon as that pass has
   // stored it (per-sample counters, zeroed by the depth pass like the other targets) instead of after the whole pass

@@ -674,14 +674,16 @@ static inline int dpc_tc_conv_z_fwd_launch(const DpcConvZArgs& a, void* stream) 
 }
 static inline int dpc_tc_conv_z_bwd_lean_launch(const DpcConvZBwdArgs& a, void* stream) {
   if (dpc_tc_level() == 2) {
-    if (cudaFuncSetAttribute(dpc_tcp_conv_z_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(dpc_tcp_conv_z_bwd_lean_kernel<DPC_PROJ_DRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(dpc_tcp_conv_z_bwd_lean_kernel<DPC_PROJ_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess)
       return DPC_ERR_CUDA;
     if ((((uintptr_t)a.vox) & 15u) != 0) return DPC_ERR_ARG;
     CUtensorMap zmap;
     if (dpc_tc_make_zmap(&zmap, a.vox, a.B) != DPC_OK) return DPC_ERR_CUDA;
     const int ntiles = 32 * a.B, grid = ntiles < dpc_tc_sm_count() ? ntiles : dpc_tc_sm_count();
     const DpcTcpTaps ht = dpc_tcp_take_host_taps(a.taps ? a.K : 0);
-    DPC_LAUNCH(dpc_tcp_conv_z_bwd_lean_kernel, dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles, ht);
+    if (a.mode == DPC_PROJ_MAX) { DPC_LAUNCH(dpc_tcp_conv_z_bwd_lean_kernel<DPC_PROJ_MAX>, dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles, ht); }
+    else { DPC_LAUNCH(dpc_tcp_conv_z_bwd_lean_kernel<DPC_PROJ_DRC>, dim3(grid), dim3(DPC_TCP_THREADS), DPC_TCP_SMEM_BYTES, stream, a, zmap, ntiles, ht); }
     return DPC_OK;
   }
   if (cudaFuncSetAttribute(dpc_tc_conv_z_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TC_SMEM_BYTES) != cudaSuccess)

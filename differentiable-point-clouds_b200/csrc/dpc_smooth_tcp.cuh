@@ -270,11 +270,15 @@ dpc_tcp_conv_z_fwd_kernel(const __grid_constant__ DpcConvZArgs a, const __grid_c
 // Roles are mirrored here: the work is in front of the GEMM (two sweeps over the ray for the gradient of every
 // level), the back end only stores.  So EIGHT producer warps (thread = (ray, depth half); the two partial products of
 // a ray meet through smem) and FOUR consumer warps (thread = ray, all 64 levels).
+// MODE = DPC_PROJ_DRC (quotient form) or DPC_PROJ_MAX (the levels that attain the ray's maximum share g equally, TF
+// _MaxGrad; max and tie count of the two half rays meet through smem).
+template <int MODE>
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
 dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const __grid_constant__ CUtensorMap zmap, int ntiles,
                                const __grid_constant__ DpcTcpTaps ht) {
   constexpr int V = 64, Vz = 64;
   __shared__ float pp[2][2][128];
+  __shared__ float pc[2][2][128];
   constexpr int kt_id = DPC_KT_Z_B;
   DPC_TCP_SETUP(a.taps, a.K, a.pl, a.rev);
   // barrier arrival counts differ from the forward's: 8 producer warps, 4 consumer warps
@@ -312,28 +316,52 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
       const float gp = e.gp, sc = e.sc;
       uint32_t wbits = e.wbits;
       const float inv_s = (sc != 0.0f) ? 1.0f / sc : 0.0f;
-      float P0 = 1.0f, P1 = 1.0f, P2 = 1.0f, P3 = 1.0f;
-#pragma unroll
-      for (int z = 0; z < 32; z += 4) {
-        P0 *= 1.0f - fminf(fmaxf(v[z + 0], D.lo), D.hi);
-        P1 *= 1.0f - fminf(fmaxf(v[z + 1], D.lo), D.hi);
-        P2 *= 1.0f - fminf(fmaxf(v[z + 2], D.lo), D.hi);
-        P3 *= 1.0f - fminf(fmaxf(v[z + 3], D.lo), D.hi);
-      }
-      pp[i & 1][h][m] = (P0 * P1) * (P2 * P3);
-      dpc_named_bar(2, 256);          // pp[i & 1] is rewritten two tiles later, behind the next tile's barrier
-      const float gT = gp * (pp[i & 1][0][m] * pp[i & 1][1][m]);
       float dsv = 0.0f;
+      if (MODE == DPC_PROJ_MAX) {
+        float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]);
 #pragma unroll
-      for (int z = 0; z < 32; ++z) {
-        const float vv = v[z];
-        const float u = fminf(fmaxf(vv, D.lo), D.hi);
-        float dv = __fdividef(gT, 1.0f - u);
-        if (z == 0 && h == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
-        if ((u != vv) || !(wbits & 1u)) dv = 0.0f;
-        wbits >>= 1;
-        dsv = fmaf(dv, vv, dsv);
-        v[z] = dv * sc;
+        for (int z = 4; z < 32; z += 2) { m0 = fmaxf(m0, v[z]); m1 = fmaxf(m1, v[z + 1]); }
+        pp[i & 1][h][m] = fmaxf(m0, m1);
+        dpc_named_bar(2, 256);
+        const float mx = fmaxf(pp[i & 1][0][m], pp[i & 1][1][m]);
+        int cnt = 0;
+#pragma unroll
+        for (int z = 0; z < 32; ++z) cnt += (v[z] == mx) ? 1 : 0;
+        pc[i & 1][h][m] = (float)cnt;
+        dpc_named_bar(2, 256);          // pp / pc [i & 1] are rewritten two tiles later, behind that tile's barriers
+        const float share = gp / (pc[i & 1][0][m] + pc[i & 1][1][m]);
+#pragma unroll
+        for (int z = 0; z < 32; ++z) {
+          const float vv = v[z];
+          float dv = (vv == mx) ? share : 0.0f;
+          if (!(wbits & 1u)) dv = 0.0f;
+          wbits >>= 1;
+          dsv = fmaf(dv, vv, dsv);
+          v[z] = dv * sc;
+        }
+      } else {
+        float P0 = 1.0f, P1 = 1.0f, P2 = 1.0f, P3 = 1.0f;
+#pragma unroll
+        for (int z = 0; z < 32; z += 4) {
+          P0 *= 1.0f - fminf(fmaxf(v[z + 0], D.lo), D.hi);
+          P1 *= 1.0f - fminf(fmaxf(v[z + 1], D.lo), D.hi);
+          P2 *= 1.0f - fminf(fmaxf(v[z + 2], D.lo), D.hi);
+          P3 *= 1.0f - fminf(fmaxf(v[z + 3], D.lo), D.hi);
+        }
+        pp[i & 1][h][m] = (P0 * P1) * (P2 * P3);
+        dpc_named_bar(2, 256);          // pp[i & 1] is rewritten two tiles later, behind the next tile's barrier
+        const float gT = gp * (pp[i & 1][0][m] * pp[i & 1][1][m]);
+#pragma unroll
+        for (int z = 0; z < 32; ++z) {
+          const float vv = v[z];
+          const float u = fminf(fmaxf(vv, D.lo), D.hi);
+          float dv = __fdividef(gT, 1.0f - u);
+          if (z == 0 && h == 0) dv = fmaf(gp, D.c0 - 1.0f, dv);
+          if ((u != vv) || !(wbits & 1u)) dv = 0.0f;
+          wbits >>= 1;
+          dsv = fmaf(dv, vv, dsv);
+          v[z] = dv * sc;
+        }
       }
       if (a.d_scale_part) {
         const float w = dpc_warp_sum(dsv * inv_s);
