@@ -278,7 +278,7 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
                                const __grid_constant__ DpcTcpTaps ht) {
   constexpr int V = 64, Vz = 64;
   __shared__ float pp[2][2][128];
-  __shared__ float pc[2][2][128];
+  __shared__ unsigned char pc[2][2][128];      // tie counts of the half rays (<= 32); bytes: static smem is nearly full
   constexpr int kt_id = DPC_KT_Z_B;
   DPC_TCP_SETUP(a.taps, a.K, a.pl, a.rev);
   // barrier arrival counts differ from the forward's: 8 producer warps, 4 consumer warps
@@ -327,9 +327,9 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
         int cnt = 0;
 #pragma unroll
         for (int z = 0; z < 32; ++z) cnt += (v[z] == mx) ? 1 : 0;
-        pc[i & 1][h][m] = (float)cnt;
+        pc[i & 1][h][m] = (unsigned char)cnt;
         dpc_named_bar(2, 256);          // pp / pc [i & 1] are rewritten two tiles later, behind that tile's barriers
-        const float share = gp / (pc[i & 1][0][m] + pc[i & 1][1][m]);
+        const float share = gp / (float)((int)pc[i & 1][0][m] + (int)pc[i & 1][1][m]);
 #pragma unroll
         for (int z = 0; z < 32; ++z) {
           const float vv = v[z];
