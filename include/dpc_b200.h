@@ -53,14 +53,24 @@ int dpc_abi_version(void);
 const char* dpc_error_string(int code);
 int dpc_last_cuda_error(void);
 /* Experiment / diagnostics knobs used by the benchmark sweeps (not needed in normal use; process-wide,
- * not thread-safe).  key 0 / 1: points per thread of the forward / backward splat kernel (1|2|4);
- * key 3: stage events (see dpc_debug_stage_ms); key 5: 1 = ignore host taps (run the vector-register
- * smoothing kernels); key 6: 1 = cp.async tile load in the depth kernels; key 7: conv_xy diagnostics
- * (1 memory path only, 2 arithmetic only, 3 empty CTAs, 4/5 skip the x / y correlation); key 8: smoothing-kernel
- * family at 64^3 (0 FFMA2, 1 single-tile tcgen05, 2 tcgen05 pipelines = default); key 10: 1 (default) = the fused
- * forward zeroes the raw grid with a kernel the splat overlaps (transform ahead of the grid dependency), 0 =
- * cudaMemsetAsync + wait-first splats; key 11: 1 = 16-byte red.v4 in the splat; key 12: 1 = arm the per-kernel
- * timeline (dpc_debug_ktrace_read). */
+ * not thread-safe; every value gives the same results -- tests/test_gpu_parity.py::test_splat_variants_full_shape):
+ *   0 / 1  points per thread of the forward / backward splat kernel (1|2|4; defaults 4 / 1)
+ *   2      1 = the producer warps of the x/y pipeline store the finished tiles (default 0)
+ *   3      stage events (see dpc_debug_stage_ms)
+ *   4      1 = splat backward meant to run co-resident with the x/y pass of the backward: per-sample completion
+ *          counters, 3-slot staging ring (default 0; measured slower)
+ *   5      1 = ignore host copies of the taps (vector-register FFMA2 kernels / device taps in the pipelines)
+ *   6      1 = cp.async tile load in the FFMA2 depth kernels
+ *   7      conv_xy (FFMA2) diagnostics: 1 memory path only, 2 arithmetic only, 3 empty CTAs, 4/5 skip the x / y correlation
+ *   8      smoothing-kernel family at 64^3: 0 FFMA2, 1 single-tile tcgen05, 2 tcgen05 pipelines (default)
+ *   9      1 = per-tile / per-CTA trace of the pipelines (dpc_debug_trace_read)
+ *   10     zeroing of the raw grid in the fused forward: 0 cudaMemsetAsync + wait-first splat (default), 1 store kernel,
+ *          2 TMA bulk-store kernel -- 1 and 2 as PDL primaries of a splat that transforms ahead of its grid dependency
+ *   11     1 = 16-byte reductions / gathers in the splats (default), 0 = 8-byte / scalar
+ *   12     1 = arm the per-kernel timeline and the splat phase stamps (dpc_debug_ktrace_read / _phase_read)
+ *   13     1 = keep the zeroing launch + dL/dscale atomics in the fused backward (default 0: folded partial sums)
+ *   14     1 = the backward splat stages + transforms ahead of its grid dependency (default)
+ *   15     1 = x/y pass in place, backward in the raw grid's storage: two grids per step (default) */
 int dpc_debug_set(int key, int value);
 /* diagnostics: after dpc_debug_set(12, 1), every kernel of the fused path folds %globaltimer (ns) into
  * out[4*k + {0: first CTA entry, 1: first CTA past its grid dependency, 2: last CTA past it, 3: last CTA exit}],
