@@ -1,5 +1,6 @@
 // C-ABI of the projection path (include/dpc_b200.h): argument checks and kernel launches.
-// No torch types, no host synchronisation, no static mutable state.
+// No torch types, no host synchronisation; process-wide state = the experiment knobs only (thread-local hand-overs
+// between an entry point and its launchers are consumed within the call).
 #include "dpc_common.cuh"
 #include "dpc_math.cuh"
 #include "dpc_splat.cuh"
