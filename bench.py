@@ -653,9 +653,9 @@ def run_ours(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "ms_per_step_events_around_launch": ms_outside / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: pointcloud_project_fast fwd+bwd, B=32 per GPU, N=8000, V=64, K=21, sigma_rel=3.0, "
+            "config": {"workload": "configs[1]: pointcloud_project_fast fwd+bwd, B=%d per GPU, N=8000, V=64, K=21, sigma_rel=3.0, " % B +
                                    "DRC projection, quaternion pose, occupancy scaling",
                        "global_batch": B * world, "parallelism": "independent samples sharded over ranks, no collective",
                        "launch": (("C-ABI step captured once in a CUDA graph, replayed per timed step; the timing events are "
@@ -774,6 +774,8 @@ def main():
     ap.add_argument("--workload", default="projection", choices=["projection", "train_supervised", "train_unsupervised"])
     ap.add_argument("--objects-per-rank", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (the driver's contract): B=32 per GPU; strong: the B=32 batch is split over the ranks (SURVEY 8e)")
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -789,6 +791,10 @@ def main():
         run_reference(args, rank)
         return
     rank, local_rank, world = D.init()
+    if args.scaling == "strong" and args.workload == "projection":
+        if 32 % world != 0:
+            raise SystemExit("--scaling strong needs a world size that divides 32")
+        globals()["B"] = 32 // world          # every rank renders 32 / world samples of its own (synthetic), B = 32 in total
     if args.workload != "projection":
         run_train(args, rank, local_rank, world)
     else:
