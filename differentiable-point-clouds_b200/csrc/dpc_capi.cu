@@ -83,7 +83,7 @@ int dpc_debug_set(int key, int value) {
   if (key == 7) dpc_xy_dbg = value;
 #ifndef DPC_EMU
   if (key == 8) dpc_tc_enable = value;
-  if (key == 2) dpc_tcp_pdrain = value ? 1 : 0;
+  if (key == 2) { dpc_tcp_pdrain = (value == 1) ? 1 : 0; dpc_tcp_ns3 = (value == 2) ? 1 : 0; }
   if (key == 9) { int v = value; cudaMemcpyToSymbol(dpc_tcp_trace_on, &v, sizeof(int)); }
   if (key == 12) {     // (re)arm the per-kernel timeline: minima to ~0, maxima to 0
     unsigned long long init[64];

@@ -55,7 +55,7 @@ int dpc_last_cuda_error(void);
 /* Experiment / diagnostics knobs used by the benchmark sweeps (not needed in normal use; process-wide,
  * not thread-safe; every value gives the same results -- tests/test_gpu_parity.py::test_splat_variants_full_shape):
  *   0 / 1  points per thread of the forward / backward splat kernel (1|2|4; defaults 4 / 1)
- *   2      1 = the producer warps of the x/y pipeline store the finished tiles (default 0)
+ *   2      1 = the producer warps of the x/y pipeline store the finished tiles; 2 = 3-slot staging ring (default 0)
  *   3      stage events (see dpc_debug_stage_ms)
  *   4      1 = splat backward meant to run co-resident with the x/y pass of the backward: per-sample completion
  *          counters, 3-slot staging ring (default 0; measured slower)
