@@ -1,6 +1,8 @@
 """f-4: point_cloud_distance (util/point_cloud_distance.py:26-39).  CPU: the oracle against the reference's own
 source run through the TF1 shim, a brute-force known answer, and the real kernel sources under the CPU emulation.
 GPU: the CUDA kernels against the oracle, bit-exact indices and distances."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -33,6 +35,33 @@ def test_oracle_matches_reference_source(dtype):
     assert np.array_equal(np.asarray(idx.numpy()), o_idx.numpy())
     assert np.array_equal(np.asarray(md.numpy()), o_md.numpy())
     assert np.array_equal(np.asarray(proj.numpy()), o_proj.numpy())
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chamfer")
+GOLDEN_NAMES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_oracle_matches_golden_fixture(name):
+    """Fixtures generated from the reference's own source (tests/golden/make_golden_chamfer.py): they travel, the
+    reference does not."""
+    fx = _load(name)
+    proj, md, idx = O.point_cloud_distance(fx["vs"], fx["vt"])
+    assert torch.equal(idx, fx["idx"]) and torch.equal(md, fx["min_dist"]) and torch.equal(proj, fx["proj"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_cuda_kernels_match_golden_fixture(name):
+    import dpc_b200.util.point_cloud_distance as pcd
+    fx = _load(name)
+    proj, md, idx = pcd.point_cloud_distance(fx["vs"].cuda(), fx["vt"].cuda())
+    assert torch.equal(idx.cpu(), fx["idx"]) and torch.equal(md.cpu(), fx["min_dist"]) and torch.equal(proj.cpu(), fx["proj"])
 
 
 def test_oracle_known_answers():
