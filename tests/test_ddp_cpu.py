@@ -1,0 +1,74 @@
+"""SURVEY section 4 item 4, the gloo/CPU variant: a data-parallel train step over two processes -- objects sharded over the
+ranks (a rank keeps all views of its objects), the renderer local with no collective, DDP's gradient all-reduce -- gives
+the gradients of the single-process step on the concatenated batch.  Tiny model, kernels under the CPU emulation
+(tests/emu); the NCCL variant is scripts/ddp_check.py (profiles/r01_n_ddp_check_*.json)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cfg(batch):
+    from dpc_b200.util.config import default_config
+    return default_config(vox_size=16, image_size=32, pc_num_points=64, batch_size=batch, step_size=2, z_dim=32, fc_dim=32,
+                          f_dim=4, pc_gauss_kernel_size=5, pc_relative_sigma=1.0, pc_point_dropout=1.0,
+                          max_number_of_steps=100)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from dpc_b200 import _capi, distributed as D
+    from dpc_b200.train import Trainer, synthetic_batch
+    from tests.emu_support import build_emu
+    _capi._LIB, _capi._REQUIRE_CUDA = _capi.load_library(build_emu()), False      # test infrastructure: emulated kernels
+    D.init(backend="gloo")
+    cpu = torch.device("cpu")
+    per_rank = 2
+    cfg, full = _cfg(per_rank), _cfg(per_rank * world)
+    big = synthetic_batch(full, cpu, seed=7)
+    lo, hi = D.shard_range(full.batch_size, rank, world)
+    s = cfg.step_size
+    mine = {k: (v[lo * s:hi * s] if k != "images_1" else v[lo:hi]).contiguous() for k, v in big.items()}
+    torch.manual_seed(0)
+    tr = Trainer(cfg, cpu, ddp=True, bf16=False)
+    out = tr.net(mine, 0, True)
+    # the per-rank loss is normalised by the rank's sample count and DDP averages over ranks: together that is the
+    # global 1/num_samples of model_pc.py:415 (equal shard sizes)
+    (tr.model.get_loss(mine, out) + tr.model.regularization_loss()).backward()
+    worst = None
+    if rank == 0:
+        torch.manual_seed(0)
+        ref = Trainer(full, cpu, ddp=False, bf16=False)
+        ref.model.load_state_dict(tr.model.state_dict())
+        out_r = ref.net(big, 0, True)
+        (ref.model.get_loss(big, out_r) + ref.model.regularization_loss()).backward()
+        num = den = 0.0
+        for (_, p), (_, q) in zip(tr.model.named_parameters(), ref.model.named_parameters()):
+            if p.grad is None and q.grad is None:
+                continue
+            num += float(((p.grad - q.grad).double() ** 2).sum())
+            den += float((q.grad.double() ** 2).sum())
+        worst = (num / max(den, 1e-30)) ** 0.5
+    D.barrier()
+    ret[rank] = worst
+    dist.destroy_process_group()
+
+
+def test_two_rank_ddp_gradients_equal_the_full_batch_gradients():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0] is not None and ret[0] < 1e-4, ret[0]
