@@ -66,15 +66,35 @@ def make_inputs(batch, seed_shift=0, clustered=False):
     return pc, q, sc, gt
 
 
+WORKLOAD = ("configs[1]: pointcloud_project_fast fwd+bwd, B=32 per GPU, N=8000, V=64, K=21, sigma_rel=3.0, "
+            "DRC projection, quaternion pose, occupancy scaling")
+
+
+def workload_config(args):
+    """The `config` object of the JSON line: built from the command line only, so both arms print the same object
+    (the driver compares them); what is specific to an arm goes to `config_detail`."""
+    world = args.gpus
+    strong = args.scaling == "strong"
+    if args.l2_flush:
+        l2 = ("GPU arm: 256 MiB written, then 256 MiB read, between steps (untimed): L2 evicted and left clean"
+              if args.l2_flush_mode == "write+read" else "GPU arm: 256 MiB written between steps (untimed) to evict L2")
+    else:
+        l2 = "GPU arm: no flush; a step touches ~200 MB of grids > 126 MB L2"
+    return {"workload": WORKLOAD.replace("B=32 per GPU", "B=32 in total, split over the ranks") if strong else WORKLOAD,
+            "global_batch": 32 if strong else 32 * world,
+            "parallelism": "independent samples sharded over ranks, no collective", "l2": l2}
+
+
 def bench_cfg():
     from dpc_b200.util.config import default_config
     return default_config(vox_size=V, pc_gauss_kernel_size=K, pc_relative_sigma=SIGMA)
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
-def time_oracle(batch, steps, warmup, threads):
+def time_oracle(batch, steps, warmup, threads, keep=None):
     """The reference's CPU implementation of the path (oracle port: torch-CPU op-for-op restatement
-    built like the reference -- 8 scatter grids + add_n, three conv3d, log-space DRC, autograd)."""
+    built like the reference -- 8 scatter grids + add_n, three conv3d, log-space DRC, autograd).
+    keep: a dict that receives the last step's outputs and gradients (the checker of the `parity` block)."""
     from oracle import dpc_oracle as O
     torch.set_num_threads(threads)
     cfg = bench_cfg()
@@ -90,6 +110,9 @@ def time_oracle(batch, steps, warmup, threads):
         t1 = time.perf_counter()
         if it >= warmup:
             times.append(t1 - t0)
+    if keep is not None:
+        keep.update(proj=out["proj"].detach(), voxels=out["voxels"].detach(), tr_pc=out["tr_pc"].detach(),
+                    d_pc=a[0].grad, d_q=a[1].grad, d_scale=a[2].grad, loss=float(loss))
     return sum(times), len(times)
 
 
@@ -112,14 +135,15 @@ def run_reference(args, rank):
         return
     threads = pick_threads()
     batch = args.ref_batch
-    total, n = time_oracle(batch, args.steps, max(1, min(args.warmup, 2)), threads)
+    total, n = time_oracle(batch, args.steps, args.warmup, threads)
     value = batch * n / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": n, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1000.0 * total / n,
+        "steps": n, "warmup": args.warmup, "ms_per_step": 1000.0 * total / n,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pointcloud_project_fast fwd+bwd, N=8000 V=64 K=21 sigma_rel=3.0, DRC, quaternion pose",
-                   "sample_batch": batch, "note": "reference TF1 path restated on torch-CPU (TensorFlow unavailable)"},
+        "config": workload_config(args),
+        "config_detail": {"sample_batch": batch, "note": "reference TF1 path restated on torch-CPU (TensorFlow unavailable); "
+                          "every step is one B=%d batch of the workload on the host cores (rank 0 only)" % batch},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d steps of a B=%d batch of the same workload" % (n, batch)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -474,6 +498,34 @@ def e2e_graphed(pipe, steps, nbuf=4):
     return dt, loss
 
 
+def parity_block(pipe, graph, ref):
+    """Max abs differences between the timed step's results (re-run once so the buffers hold that step) and the oracle on
+    the same seeded inputs -- the north star's gate (tr_pc / indices bit-exact, 1e-5 abs elsewhere), at the headline shape."""
+    if graph is not None:
+        graph.replay()
+    else:
+        pipe.step()
+    torch.cuda.synchronize()
+
+    def mad(dev_t, ref_t):
+        return float((dev_t.detach().cpu().double().reshape(-1) - ref_t.double().reshape(-1)).abs().max())
+
+    proj = pipe.proj.cpu()
+    loss = float(((pipe.gt3.cpu() - proj) ** 2).sum() / 2 / B)
+    return {
+        "checker": "oracle (torch-CPU restatement of the reference), same seeded inputs as the timed step",
+        "tr_pc_bit_exact": bool(torch.equal(pipe.tr_pc.cpu(), ref["tr_pc"])),
+        "max_abs_proj": mad(pipe.proj, ref["proj"]),
+        "mean_abs_proj": float((proj.double().reshape(-1) - ref["proj"].double().reshape(-1)).abs().mean()),
+        "max_abs_voxels": mad(pipe.vox, ref["voxels"]),
+        "max_abs_d_pc": mad(pipe.d_pc, ref["d_pc"]), "max_abs_d_q": mad(pipe.d_q, ref["d_q"]),
+        "max_abs_d_scale": mad(pipe.d_sc, ref["d_scale"]),
+        "grad_magnitude": {"d_pc": float(ref["d_pc"].abs().max()), "d_q": float(ref["d_q"].abs().max()),
+                           "d_scale": float(ref["d_scale"].abs().max())},
+        "loss": loss, "loss_oracle": ref["loss"], "tolerance_abs": 1e-5,
+    }
+
+
 def variant_rows(dev, steps, flush):
     """SURVEY 8(d)'s other rows of the same workload, timed like the headline (graph replay, in-graph events, L2
     evicted between steps): init-clustered cloud (decoder init, stddev 0.025: every point of a sample in ~27 voxels,
@@ -637,49 +689,60 @@ def run_ours(args, rank, local_rank, world):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         stages = pipe.stage_times(min(args.steps, 20), flush)
-        dom = max((k for k in stages if k in STAGE_BYTES), key=stages.get)
-        achieved = STAGE_BYTES[dom] * B / (stages[dom] * 1e-3) / 1e9
         step_gbs = FULL_PATH_BYTES * B / ((ms_total / args.steps) * 1e-3) / 1e9 if world == 1 else None
-        busy = pipe.kernel_timeline(graph, flush)
+        busy = pipe.kernel_timeline(graph, flush, reps=50)
+        full_shape = (B == 32 and N == 8000 and V == 64)
         roofline_busy = None
         if busy:
-            # the same ratio with each kernel's duration taken INSIDE the timed step (globaltimer stamps of its own CTAs,
-            # first CTA past its grid dependency -> last exit; PDL chaining and graph replay intact)
+            # each kernel's duration INSIDE the timed step (globaltimer stamps of its own CTAs, first CTA past its grid
+            # dependency -> last exit; PDL chaining and graph replay intact, L2 evicted before the step): the only clock
+            # whose kernel durations add up to less than the step.  `achieved` = ALGORITHMIC bytes / that duration: the
+            # grids the previous kernel left in L2 are not re-read from HBM (ncu: DRAM traffic ~0.5x algorithmic for the
+            # smoothing kernels), so a fraction is "algorithmic GB/s over HBM peak, L2-assisted", not DRAM utilisation.
             per = {k: {"busy_us": busy[k], "achieved": STAGE_BYTES[k] * B / (busy[k] * 1e-6) / 1e9,
                        "frac": STAGE_BYTES[k] * B / (busy[k] * 1e-6) / 1e9 / peak} for k in STAGE_BYTES if k in busy}
             slow = max(per, key=lambda k: per[k]["busy_us"])
             roofline_busy = {"bound": "hbm", "unit": "GB/s", "peak": peak, "dominant_kernel": slow,
-                             "achieved": per[slow]["achieved"], "frac": per[slow]["frac"], "per_kernel": per}
+                             "achieved": per[slow]["achieved"], "frac": per[slow]["frac"], "per_kernel": per,
+                             "meaning": "algorithmic bytes / in-step kernel duration / HBM peak (L2-assisted: inputs left in "
+                                        "L2 by the previous kernel are not re-read from HBM)"}
+            roofline = {"bound": "hbm", "kernel": slow, "achieved": per[slow]["achieved"], "peak": peak, "unit": "GB/s",
+                        "frac": per[slow]["frac"], "traffic": NCU_TRAFFIC_B32.get(slow) if full_shape else None,
+                        "traffic_source": NCU_TRAFFIC_SOURCE,
+                        "duration_us": busy[slow],
+                        "duration_source": "in-step: %globaltimer stamps of the kernel's own CTAs (first CTA past its grid "
+                                           "dependency -> last exit), mean of 50 graph replays of the timed step, L2 evicted "
+                                           "before each; the longest kernel of the step by that clock",
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": STAGE_BYTES[slow] * B}
+        else:
+            dom = max((k for k in stages if k in STAGE_BYTES), key=stages.get)
+            achieved = STAGE_BYTES[dom] * B / (stages[dom] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": NCU_TRAFFIC_B32.get(dom) if full_shape else None,
+                        "traffic_source": NCU_TRAFFIC_SOURCE,
+                        "duration_source": "CUDA events recorded by the library around the stage (serialises the kernels)",
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": STAGE_BYTES[dom] * B}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "ms_per_step_events_around_launch": ms_outside / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: pointcloud_project_fast fwd+bwd, B=%d per GPU, N=8000, V=64, K=21, sigma_rel=3.0, " % B +
-                                   "DRC projection, quaternion pose, occupancy scaling",
-                       "global_batch": B * world, "parallelism": "independent samples sharded over ranks, no collective",
-                       "launch": (("C-ABI step captured once in a CUDA graph, replayed per timed step; the timing events are "
-                                   "nodes of that graph (first / last), so the graph's launch latency behind the untimed L2 "
-                                   "eviction is not charged to the step -- ms_per_step_events_around_launch has it")
-                                  if g_ev0 is not None else
-                                  "C-ABI step captured once in a CUDA graph, replayed per timed step, events around the launch"
-                                  if graph is not None else "eager C-ABI calls"),
-                       "l2": (flush.describe() if args.l2_flush else
-                              "no flush; a step touches ~200 MB of grids > 126 MB L2")},
+            "config": workload_config(args),
+            "config_detail": {
+                "launch": (("C-ABI step captured once in a CUDA graph, replayed per timed step; the timing events are "
+                            "nodes of that graph (first / last), so the graph's launch latency behind the untimed L2 "
+                            "eviction is not charged to the step -- ms_per_step_events_around_launch has it")
+                           if g_ev0 is not None else
+                           "C-ABI step captured once in a CUDA graph, replayed per timed step, events around the launch"
+                           if graph is not None else "eager C-ABI calls"),
+                "l2": flush.describe() if args.l2_flush else "no flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * t_e2e / n_e2e, "loss": loss,
                     "mode": e2e_mode, "eager_pipelined_value": e2e_eager,
                     "serial_value": e2e_serial, "serial_ms_per_step": serial_ms},
             "gpu_launches": Pipeline.LAUNCHES_PER_STEP * args.steps,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": (NCU_TRAFFIC_B32.get(dom) if (B == 32 and N == 8000 and V == 64) else None),
-                         "traffic_source": NCU_TRAFFIC_SOURCE,
-                         "duration_source": "CUDA events recorded by the library around the stage on the launch stream "
-                                            "(serialises the kernels: includes the launch gap and the un-overlapped prologue)",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": STAGE_BYTES[dom] * B},
+            "roofline": roofline,
             "roofline_step": {"algorithmic_bytes_per_projection": FULL_PATH_BYTES, "achieved": step_gbs,
                               "frac": (step_gbs / peak) if step_gbs else None, "unit": "GB/s"},
             "stages_ms": stages,
@@ -688,15 +751,19 @@ def run_ours(args, rank, local_rank, world):
         }
         if world == 1 and g_ev0 is not None:
             try:
-                line["variants"] = variant_rows(dev, min(args.steps, 20), flush)
+                line["variants"] = variant_rows(dev, max(args.steps, 50), flush)
             except Exception as exc:
                 print("variant rows failed: %r" % (exc,), file=sys.stderr)
         if not args.no_cpu_baseline and world == 1:
             threads = pick_threads()
-            total, n = time_oracle(args.ref_batch, 3, 1, threads)
+            kept = {}
+            total, n = time_oracle(args.ref_batch, 3, 1, threads, keep=kept)
             line["cpu_baseline"] = {"value": args.ref_batch * n / total, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d fwd+bwd steps of a B=%d batch of the same workload (oracle, torch-CPU)"
                                               % (n, args.ref_batch)}
+            if args.ref_batch == B:
+                # the oracle ran on the very inputs of the timed step (make_inputs(B), rank 0): compare the step's results
+                line["parity"] = parity_block(pipe, graph, kept)
         emit(line)
     D.barrier()
 
