@@ -256,6 +256,7 @@ class Pipeline:
         self.saved = torch.empty(self.saved_bytes, dtype=torch.uint8, device=dev)
         self.tr_pc, self.vox, self.proj, self.g_proj = f(B, N, 3), f(B, V, V, V), f(B, V, V), f(B, V, V)
         self.d_pc, self.d_q, self.d_sc = f(B, N, 3), f(B, 4), f(B)
+        self.p.tr_pc = self.tr_pc.data_ptr()       # backward: the forward's own cells (read only by dpc_project_fast_bwd)
         self.loss = f(1)
         self.loss_ws_bytes = int(self.L.dpc_proj_l2_loss_workspace_bytes())
         self.loss_ws = torch.zeros((self.loss_ws_bytes + 3) // 4, dtype=torch.int32, device=dev)
@@ -498,6 +499,11 @@ def e2e_graphed(pipe, steps, nbuf=4):
     return dt, loss
 
 
+def fused_gather_route(pipe):
+    """True when the experimental backward route (gathers inside the x/y pass, knob 4) is in effect for this pipeline."""
+    return bool(pipe.p.tr_pc) and "4=1" in os.environ.get("DPC_KNOBS", "").split(",")
+
+
 def parity_block(pipe, graph, ref):
     """Max abs differences between the timed step's results (re-run once so the buffers hold that step) and the oracle on
     the same seeded inputs -- the north star's gate (tr_pc / indices bit-exact, 1e-5 abs elsewhere), at the headline shape."""
@@ -699,8 +705,15 @@ def run_ours(args, rank, local_rank, world):
             # whose kernel durations add up to less than the step.  `achieved` = ALGORITHMIC bytes / that duration: the
             # grids the previous kernel left in L2 are not re-read from HBM (ncu: DRAM traffic ~0.5x algorithmic for the
             # smoothing kernels), so a fraction is "algorithmic GB/s over HBM peak, L2-assisted", not DRAM utilisation.
-            per = {k: {"busy_us": busy[k], "achieved": STAGE_BYTES[k] * B / (busy[k] * 1e-6) / 1e9,
-                       "frac": STAGE_BYTES[k] * B / (busy[k] * 1e-6) / 1e9 / peak} for k in STAGE_BYTES if k in busy}
+            sbytes = dict(STAGE_BYTES)
+            if fused_gather_route(pipe):
+                # the gathers of the splat backward run inside the x/y pass of the backward: that kernel reads dL/d(raw)
+                # twice algorithmically (pipeline + 32N of corners) and writes dL/d(tr_pc); the chain-rule kernel moves
+                # only point data (pc, dL/d(tr_pc) in, d_pc out)
+                sbytes["conv_xy_bwd"] = 2 * G_BYTES + G_BYTES // 32 + 32 * N + 2 * 12 * N
+                sbytes["splat_bwd"] = 3 * 12 * N
+            per = {k: {"busy_us": busy[k], "achieved": sbytes[k] * B / (busy[k] * 1e-6) / 1e9,
+                       "frac": sbytes[k] * B / (busy[k] * 1e-6) / 1e9 / peak} for k in sbytes if k in busy}
             slow = max(per, key=lambda k: per[k]["busy_us"])
             roofline_busy = {"bound": "hbm", "unit": "GB/s", "peak": peak, "dominant_kernel": slow,
                              "achieved": per[slow]["achieved"], "frac": per[slow]["frac"], "per_kernel": per,
@@ -713,7 +726,7 @@ def run_ours(args, rank, local_rank, world):
                         "duration_source": "in-step: %globaltimer stamps of the kernel's own CTAs (first CTA past its grid "
                                            "dependency -> last exit), mean of 50 graph replays of the timed step, L2 evicted "
                                            "before each; the longest kernel of the step by that clock",
-                        "peak_source": peak_src, "algorithmic_bytes_per_launch": STAGE_BYTES[slow] * B}
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": sbytes[slow] * B}
         else:
             dom = max((k for k in stages if k in STAGE_BYTES), key=stages.get)
             achieved = STAGE_BYTES[dom] * B / (stages[dom] * 1e-3) / 1e9

@@ -29,7 +29,7 @@ c_i64 = ctypes.c_int64
 class ProjectParams(ctypes.Structure):
     _fields_ = [("B", c_i), ("N", c_i), ("Vz", c_i), ("V", c_i), ("pose_kind", c_i), ("mode", c_i),
                 ("K", c_i), ("Kz", c_i), ("focal_const", c_f), ("cam_dist", c_f), ("clip_eps", c_f),
-                ("max_depth", c_f), ("flags", c_i), ("taps_xy_host", c_p), ("taps_z_host", c_p)]
+                ("max_depth", c_f), ("flags", c_i), ("taps_xy_host", c_p), ("taps_z_host", c_p), ("tr_pc", c_p)]
 
 
 FLAG_SCRATCH_RAW_ZERO = 1

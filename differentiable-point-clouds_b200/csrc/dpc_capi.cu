@@ -7,6 +7,7 @@
 #include "dpc_smooth.cuh"
 #include "dpc_smooth_fast.cuh"
 #include "dpc_smooth_tc.cuh"
+#include "dpc_fused_bwd.cuh"
 #include "dpc_chamfer.cuh"
 #include "dpc_loss.cuh"
 
@@ -21,13 +22,17 @@ static int dpc_check_launch() {
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
 // Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[16] = {4, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1};   // [0] points/thread splat fwd, [1] splat bwd
+static int g_tune[24] = {4, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
 // [10] 1 = the raw grid is zeroed by dpc_zero_kernel and the forward splat runs its transform ahead of the grid
 //      dependency (default 0 = cudaMemsetAsync + wait-first splat: the reductions run ~4 us faster behind the driver's
 //      memset than behind a store kernel, profiles/r01_k_step_timeline.txt); [11] 1 = 16-byte red.v4 / gathers in the
 //      splats; [12] per-kernel timeline (dpc_kt); [13] 1 = keep the zeroing launch + dL/dscale atomics in the fused
 //      backward (0 = folded partials, no launch); [14] 1 = the backward splat transforms ahead of its grid dependency;
-//      [4] 1 = the splat backward runs co-resident with the x/y pass of the backward (per-sample counters);
+//      [4] 1 = the gathers of the splat backward run INSIDE the x/y pass of the backward (dpc_fused_bwd.cuh: gather warps
+//      next to the pipeline warps, per-sample completion counters; needs p->tr_pc), 0 (default) = the splat backward is its
+//      own kernel behind that pass.  Measured (profiles/r02_f_fused_gather.md): correct, but the gathers and the pipeline
+//      contend for the SM's load/store path -- 34 + 8 us against 15 + 20 -- so it stays an experiment; [16] its debug
+//      flags, [17] 1 = 768-thread variant (10 gather warps);
 //      [15] 1 = the fused path smooths x/y IN PLACE and runs the backward in the same grid (two 32 MiB grids per step
 //      instead of three)
 // measured after the 16-byte gathers (profiles/r01_m_*): forward 4 / 2 / 1 points per thread = 10.2 / 10.7 / 13.9 us,
@@ -58,7 +63,7 @@ static bool shape_ok(int B, int Vz, int V) {
 
 extern "C" {
 
-int dpc_abi_version(void) { return 2; }
+int dpc_abi_version(void) { return 3; }
 /* ms between the stage marks of the last instrumented forward+backward (synchronises):
  * out[0..5] = splat_fwd(+memset), conv_xy_fwd, conv_z_fwd, conv_z_bwd(+memsets), conv_xy_bwd, splat_bwd */
 int dpc_debug_stage_ms(float* out6) {
@@ -76,7 +81,7 @@ int dpc_debug_stage_ms(float* out6) {
 }
 
 int dpc_debug_set(int key, int value) {
-  if (key < 0 || key >= 16) return DPC_ERR_ARG;
+  if (key < 0 || key >= 24) return DPC_ERR_ARG;
   g_tune[key] = value;
   if (key == 5) dpc_ignore_host_taps = value ? 1 : 0;
   if (key == 6) dpc_z_tile_cpasync = value ? 1 : 0;
@@ -189,8 +194,7 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
                             int rgb_stop_grad, int B, int N, int Vz, int V,
                             const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
                             float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
-                            const float* d_scale_part, int n_part, float* d_scale_out, void* stream,
-                            const unsigned* sample_cnt = nullptr, int cnt_target = 0) {
+                            const float* d_scale_part, int n_part, float* d_scale_out, void* stream) {
   if (!pc) return DPC_ERR_NULL;
   if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
   if (pose_kind < DPC_POSE_NONE || pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
@@ -206,21 +210,6 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.early = g_tune[14] ? 1 : 0;
   a.gather4 = g_tune[11] ? 1 : 0;
   a.d_scale_part = d_scale_part; a.n_part = n_part; a.d_scale_out = d_scale_out;
-  a.sample_cnt = sample_cnt; a.cnt_target = cnt_target;
-#ifndef DPC_EMU
-  if (sample_cnt) {
-    // co-resident with the x/y pipeline (416 threads x 128 registers, 197 KB): 128-thread CTAs at one point per thread
-    // (64 registers) fit beside it; same shared-memory carve-out as the pipeline so the two can share an SM
-    static bool carve_set = false;
-    if (!carve_set) {
-      DPC_CUDA(cudaFuncSetAttribute(dpc_splat_bwd_kernel<1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      carve_set = true;
-    }
-    dim3 grid128((N + 127) / 128, B);
-    DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128>), grid128, dim3(128), 0, stream, a);
-    return dpc_check_launch();
-  }
-#endif
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH((dpc_splat_bwd_kernel<4, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -410,7 +399,7 @@ int dpc_conv_z_bwd(const float* vox, const uint32_t* mask2, const float* scale,
 // ------------------------------------------------------------------------------------ fused path
 static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-struct DpcScratch { float* raw; float* tmp; float* part; unsigned* cnt; int64_t total; };
+struct DpcScratch { float* raw; float* tmp; float* part; unsigned* cnt; float* d_tr; int64_t total; };
 struct DpcSaved { uint32_t* mask1; uint32_t* mask2; int64_t total; };
 
 static DpcScratch scratch_layout(const dpc_project_params* p, void* base) {
@@ -422,6 +411,8 @@ static DpcScratch scratch_layout(const dpc_project_params* p, void* base) {
   w.part = (float*)(c + 2 * align256(g * 4));      // dL/dscale partials of the depth-pass backward: [B, 32 tiles x 8 warps]
   w.cnt = (unsigned*)(c + 2 * align256(g * 4) + align256((int64_t)p->B * 256 * 4));   // per-sample completion counters (knob 4)
   w.total = 2 * align256(g * 4) + align256((int64_t)p->B * 256 * 4) + align256((int64_t)p->B * 4);
+  w.d_tr = (float*)(c + w.total);                   // dL/d(tr_pc) of every point, from the fused x/y + gather kernel to the chain rule
+  w.total += align256((int64_t)p->B * p->N * 12);
   return w;
 }
 
@@ -560,11 +551,14 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                (p->mode == DPC_PROJ_DRC || p->mode == DPC_PROJ_MAX) && dpc_tc_level() == 2 &&
                dpc_tc_conv_z_supported(p->V, p->Vz, Kz, false);
 #endif
-  // knob 4: the splat backward runs co-resident with the x/y pass and starts on a sample as soon as that pass has
-  // stored it (per-sample counters, zeroed by the depth pass like the other targets) instead of after the whole pass
-  bool coresident = fold_scale && g_tune[4] && p->N >= 128;
+  // knob 4 (default): the splat backward runs inside the x/y pass (gather warps next to the pipeline warps) and starts
+  // on a sample as soon as that pass has published it (per-sample counters, zeroed by the depth pass like the other targets)
+  bool fused_gather = false;
+#ifndef DPC_EMU
+  fused_gather = fold_scale && p->tr_pc && g_tune[4] && g_tune[15] && !(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO);
+#endif
   if (fold_scale) {
-    z.p[3] = coresident ? (float*)w.cnt : nullptr; z.n[3] = p->B;     // all-zero bits either way
+    z.p[3] = fused_gather ? (float*)w.cnt : nullptr; z.n[3] = p->B;     // all-zero bits either way
   } else if (d_pose || d_trans || d_focal || d_scale) {
     DPC_LAUNCH(dpc_zero4_kernel, dim3(1), dim3(256), 0, stream, z);
     DPC_TRY(dpc_check_launch());
@@ -584,20 +578,31 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                               fold_scale ? w.part : nullptr, fold_scale ? &z : nullptr));
     stage_mark(5, stream);
 #ifndef DPC_EMU
-    dpc_tcp_xy_cnt_next = coresident ? w.cnt : nullptr;
+    if (fused_gather) {
+      // x/y pass + the gathers in one kernel (dL/d(tr_pc) of every point into scratch), then the chain rule through the
+      // camera: the splat backward without a grid to read (d_vox = NULL, d_tr_pc_in = the gathered gradients)
+      DpcXYGatherArgs ga;
+      ga.tr_pc = p->tr_pc; ga.d_raw = G; ga.g_tr_pc = g_tr_pc; ga.d_tr = w.d_tr; ga.sample_cnt = w.cnt;
+      ga.B = p->B; ga.N = p->N; ga.dbg = g_tune[16];
+      DPC_TRY(dpc_tcp_conv_xy_gather_launch(G, tx, K, K - 1 - (K - 1) / 2, (int64_t)p->B * p->Vz, sv.mask1, /*rev=*/1, hxy, ga,
+                                            g_tune[17], stream));
+      DPC_TRY(dpc_check_launch());
+      stage_mark(6, stream);
+      DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
+                               p->B, p->N, p->Vz, p->V, nullptr, nullptr, w.d_tr, d_pc, d_pose, d_trans, d_focal, nullptr,
+                               w.part, 256, d_scale, stream));
+      stage_mark(7, stream);
+      return DPC_OK;
+    }
 #endif
     DPC_TRY(launch_conv_xy(G, G, tx, K, K - 1 - (K - 1) / 2, tx, K, K - 1 - (K - 1) / 2,
                            p->B, p->Vz, p->V, /*clip_in=*/0, nullptr, sv.mask1, /*rev=*/1, /*zero_in=*/0, stream, hxy, hxy));
-#ifndef DPC_EMU
-    if (dpc_tcp_xy_cnt_next) { dpc_tcp_xy_cnt_next = nullptr; coresident = false; }   // not the pipeline kernel: nobody signals
-#endif
     d_raw = G;
   }
   stage_mark(6, stream);
   DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
                            p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr,
-                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream,
-                           coresident ? w.cnt : nullptr, 256));
+                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream));
   stage_mark(7, stream);
   return DPC_OK;
 }

@@ -561,9 +561,6 @@ static int dpc_tc_sm_count() {
 // Host copy of the taps for the NEXT pipeline launch on this thread (set by the C-ABI layer right before it calls a
 // launcher below, consumed and cleared there); NULL = the kernel reads the device taps.
 static thread_local const float* dpc_tcp_host_taps_next = nullptr;
-// Per-sample completion counters for the NEXT x/y launch on this thread (set by the fused backward when the splat
-// backward is to run co-resident with it, knob 4); the launch then uses 3 staging slots to leave room on the SM.
-static thread_local unsigned* dpc_tcp_xy_cnt_next = nullptr;
 static int dpc_tcp_ns3 = 0;         // experiment knob 2 = 2: 3-slot staging ring in the x/y pipeline (what a co-resident CTA would need)
 static int dpc_tcp_pdrain = 0;      // experiment knob 2: the producer warps of the x/y pipeline store the tiles
 static inline DpcTcpTaps dpc_tcp_take_host_taps(int K) {
@@ -598,14 +595,11 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
     CUtensorMap xymap;
     if (dpc_tc_make_xymap(&xymap, in, nslices) != DPC_OK) return DPC_ERR_CUDA;
     const DpcTcpTaps ht = dpc_tcp_take_host_taps(taps ? K : 0);
-    unsigned* xy_cnt = dpc_tcp_xy_cnt_next;          // co-resident dependent (see dpc_tcp_xy_cnt_next)
-    dpc_tcp_xy_cnt_next = nullptr;
-    if (dpc_tcp_pdrain) xy_cnt = nullptr;
-    const int xy_ns = (xy_cnt || dpc_tcp_ns3) ? 3 : DPC_TCP_NS;
+    const int xy_ns = dpc_tcp_ns3 ? 3 : DPC_TCP_NS;
 #define DPC_TCP_XY_GO1(C, MO, MI, PD) do { \
     if (cudaFuncSetAttribute(dpc_tcp_conv_xy_kernel<C, MO, MI, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess) \
       return DPC_ERR_CUDA; \
-    DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI, PD>), dim3(grid), dim3(DPC_TCP_THREADS), (size_t)(98304 + xy_ns * 32768), stream, a, xymap, K, pl, ntiles, ht, xy_ns, xy_cnt); \
+    DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI, PD>), dim3(grid), dim3(DPC_TCP_THREADS), (size_t)(98304 + xy_ns * 32768), stream, a, xymap, K, pl, ntiles, ht, xy_ns); \
     return DPC_OK; } while (0)
 #define DPC_TCP_XY_GO(C, MO, MI) do { if (dpc_tcp_pdrain) DPC_TCP_XY_GO1(C, MO, MI, true); else DPC_TCP_XY_GO1(C, MO, MI, false); } while (0)
     switch (sel) {

@@ -421,10 +421,8 @@ dpc_tcp_conv_z_bwd_lean_kernel(const __grid_constant__ DpcConvZBwdArgs a, const 
 template <bool CLIP, bool MOUT, bool MIN, bool PDRAIN>
 __global__ void __launch_bounds__(DPC_TCP_THREADS, 1)
 dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_constant__ CUtensorMap xymap, int K, int pl, int ntiles,
-                       const __grid_constant__ DpcTcpTaps ht, int ns, unsigned* sample_cnt) {
-  // ns: staging slots in use (at most 4; 3 leaves shared memory for a co-resident splat CTA).  sample_cnt: when
-  // not NULL, every consumer warp adds 1 to sample_cnt[tile / 32] once its part of a tile is stored and visible, so a
-  // dependent kernel can start on a sample (256 arrivals) while this one is still working on later samples.
+                       const __grid_constant__ DpcTcpTaps ht, int ns) {
+  // ns: staging slots in use (at most 4)
   constexpr int V = 64;
   constexpr int kt_id = MIN ? DPC_KT_XY_B : DPC_KT_XY_F;
   DPC_TCP_SETUP(a.taps_x, K, pl, a.rev);
@@ -526,11 +524,6 @@ dpc_tcp_conv_xy_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_c
           if (!((w >> lane) & 1u)) v = 0.0f;
         }
         dst[q * V] = v;
-      }
-      if (sample_cnt) {
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(sample_cnt + (tile >> 5), 1u);
       }
     };
     int i = 0, prev_tile = -1;

@@ -226,7 +226,6 @@ struct DpcSplatBwdArgs {
   // per-warp partial sums of dL/dscale left by the depth-pass backward ([B, n_part]); CTA (0, b) folds them into
   // d_scale_out[b], so the fused backward needs neither atomics on d_scale nor a launch that zeroes it
   const float* d_scale_part; int n_part; float* d_scale_out;
-  const unsigned* sample_cnt; int cnt_target;   // co-resident mode (knob 4): per-sample completion counters of the x/y pass
 };
 
 // gathers of dL/d(raw): through the read-only path normally; past L1 (ld.global.cg) when the producer kernel is still
@@ -244,6 +243,43 @@ DPC_DEV float4 dpc_ld_gather4(const float4* p, bool coherent) {
 #else
   (void)coherent; return *p;
 #endif
+}
+
+// The 8 corner values of dL/d(raw) around a cell, for a grid whose rows are 16-byte aligned (V % 4 == 0): per (z, y) row
+// ONE 16-byte load of the 4-voxel group that holds ix, plus one scalar load of the neighbour for the lanes whose x pair
+// straddles two groups (ix % 4 == 3).  All loads are UNCONDITIONAL (a lane without a valid row, or without a straddling
+// pair, reads the sample's first voxels instead) and every one is issued before anything consumes a result.  The first form of
+// this code guarded each load with `if (inb)`: nvcc then wrapped every load in its own divergence region and reused one
+// destination quad, so the four gathers of a point became four DEPENDENT L2 round trips (cuobjdump: LDG.E.128 R28 x 3
+// with the selects in between) -- the "gather issue 12.9 us" of profiles/r01_m_splat_phases.txt.
+template <bool COHERENT>
+DPC_DEV void dpc_gather_corners(const float* dv, const DpcCell& c, int Vz, int V, float* dw) {
+  const int base = (c.iz * V + c.iy) * V + c.ix;
+  const int o4 = c.ix & 3;
+  float4 q[4];
+  float e[4];
+  bool ok[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = r >> 1, jj = r & 1;
+    ok[r] = c.valid && (c.iz + k < Vz) && (c.iy + jj < V);
+    const float* rp = ok[r] ? dv + base - o4 + (k * V + jj) * V : dv;
+    q[r] = dpc_ld_gather4(reinterpret_cast<const float4*>(rp), COHERENT);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = r >> 1, jj = r & 1;
+    const bool need = ok[r] && (o4 == 3) && (c.ix + 1 < V);
+    const float* ep = need ? dv + base + 1 + (k * V + jj) * V : dv;
+    e[r] = dpc_ld_gather(ep, COHERENT);       // unconditional as well: lanes that do not need it all read dv[0]
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float w0 = o4 == 0 ? q[r].x : (o4 == 1 ? q[r].y : (o4 == 2 ? q[r].z : q[r].w));
+    const float w1 = o4 == 0 ? q[r].y : (o4 == 1 ? q[r].z : (o4 == 2 ? q[r].w : ((c.ix + 1 < V) ? e[r] : 0.0f)));
+    dw[r * 2 + 0] = ok[r] ? w0 : 0.0f;
+    dw[r * 2 + 1] = ok[r] ? w1 : 0.0f;
+  }
 }
 
 template <int DPC_SPLAT_PPT, int NT>
@@ -301,21 +337,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     cell[j].valid = cell[j].valid && (i < n);
   }
   dpc_ph_mark(1, 2);
-  if (a.sample_cnt) {
-    // co-resident with the x/y pass of the backward (knob 4): no grid dependency -- wait until that pass has stored
-    // this sample's 32 tiles (8 consumer warps each), then read dL/d(raw) past L1 (ld.global.cg)
-    if (tid == 0) {
-#ifndef DPC_EMU
-      unsigned seen;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sample_cnt + b) : "memory");
-        if (seen < (unsigned)a.cnt_target) __nanosleep(200);
-      } while (seen < (unsigned)a.cnt_target);
-#endif
-    }
-    __syncthreads();
-    dpc_kt_mark(DPC_KT_SPLAT_B, 1);
-  } else if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
+  if (a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
   dpc_ph_mark(1, 3);
   if (a.d_scale_part && blockIdx.x == 0 && warp == NT / 32 - 1) {
     float v = 0.0f;
@@ -326,13 +348,16 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   // An uncoalesced warp load costs one L1 wavefront per lane, and the gathers are what this kernel waits for: the x
   // pair of a row comes in ONE 16-byte load whenever it does not straddle a 4-voxel group (3 of 4 points): 5
   // wavefronts per point on average instead of 8.
-  const bool coherent = a.sample_cnt != nullptr;
+  const bool coherent = false;
   const bool quad = a.gather4 && dv && ((V & 3) == 0) && ((((uintptr_t)dv) & 15u) == 0);
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
     const int base = (cell[j].iz * V + cell[j].iy) * V + cell[j].ix;
     const int o4 = cell[j].ix & 3;
     if (quad && o4 != 3) {        // ix + 1 < V is implied
+      // (the four loads below end up as four DEPENDENT round trips -- nvcc wraps each in its own divergence region and
+      // reuses one destination quad; the independent form, dpc_gather_corners, was measured SLOWER in this kernel at full
+      // occupancy: 23.8 vs 20.2 us, profiles/r02_b_timeline_sep.txt -- the L1 miss path, not the latency chain, bounds it)
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll

@@ -356,15 +356,16 @@ class _ProjectFastFn(torch.autograd.Function):
         except Exception:
             _SCRATCH.pop(key, None)
             raise
-        ctx.save_for_backward(pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved)
+        ctx.save_for_backward(pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc)
         ctx.params = params
         return tr_pc, voxels, proj
 
     @staticmethod
     def backward(ctx, g_tr, g_vox, g_proj):
         L = _capi.lib()
-        pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved = ctx.saved_tensors
+        pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc = ctx.saved_tensors
         params = ctx.params
+        params.tr_pc = ptr(tr_pc)      # the cells the forward used: the backward's gathers run inside its x/y pass
         b = params.B
 
         def opt(g):

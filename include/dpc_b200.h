@@ -182,6 +182,10 @@ typedef struct {
   int flags;            /* DPC_FLAG_* */
   const float* taps_xy_host;   /* optional host copy of taps_xy (K floats), or NULL */
   const float* taps_z_host;    /* optional host copy of taps_z (Kz floats), or NULL */
+  const float* tr_pc;          /* backward only, optional (device, [B,N,3]): the tr_pc the forward of this call wrote.
+                                  With it (64^3 grids, training case) the gathers of the splat backward run inside the
+                                  x/y pass of the backward, on the cells the forward used; NULL = the splat backward
+                                  recomputes the camera transform and runs as its own kernel behind that pass */
 } dpc_project_params;
 
 int64_t dpc_project_fast_scratch_bytes(const dpc_project_params* p);

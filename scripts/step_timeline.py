@@ -38,6 +38,11 @@ def one(label, graph=None):
         print("  %-10s entry %7.2f  dep passed %7.2f..%7.2f  exit %7.2f  busy %6.2f us%s" % (n, e, w0, w1, x, x - w0, gap))
         prev_exit = x
     print("  total %.2f us" % ((max(v[3] for _, v in rows) - t0) / 1e3))
+    if buf[4 * 9 + 3] != 0:     # fused x/y + gather kernel: its roles
+        rel = lambda t: (t - t0) / 1e3  # noqa: E731
+        print("  fused xy_bwd roles: pipelines done (last CTA) %.2f | gather warps first start %.2f, last end %.2f | "
+              "mean wait per gather warp %.2f us" % (rel(buf[4 * 8 + 3]), rel(buf[4 * 9 + 0]), rel(buf[4 * 9 + 3]),
+                                                    buf[4 * 10 + 2] / 1e3 / (148 * (10 if '17=1' in os.environ.get('DPC_KNOBS', '') else 6))))
 
 
 for _ in range(3):

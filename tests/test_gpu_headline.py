@@ -4,10 +4,15 @@ the oracle on the same seeded inputs, with the north star's ABSOLUTE tolerances:
   * tr_pc bit-exact (and with it every voxel index);
   * proj / voxels within 1e-5 abs, silhouette L1 (mean |diff|) < 1e-5;
   * d_pc within 1e-5 abs;
-  * d_q, d_scale (per-sample sums over 8000 points x 64^3 cells) within 1e-5 abs OR within 3x the reference
-    algorithm's own fp32 summation-order noise, measured here by running the oracle a second time with the points
-    of every sample permuted (same mathematics, different accumulation order).  Both numbers are written to the
-    report so the claim can be read, not inferred.
+  * d_scale within 1e-5 abs;
+  * d_q -- a per-sample SUM of 8000 per-point terms t_i with heavy cancellation -- within 1e-5 abs, or, where that is
+    below what fp32 can resolve, within u * sum_i |t_i| (u = 2^-24, the unit roundoff: the first-order error bound of
+    ANY fp32 evaluation of that sum, whatever its order).  sum_i |t_i| is computed here by the oracle (forward-mode
+    Jacobian of the camera transform times dL/dtr_pc).  At sigma = 0.2 it is ~1028 per sample, i.e. the bound is
+    6e-5 while |d_q| <= 27: 1e-5 abs is then less than one rounding per term.  The report also carries the reference
+    algorithm's own noise: the oracle re-run with the points of every sample permuted (same mathematics, different
+    accumulation order) and the oracle's d_q re-derived through the forward-mode Jacobian (same mathematics,
+    different association).
 
 The achieved errors of every variant go to gpurun_out/parity_r02.json (copied to profiles/ by the session script).
 """
@@ -80,6 +85,24 @@ def test_headline_config_against_oracle(name):
     po, pg, _ = _run(O, O, "cpu", cfg, pc_perm, q, sc, gt, v["sigma"])
     inv = torch.argsort(perm, dim=1)
     pg_pc = torch.gather(pg[0], 1, inv.unsqueeze(-1).expand(B, N, 3))
+    # per-point terms of d_q: t[b,i,c] = sum_k dL/dtr_pc[b,i,k] * d tr_pc[b,i,k] / d q[b,c]
+    from torch.func import jvp
+    leaves = [t.clone().requires_grad_(True) for t in (pc, q, sc)]
+    out = O.pointcloud_project_fast(cfg, leaves[0], leaves[1], None, None, O.smoothing_kernel(cfg, torch.tensor(v["sigma"])), leaves[2])
+    out["tr_pc"].retain_grad()
+    (((gt - out["proj"]) ** 2).sum() / 2 / B).backward()
+    g_tr = out["tr_pc"].grad
+    sum_abs_t, dq_refactored = [], []
+    for c in range(4):
+        e = torch.zeros_like(q)
+        e[:, c] = 1.0
+        _, jac = jvp(lambda qq: O.pc_perspective_transform(cfg, pc, qq), (q,), (e,))
+        t = (g_tr * jac).sum(-1)
+        sum_abs_t.append(t.abs().sum(1))
+        dq_refactored.append(t.sum(1))
+    sum_abs_t = torch.stack(sum_abs_t, -1)            # [B, 4]
+    dq_refactored = torch.stack(dq_refactored, -1)
+    dq_bound = float(sum_abs_t.max()) * 2.0 ** -24
 
     def mad(a, b):
         return float((a.double() - b.double()).abs().max())
@@ -94,13 +117,17 @@ def test_headline_config_against_oracle(name):
         "grad_magnitude": {"d_pc": float(og[0].abs().max()), "d_q": float(og[1].abs().max()), "d_scale": float(og[2].abs().max())},
         "oracle_order_noise": {"proj": mad(po["proj"], oo["proj"]), "voxels": mad(po["voxels"], oo["voxels"]),
                                "d_pc": mad(pg_pc, og[0]), "d_q": mad(pg[1], og[1]), "d_scale": mad(pg[2], og[2])},
+        "oracle_reassociation_noise_d_q": mad(dq_refactored, og[1]),
+        "d_q_sum_abs_terms_max": float(sum_abs_t.max()),
+        "d_q_fp32_bound_u_sum_abs": dq_bound,
+        "d_q_error_elementwise_within_bound": bool(((cg[1].double() - og[1].double()).abs()
+                                                    <= torch.clamp(sum_abs_t.double() * 2.0 ** -24, min=ATOL)).all()),
     }
     _update_report(name, row)
     assert row["tr_pc_bit_exact"], "tr_pc must be bit-exact"
     assert row["max_abs_proj"] <= ATOL and row["max_abs_voxels"] <= ATOL, row
     assert row["mean_abs_proj"] < ATOL, row
     assert row["max_abs_d_pc"] <= ATOL, row
-    for key in ("d_q", "d_scale"):
-        tol = max(ATOL, 3.0 * row["oracle_order_noise"][key])
-        assert row["max_abs_" + key] <= tol, (key, row)
+    assert row["max_abs_d_scale"] <= ATOL, row
+    assert row["d_q_error_elementwise_within_bound"], row          # per element: max(1e-5, u * sum_i |t_i|) of ITS sample
     assert abs(closs - oloss) <= 1e-5 * max(1.0, abs(oloss)), row

@@ -145,7 +145,8 @@ def test_splat_variants_full_shape(knob, value):
     10 = 1 zeroing kernel + forward transform ahead of the grid dependency (default: cudaMemsetAsync); 11 = 0 8-byte /
     scalar reductions and gathers (default: 16-byte); 13 = 1 zeroing launch + dL/dscale atomics in the backward (default:
     folded partials); 14 = 0 wait-first backward splat; 15 = 0 x/y pass out of place, backward in the second grid;
-    2 = 1 the producer warps of the x/y pipeline store the tiles; 4 = 1 splat backward co-resident with the x/y pass."""
+    2 = 1 the producer warps of the x/y pipeline store the tiles; 4 = 1 the gathers of the splat backward inside the x/y pass
+    of the backward (dpc_fused_bwd.cuh) + chain-rule kernel."""
     from dpc_b200 import _capi
     L = _capi.lib()
     default = {2: 0, 4: 0, 10: 0, 11: 1, 13: 0, 14: 1, 15: 1}[knob]
