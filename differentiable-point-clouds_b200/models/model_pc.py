@@ -13,7 +13,8 @@ from ..nets.img_encoder import ImgEncoder, _fc
 from ..nets.pc_decoder import PcDecoder, _trunc_fc
 from ..nets.pose_net import PoseNet
 from ..util import gauss_kernel, point_cloud
-from ..util.quaternion import quaternion_conjugate, quaternion_multiply, quaternion_normalise
+from ..util import losses as L
+from ..util.quaternion import quaternion_conjugate, quaternion_multiply, quaternion_normalise, quaternion_rotate
 
 
 def tf_repeat_0(t, num):
@@ -59,7 +60,18 @@ class ModelPointCloud(nn.Module):
         self.encoder = ImgEncoder(cfg)
         self.decoder = PcDecoder(cfg)
         self.scale_fc = _trunc_fc(cfg.z_dim, 1, 0.025) if cfg.pc_learn_occupancy_scaling else None
+        self.focal_fc = _trunc_fc(cfg.z_dim, 1, 0.025) if cfg.learn_focal_length else None      # model_pc.py:111-127
         self.posenet = PoseNet(cfg) if cfg.predict_pose else None
+        if cfg.pc_rgb_deep_decoder:
+            raise NotImplementedError("pc_rgb_deep_decoder is not implemented (pc_decoder.py:24-31)")
+        if cfg.bicubic_gt_downsampling:
+            raise NotImplementedError("bicubic_gt_downsampling is not implemented (model_pc.py:394-395)")
+        if cfg.pose_student_align_loss:
+            # 2000 reference points ~ N(0, 1) clipped to +-3 sigma; a (trainable) tf.Variable in the reference
+            # (model_pc.py:162-169), so a Parameter here
+            import numpy as np
+            vals = np.clip(np.random.normal(loc=0.0, scale=1.0, size=(2000, 3)), -3.0, 3.0)
+            self.pc_for_alignloss = nn.Parameter(torch.tensor(vals, dtype=torch.float32))
 
     # ------------------------------------------------------------------ prediction
     def model_predict(self, images):
@@ -74,7 +86,9 @@ class ModelPointCloud(nn.Module):
         out["points_1"], out["rgb_1"] = dec["xyz"], dec["rgb"]
         out["scaling_factor"] = (torch.sigmoid(self.scale_fc(ids)) * cfg.pc_occupancy_scaling_maximum
                                  if self.scale_fc is not None else None)
-        out["focal_length"] = None
+        # model_pc.py:205: the focal length is predicted from the identity units of ALL encoded views
+        out["focal_length"] = (cfg.focal_length_mean + torch.sigmoid(self.focal_fc(enc["ids"])) * cfg.focal_length_range
+                               if self.focal_fc is not None else None)
         if self.posenet is not None:
             out.update(self.posenet(enc["poses"]))
         return out
@@ -99,7 +113,8 @@ class ModelPointCloud(nn.Module):
                 focal_length=outputs["all_focal_length"])
         outputs["projs"] = proj_out["proj"]
         outputs["projs_rgb"] = proj_out["proj_rgb"]
-        outputs["proj_out"] = proj_out      # drc_probs / proj_depth stay lazy until a loss asks for them
+        outputs["proj_out"] = proj_out      # drc_probs / proj_depth stay lazy until a loss asks for them (get_loss)
+        outputs["sigma_rel"] = float(get_smooth_sigma(cfg, global_step))
         outputs["projs_1"] = proj_out["proj"][0:outputs["points_1"].shape[0]]
         return outputs
 
@@ -115,7 +130,9 @@ class ModelPointCloud(nn.Module):
             all_points = tf_repeat_0(all_points, k)
             if cfg.predict_translation:
                 outputs["predicted_translation"] = tf_repeat_0(outputs["predicted_translation"], k)
-        outputs["all_focal_length"] = None
+        # model_pc.py:283-296: the predicted focal length only reaches the renderer with several pose candidates
+        outputs["all_focal_length"] = (tf_repeat_0(outputs["focal_length"], k)
+                                       if (k > 1 and outputs["focal_length"] is not None) else None)
         outputs["all_points"] = all_points
         sc = outputs["scaling_factor"]
         if sc is not None:
@@ -127,63 +144,81 @@ class ModelPointCloud(nn.Module):
         return self.compute_projection(inputs, outputs, global_step, is_training)
 
     # ------------------------------------------------------------------ losses
-    def proj_loss_pose_candidates(self, gt, pred):
+    def proj_loss_pose_candidates(self, gt, pred, inputs=None):
         """min over pose candidates (model_pc.py:308-337) -> (loss, winning candidate per view)."""
-        k = int(self.cfg.pose_predict_num_candidates)
+        cfg = self.cfg
+        k = int(cfg.pose_predict_num_candidates)
         gt = tf_repeat_0(gt, k)
         all_loss = ((gt - pred) ** 2).sum(dim=(1, 2, 3)).reshape(-1, k)
         winner = all_loss.argmin(dim=1)
         mask = torch.nn.functional.one_hot(winner, k).to(pred.dtype).reshape(-1, 1, 1, 1)
         loss_tensor = (gt - pred) * mask
+        if cfg.variable_num_views:      # padded views carry weight 0 (model_pc.py:329-333)
+            w = tf_repeat_0(inputs["valid_samples"].to(pred.dtype), k)
+            loss_tensor = loss_tensor * w.reshape(-1, 1, 1, 1)
         num_samples = winner.shape[0]
         return (loss_tensor ** 2).sum() / 2 / num_samples, winner
 
-    def add_student_loss(self, outputs, winner):
-        """model_pc.py:339-381 (quaternion-angle variant)."""
+    def add_student_loss(self, inputs, outputs, winner, add_summary=False):
+        """model_pc.py:339-381: the student regresses the winning candidate (teacher, no gradient): quaternion-angle
+        loss, or -- pose_student_align_loss -- the distance between a fixed cloud rotated by both.  The quaternion
+        algebra runs in fp32 whatever the autocast state of the networks (1 - w^2 near w = 1 needs the mantissa)."""
         cfg = self.cfg
         k = int(cfg.pose_predict_num_candidates)
-        teachers = outputs["poses"].reshape(-1, k, 4)
+        student = outputs["pose_student"].float()
+        teachers = outputs["poses"].float().reshape(-1, k, 4)
         teachers = teachers[torch.arange(teachers.shape[0], device=teachers.device), winner].detach()
-        q_diff = quaternion_normalise(quaternion_multiply(teachers, quaternion_conjugate(outputs["pose_student"])))
-        loss = (1.0 - q_diff[:, 0] ** 2).sum() / winner.shape[0]
+        weights = inputs["valid_samples"].float() if cfg.variable_num_views else 1.0
+        if cfg.pose_student_align_loss:
+            ref = self.pc_for_alignloss.float().unsqueeze(0).expand(teachers.shape[0], -1, -1)
+            d = quaternion_rotate(ref, teachers) - quaternion_rotate(ref, student)
+            loss = (d ** 2).sum() / 2 / self.pc_for_alignloss.shape[0]
+        else:
+            q_diff = quaternion_normalise(quaternion_multiply(teachers, quaternion_conjugate(student)))
+            loss = ((1.0 - q_diff[:, 0] ** 2) * weights).sum()
+        loss = loss / winner.shape[0]
         return loss * cfg.pose_predictor_student_loss_weight
 
-    def add_proj_loss(self, inputs, outputs):
+    def add_proj_loss(self, inputs, outputs, weight_scale=None, add_summary=False):
         """model_pc.py:383-423.  TF1's bilinear resize without half-pixel centres is exact [::2,::2]
         subsampling for 128 -> 64."""
         cfg = self.cfg
-        gt, pred = inputs["masks"], outputs["projs"]
-        gs, ps = gt.shape[1], pred.shape[1]
-        assert gs >= ps, "GT size should not be higher than prediction size"
-        if gs > ps:
-            assert gs % ps == 0
-            gt = gt[:, ::gs // ps, ::gs // ps, :]
+        weight_scale = cfg.proj_weight if weight_scale is None else weight_scale
+        gt, pred = inputs["masks"], outputs["projs"].float()
+        assert gt.shape[1] >= pred.shape[1], "GT size should not be higher than prediction size"
+        gt = L.resize_tf1(gt, pred.shape[1], "bicubic" if cfg.bicubic_gt_downsampling else "bilinear")
+        gt = L._filtered_gt(cfg, gt, outputs.get("sigma_rel"), cfg.pc_gauss_filter_gt)
         total = pred.new_zeros(())
         if int(cfg.pose_predict_num_candidates) > 1:
-            proj_loss, winner = self.proj_loss_pose_candidates(gt, pred)
+            proj_loss, winner = self.proj_loss_pose_candidates(gt, pred, inputs)
             if cfg.pose_predictor_student:
-                total = total + self.add_student_loss(outputs, winner)
+                total = total + self.add_student_loss(inputs, outputs, winner, add_summary)
         else:
             if pred.is_cuda:      # model_pc.py:414-415 as one kernel (value + gradient), util/losses.py
-                from ..util.losses import proj_l2_loss
-                proj_loss = proj_l2_loss(gt.contiguous(), pred, pred.shape[0])
-            else:                 # CPU tensors only occur in the CPU test-suite (emulated kernels)
+                proj_loss = L.proj_l2_loss(gt.contiguous(), pred, pred.shape[0])
+            else:                 # CPU tensors only occur in the CPU test-suite
                 proj_loss = ((gt - pred) ** 2).sum() / 2 / pred.shape[0]
-        return (total + proj_loss) * cfg.proj_weight
+        return (total + proj_loss) * weight_scale
 
-    def get_loss(self, inputs, outputs):
-        """model_pc.py:425-445 (projection loss; drc / depth terms when their weights are non-zero)."""
+    def get_loss(self, inputs, outputs, add_summary=False):
+        """model_pc.py:425-445: projection loss, + DRC loss (drc_weight), + rgb projection loss (pc_rgb, weighted by
+        proj_rgb_weight), + depth projection loss (proj_depth_weight).  drc_probs / projs_depth are taken from the
+        projection's lazy result, so they cost nothing unless their weight is non-zero."""
         cfg = self.cfg
-        loss = outputs["projs"].new_zeros(())
+        loss = outputs["projs"].new_zeros((), dtype=torch.float32)
+        sigma = outputs.get("sigma_rel")
         if cfg.proj_weight:
-            loss = loss + self.add_proj_loss(inputs, outputs)
+            loss = loss + self.add_proj_loss(inputs, outputs, cfg.proj_weight, add_summary)
         if cfg.drc_weight:
-            gt = inputs["masks"]
-            pred = outputs["proj_out"]["drc_probs"]
-            if gt.shape[1] != pred.shape[2]:
-                gt = gt[:, ::gt.shape[1] // pred.shape[2], ::gt.shape[1] // pred.shape[2], :]
-            psi = torch.cat([(1 - gt).unsqueeze(0).expand(cfg.vox_size, -1, -1, -1, -1), gt.unsqueeze(0)], 0)
-            loss = loss + (pred * psi).sum() / gt.shape[0] * cfg.drc_weight
+            if outputs.get("drc_probs") is None:
+                outputs["drc_probs"] = outputs["proj_out"]["drc_probs"]
+            loss = loss + L.add_drc_loss(cfg, inputs, outputs, cfg.drc_weight, add_summary)
+        if cfg.pc_rgb:
+            loss = loss + L.add_proj_rgb_loss(cfg, inputs, outputs, cfg.proj_rgb_weight, add_summary, sigma)
+        if cfg.proj_depth_weight:
+            if outputs.get("projs_depth") is None:
+                outputs["projs_depth"] = outputs["proj_out"]["proj_depth"]
+            loss = loss + L.add_proj_depth_loss(cfg, inputs, outputs, cfg.proj_depth_weight, sigma, add_summary)
         return loss
 
     def regularization_loss(self):
@@ -191,7 +226,7 @@ class ModelPointCloud(nn.Module):
         if self.cfg.weight_decay <= 0:
             return 0.0
         reg = 0.0
-        for mod in (self.encoder, self.decoder, self.scale_fc, self.posenet):
+        for mod in (self.encoder, self.decoder, self.scale_fc, self.focal_fc, self.posenet):
             if mod is None:
                 continue
             for name, p in mod.named_parameters():

@@ -28,7 +28,14 @@ _DEFAULTS = {
     # loss / optimisation (default_config.yaml:92-122)
     "proj_weight": 1.0,
     "drc_weight": 0.0,
+    "proj_rgb_weight": 0.0,
     "proj_depth_weight": 0.0,
+    "max_dataset_depth": 10.0,
+    "pc_gauss_filter_gt": False,
+    "pc_gauss_filter_gt_rgb": False,
+    "pc_gauss_filter_gt_switch_off": False,
+    "bicubic_gt_downsampling": False,
+    "clip_gradient_norm": 0.0,
     "learning_rate": 0.0001,
     "learning_rate_step": 1.0,
     "learning_rate_2": 0.00001,
@@ -63,7 +70,10 @@ _DEFAULTS = {
     "pc_rgb_clip_after_conv": False,
     "pc_rgb_divide_by_occupancies": False,
     "pc_rgb_divide_by_occupancies_epsilon": 0.01,
+    "pc_rgb_deep_decoder": False,
     "learn_focal_length": False,
+    "focal_length_range": 1.0,
+    "focal_length_mean": 2.0,
     # projection (default_config.yaml:77-90)
     "vox_size": 64,
     "vox_size_z": -1,
@@ -137,13 +147,41 @@ def experiment_config(name):
     raise KeyError(name)
 
 
+# Keys of the reference's default_config.yaml that configure subsystems outside this package (data input, checkpoints,
+# visualisation, evaluation drivers, Blender rendering): accepted in a YAML file and dropped.
+_IGNORED_KEYS = frozenset("""
+config inp_dir synth_set num_views num_views_to_use tfrecords_gzip_compressed saved_camera saved_depth
+encoder_name decoder_name posenet_name decoder_conv_init_stdev focal_range voxel_grid_size checkpoint_dir gpu
+gpu_allow_growth per_process_gpu_memory_fraction shuffle_batch shuffle_dataset drc_rgb_weight compute_validation_loss
+validation_interval save_intermediate_pcs save_intermediate_pcs_interval num_dataset_samples save_predictions_dir
+vis_threshold vox_threshold vis_size vis_voxels vis_depth_projs vis_all_views save_individual_images save_predictions
+save_voxels save_point_clouds save_as_mat save_rotated_points models_list gt_pc_dir eval_split pc_eval_chamfer_num_parts
+eval_unsupervised_shape save_val_projection save_val_projection_dir vox_marching_cubes_isosurface
+vox_marching_cubes_dense pose_accuracy_threshold vis_azimuth vis_elevation vis_dist render_image_size
+render_cycles_samples render_colored_subsets
+""".split())
+# Keys that change what is computed and have NO implementation here: a YAML may carry them only at the reference default.
+_UNIMPLEMENTED_AT_DEFAULT = {"pc_normalise_gauss": False, "pc_normalise_gauss_analytical": True, "align_to_canonical": False,
+                             "pc_unit_cube": True, "pc_fast": True, "pc_rgb_deep_decoder": False}
+
+
 def load_config(path, **overrides):
-    """Defaults <- YAML file (only keys known here are taken; the reference's YAML carries many
-    keys for subsystems outside this package) <- overrides."""
+    """Defaults <- YAML file <- overrides, with the reference's rule that an unknown key is an error
+    (config.py:16-17).  Keys of subsystems outside this package (_IGNORED_KEYS) are dropped; a key that changes the
+    objective but is not implemented here raises unless it has the reference's default value."""
     import yaml
     with open(path) as f:
         data = yaml.safe_load(f) or {}
     cfg = default_config()
-    merge_into(cfg, {k: v for k, v in data.items() if k in cfg})
+    take = {}
+    for k, v in data.items():
+        if k in _UNIMPLEMENTED_AT_DEFAULT and v != _UNIMPLEMENTED_AT_DEFAULT[k]:
+            raise NotImplementedError("config key %s=%r is not implemented in dpc_b200 (only the reference default %r is)"
+                                      % (k, v, _UNIMPLEMENTED_AT_DEFAULT[k]))
+        if k in cfg:
+            take[k] = v
+        elif k not in _IGNORED_KEYS and k not in _UNIMPLEMENTED_AT_DEFAULT:
+            raise KeyError("%s is not a valid config key" % k)
+    merge_into(cfg, take)
     merge_into(cfg, overrides)
     return cfg

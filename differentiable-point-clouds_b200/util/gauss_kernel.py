@@ -66,3 +66,19 @@ def smoothing_kernel(cfg, sigma):
         # the reference reaches an unbound local here (gauss_kernel.py:51-54)
         raise NotImplementedError("pc_separable_gauss_filter=false has no kernel in the reference either")
     return separable_kernels(k1d)
+
+
+def gauss_smoothen_image(cfg, img, sigma_rel):
+    """[B,H,W,C] image smoothed by the separable Gaussian of pc_gauss_kernel_size taps, every channel on its own,
+    zero 'SAME' padding: two tf.nn.depthwise_conv2d calls, along W then along H (gauss_kernel.py:14-24).  Library
+    convolution (the loss side of the train step is library code)."""
+    import torch.nn.functional as F
+    fsz = int(cfg.pc_gauss_kernel_size)
+    sig = sigma_rel.to(img.device) if torch.is_tensor(sigma_rel) else sigma_rel
+    k = gauss_kernel_1d(fsz, sig).to(device=img.device, dtype=img.dtype)
+    c = img.shape[-1]
+    x = img.permute(0, 3, 1, 2)
+    lo, hi = (fsz - 1) // 2, (fsz - 1) - (fsz - 1) // 2
+    x = F.conv2d(F.pad(x, [lo, hi, 0, 0]), k.reshape(1, 1, 1, fsz).expand(c, 1, 1, fsz).contiguous(), groups=c)
+    x = F.conv2d(F.pad(x, [0, 0, lo, hi]), k.reshape(1, 1, fsz, 1).expand(c, 1, fsz, 1).contiguous(), groups=c)
+    return x.permute(0, 2, 3, 1).contiguous()

@@ -1,4 +1,12 @@
-"""The silhouette loss of the training step as one kernel.
+"""Loss terms of the training step (reference: dpc/util/losses.py) and the silhouette loss as one kernel.
+
+  /root/reference/dpc/util/losses.py:25-33   drc_loss
+  /root/reference/dpc/util/losses.py:53-69   add_drc_loss
+  /root/reference/dpc/util/losses.py:72-93   add_proj_rgb_loss
+  /root/reference/dpc/util/losses.py:116-140 add_proj_depth_loss
+Same names and argument order (cfg, inputs, outputs, weight_scale, ...); `add_summary` is accepted and ignored (there
+is no summary writer here).  The resizes are the TF 1.x ones (align_corners=False, no half-pixel centres), for which an
+integer reduction factor is exact sub-sampling; other factors are not needed by the reference's configs and raise.
 
 Mirrors `proj_loss = tf.nn.l2_loss(gt - pred); proj_loss /= tf.to_float(num_samples)`
 (/root/reference/dpc/models/model_pc.py:414-415; `tf.nn.l2_loss(x) = sum(x**2) / 2`): forward value and the gradient
@@ -54,3 +62,62 @@ def proj_l2_loss(gt, pred, num_samples=None):
     if num_samples is None:
         num_samples = pred.shape[0]
     return _ProjL2LossFn.apply(pred, gt, num_samples)
+
+
+# ------------------------------------------------------------------ the reference's loss terms (dpc/util/losses.py)
+def resize_tf1(img, size, method="bilinear"):
+    """tf.image.resize_images(img [B,H,W,C], [size, size]) of TF 1.x for an integer reduction factor (identity when the
+    size already matches): source coordinate = i * in / out is an integer, so bilinear and nearest are the same
+    exact sub-sampling.  (Bicubic -- cfg.bicubic_gt_downsampling -- has no implementation here.)"""
+    h = img.shape[1]
+    if h == size:
+        return img
+    if method == "bicubic":
+        raise NotImplementedError("bicubic_gt_downsampling is not implemented (the reference's experiments use bilinear)")
+    if h < size or h % size != 0:
+        raise NotImplementedError("resize %d -> %d: only integer reduction factors are implemented" % (h, size))
+    s = h // size
+    return img[:, ::s, ::s, :]
+
+
+def _filtered_gt(cfg, gt, sigma, enabled):
+    """pc_gauss_filter_gt(_rgb) with the switch-off at sigma < 1 (losses.py:82-87, model_pc.py:399-405)."""
+    if not enabled:
+        return gt
+    from .gauss_kernel import gauss_smoothen_image
+    smoothed = gauss_smoothen_image(cfg, gt, sigma)
+    if cfg.pc_gauss_filter_gt_switch_off:
+        return gt if float(sigma) < 1.0 else smoothed
+    return smoothed
+
+
+def drc_loss(cfg, probs, gt_proj):
+    """sum(probs * psi), psi = [1 - gt] * vox_size ++ [gt]  (losses.py:25-33); probs [Vz+1,B,V,V,1]."""
+    g = gt_proj.unsqueeze(0)
+    psi = torch.cat([(1 - g).expand(int(cfg.vox_size), -1, -1, -1, -1), g], 0)
+    return (probs * psi).sum()
+
+
+def add_drc_loss(cfg, inputs, outputs, weight_scale, add_summary=True):
+    gt, pred = inputs["masks"], outputs["drc_probs"]
+    gt = resize_tf1(gt, pred.shape[2])
+    return drc_loss(cfg, pred, gt) / gt.shape[0] * weight_scale
+
+
+def add_proj_rgb_loss(cfg, inputs, outputs, weight_scale, add_summary=True, sigma=None):
+    gt, pred = inputs["images"], outputs["projs_rgb"]
+    gt = resize_tf1(gt, pred.shape[1])
+    gt = _filtered_gt(cfg, gt, sigma, cfg.pc_gauss_filter_gt_rgb)
+    return ((gt - pred) ** 2).sum() / 2 / pred.shape[0] * weight_scale
+
+
+def add_proj_depth_loss(cfg, inputs, outputs, weight_scale, sigma_rel, add_summary=True):
+    gt, pred = inputs["depths"], outputs["projs_depth"]
+    if cfg.max_depth != cfg.max_dataset_depth:
+        far = gt == cfg.max_dataset_depth
+        gt = (~far).to(gt.dtype) * gt + far.to(gt.dtype) * cfg.max_depth
+    gt = resize_tf1(gt, pred.shape[1], "nearest")
+    if cfg.pc_gauss_filter_gt:
+        from .gauss_kernel import gauss_smoothen_image
+        gt = gauss_smoothen_image(cfg, gt, sigma_rel)
+    return ((gt - pred) ** 2).sum() / 2 / pred.shape[0] * weight_scale
