@@ -29,7 +29,7 @@ c_i64 = ctypes.c_int64
 class ProjectParams(ctypes.Structure):
     _fields_ = [("B", c_i), ("N", c_i), ("Vz", c_i), ("V", c_i), ("pose_kind", c_i), ("mode", c_i),
                 ("K", c_i), ("Kz", c_i), ("focal_const", c_f), ("cam_dist", c_f), ("clip_eps", c_f),
-                ("max_depth", c_f), ("flags", c_i), ("taps_xy_host", c_p), ("taps_z_host", c_p), ("tr_pc", c_p)]
+                ("max_depth", c_f), ("flags", c_i), ("taps_xy_host", c_p), ("taps_z_host", c_p), ("tr_pc", c_p), ("sel", c_p), ("N_src", c_i)]
 
 
 FLAG_SCRATCH_RAW_ZERO = 1
@@ -72,6 +72,7 @@ _SIGNATURES = {
                                    c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
     "dpc_project_fast_bwd": (c_i, [_PP, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                    c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
+    "dpc_dropout_indices": (c_i, [ctypes.c_uint64, ctypes.c_uint64, c_p, c_i, c_i, c_i, c_p, c_p]),
     "dpc_gather_points": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "dpc_gather_points_bwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
 }

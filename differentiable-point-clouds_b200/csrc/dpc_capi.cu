@@ -160,12 +160,15 @@ const char* dpc_error_string(int code) {
   }
 }
 
-int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float* trans,
-                  const float* focal, float focal_const, float cam_dist, const float* rgb,
-                  int B, int N, int Vz, int V,
-                  float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
-                  void* stream) {
+}  // extern "C"
+
+static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, const float* trans,
+                            const float* focal, float focal_const, float cam_dist, const float* rgb,
+                            int B, int N, int Vz, int V,
+                            float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
+                            const int32_t* sel, int N_src, void* stream) {
   if (!pc) return DPC_ERR_NULL;
+  if (sel && (N_src < N || rgb)) return DPC_ERR_ARG;
   if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
   if (pose_kind < DPC_POSE_NONE || pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
   if (trans && pose_kind != DPC_POSE_QUAT) return DPC_ERR_ARG;  // reference: tf.slice rank error
@@ -176,8 +179,9 @@ int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float
   a.pose_kind = pose_kind; a.focal_const = focal_const; a.cam_dist = cam_dist;
   a.B = B; a.N = N; a.Vz = Vz; a.V = V;
   a.tr_pc = tr_pc; a.vox = vox; a.vox_rgb = vox_rgb; a.idx_out = idx_out; a.valid_out = valid_out;
-  a.early = g_splat_early_next; g_splat_early_next = 0;
+  a.early = sel ? 0 : g_splat_early_next; g_splat_early_next = 0;
   a.red4 = g_tune[11] ? 1 : 0;
+  a.sel = sel; a.N_src = N_src;
   const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH(dpc_splat_fwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -186,7 +190,14 @@ int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float
   return dpc_check_launch();
 }
 
-}  // extern "C"
+extern "C" int dpc_splat_fwd(const float* pc, const float* pose, int pose_kind, const float* trans,
+                             const float* focal, float focal_const, float cam_dist, const float* rgb,
+                             int B, int N, int Vz, int V,
+                             float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
+                             void* stream) {
+  return splat_fwd_launch(pc, pose, pose_kind, trans, focal, focal_const, cam_dist, rgb, B, N, Vz, V, tr_pc, vox, vox_rgb,
+                          idx_out, valid_out, nullptr, 0, stream);
+}
 
 // the public entry point plus the fused backward's extra: fold the depth pass's dL/dscale partials
 static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, const float* trans,
@@ -194,8 +205,10 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
                             int rgb_stop_grad, int B, int N, int Vz, int V,
                             const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
                             float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
-                            const float* d_scale_part, int n_part, float* d_scale_out, void* stream) {
+                            const float* d_scale_part, int n_part, float* d_scale_out, void* stream,
+                            const int32_t* sel = nullptr, int N_src = 0) {
   if (!pc) return DPC_ERR_NULL;
+  if (sel && (N_src < N || rgb)) return DPC_ERR_ARG;
   if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
   if (pose_kind < DPC_POSE_NONE || pose_kind > DPC_POSE_MATRIX) return DPC_ERR_ARG;
   if (trans && pose_kind != DPC_POSE_QUAT) return DPC_ERR_ARG;
@@ -210,6 +223,8 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.early = g_tune[14] ? 1 : 0;
   a.gather4 = g_tune[11] ? 1 : 0;
   a.d_scale_part = d_scale_part; a.n_part = n_part; a.d_scale_out = d_scale_out;
+  a.sel = sel; a.N_src = N_src;
+  if (sel && d_pc) DPC_CUDA(cudaMemsetAsync(d_pc, 0, (size_t)B * N_src * 12, (cudaStream_t)stream));      // dropped points: zero gradient
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH((dpc_splat_bwd_kernel<4, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -494,8 +509,9 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
       DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
     }
   }
-  DPC_TRY(dpc_splat_fwd(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
-                        p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, stream));
+  if (p->sel && p->N_src < p->N) return DPC_ERR_ARG;
+  DPC_TRY(splat_fwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
+                           p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, p->sel, p->N_src, stream));
   stage_mark(1, stream);
   // clip + x/y smoothing.  With DPC_FLAG_SCRATCH_RAW_ZERO the pass also hands the raw grid back
   // all-zero (so the next forward needs no memset).  Measured on B200 (profiles/r01_d): not a win --
@@ -590,7 +606,7 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
       stage_mark(6, stream);
       DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
                                p->B, p->N, p->Vz, p->V, nullptr, nullptr, w.d_tr, d_pc, d_pose, d_trans, d_focal, nullptr,
-                               w.part, 256, d_scale, stream));
+                               w.part, 256, d_scale, stream, p->sel, p->N_src));
       stage_mark(7, stream);
       return DPC_OK;
     }
@@ -602,9 +618,18 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   stage_mark(6, stream);
   DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
                            p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr,
-                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream));
+                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream, p->sel, p->N_src));
   stage_mark(7, stream);
   return DPC_OK;
+}
+
+int dpc_dropout_indices(unsigned long long seed, unsigned long long draw, const unsigned long long* state,
+                        int B, int N, int n_keep, int32_t* sel, void* stream) {
+  if (!sel) return DPC_ERR_NULL;
+  if (B < 1 || B > 65535 || N < 1 || n_keep < 0 || n_keep > N) return DPC_ERR_SHAPE;
+  if (n_keep == 0) return DPC_OK;
+  DPC_LAUNCH(dpc_dropout_indices_kernel, dim3((n_keep + 255) / 256, B), dim3(256), 0, stream, seed, draw, state, N, n_keep, sel);
+  return dpc_check_launch();
 }
 
 int dpc_gather_points(const float* in, const int64_t* sel, int B, int N, int n_keep, int C, float* out, void* stream) {

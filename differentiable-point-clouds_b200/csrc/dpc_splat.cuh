@@ -22,15 +22,28 @@ struct DpcSplatArgs {
   float* tr_pc; float* vox; float* vox_rgb; int32_t* idx_out; uint8_t* valid_out;
   int early;   // the stream predecessor only zeroes `vox` (fused path): stage + transform + tr_pc before the grid dependency
   int red4;    // x pairs go out as one 16-byte red.v4 when they do not straddle a 4-voxel group (experiment knob 11)
+  // f-2, point dropout consumed by the load stage (point_cloud.py:293-319): sel != NULL => pc is [B,N_src,3] and point i
+  // of sample b is pc[b, sel[b*N + i]]; the points that were dropped are never read.  Outputs are [B,N,..] as usual.
+  const int32_t* sel; int N_src;
 };
 
 // Stage `n` points (3n floats) into smem: one TMA bulk copy when the 16-byte rules allow it
 // (issued by thread 0, completion on `bar`), else a cooperative copy.  Returns with the tile
 // visible to every thread.  While the copy is in flight thread 32 prepares the sample's camera.
+// sel != NULL: `src` is the SAMPLE's first point and the tile is gathered through the index list instead (f-2).
 DPC_DEV void dpc_stage_points(float* tile, uint64_t* bar, const float* src, int n, DpcPose* pose_sm,
                               const float* pose, int pose_kind, const float* trans, const float* focal,
-                              float focal_const, float cam_dist, int b) {
+                              float focal_const, float cam_dist, int b, const int32_t* sel = nullptr) {
   const unsigned bytes = (unsigned)n * 12u;
+  if (sel) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float* q = src + (size_t)sel[i] * 3;
+      tile[i * 3 + 0] = q[0]; tile[i * 3 + 1] = q[1]; tile[i * 3 + 2] = q[2];
+    }
+    if (threadIdx.x == 32) dpc_pose_load(*pose_sm, pose, pose_kind, trans, focal, focal_const, cam_dist, b);
+    __syncthreads();
+    return;
+  }
   const bool bulk_ok = ((((uintptr_t)src) & 15u) == 0) && ((bytes & 15u) == 0);
   if (bulk_ok && threadIdx.x == 0) dpc_mbar_init(bar, 1);
   __syncthreads();
@@ -77,8 +90,10 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
   dpc_ph_mark(0, 0);
   dpc_grid_dep_trigger();
   if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_F, 1); }
-  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
-                   a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  if (a.sel) dpc_stage_points(tile, &bar, a.pc + (size_t)b * a.N_src * 3, n, &pose_sm, a.pose, a.pose_kind, a.trans, a.focal,
+                              a.focal_const, a.cam_dist, b, a.sel + (size_t)b * a.N + p_first);
+  else dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
+                        a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
   dpc_ph_mark(0, 1);
 
@@ -226,6 +241,9 @@ struct DpcSplatBwdArgs {
   // per-warp partial sums of dL/dscale left by the depth-pass backward ([B, n_part]); CTA (0, b) folds them into
   // d_scale_out[b], so the fused backward needs neither atomics on d_scale nor a launch that zeroes it
   const float* d_scale_part; int n_part; float* d_scale_out;
+  // f-2 (see DpcSplatArgs): pc and d_pc are [B,N_src,3], addressed through sel[B,N]; d_pc is ZEROED by the launcher and
+  // the selected rows are written (the indices of a sample are distinct: plain stores)
+  const int32_t* sel; int N_src;
 };
 
 // gathers of dL/d(raw): through the read-only path normally; past L1 (ld.global.cg) when the producer kernel is still
@@ -307,8 +325,10 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   dpc_ph_mark(1, 0);
   dpc_grid_dep_trigger();
   if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
-  dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
-                   a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  if (a.sel) dpc_stage_points(tile, &bar, a.pc + (size_t)b * a.N_src * 3, n, &pose_sm, a.pose, a.pose_kind, a.trans, a.focal,
+                              a.focal_const, a.cam_dist, b, a.sel + (size_t)b * a.N + p_first);
+  else dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
+                        a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   const DpcPose P = pose_sm;
   dpc_ph_mark(1, 1);
 
@@ -434,7 +454,15 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     }
   }
   dpc_ph_mark(1, 5);   // gathers consumed, chain rule done
-  if (a.d_pc) {
+  if (a.d_pc && a.sel) {
+    __syncthreads();
+    const int32_t* sl = a.sel + (size_t)b * a.N + p_first;
+    float* dst = a.d_pc + (size_t)b * a.N_src * 3;
+    for (int i = tid; i < n; i += NT) {
+      float* q = dst + (size_t)sl[i] * 3;
+      q[0] = tile[i * 3 + 0]; q[1] = tile[i * 3 + 1]; q[2] = tile[i * 3 + 2];
+    }
+  } else if (a.d_pc) {
     dpc_fence_proxy_async();
     __syncthreads();
     dpc_unstage_points(a.d_pc + ((size_t)b * a.N + p_first) * 3, tile, n);
@@ -571,4 +599,57 @@ dpc_gather_bwd_kernel(const float* g_out, const int64_t* sel, int N, int n_keep,
   const int r = i / C, ch = i - r * C;
   const int64_t s = sel[(size_t)b * n_keep + r];
   atomicAdd(g_in + ((size_t)b * N + s) * C + ch, g_out[((size_t)b * n_keep + r) * C + ch]);
+}
+
+// ------------------------------------------------------------------------------ f-2: dropout index lists on the device
+// pc_point_dropout (point_cloud.py:293-319) keeps int(N * keep_prob) points per sample, drawn without replacement with
+// np.random.choice on the host through tf.py_func.  Here the subset of sample b is {pi_b(0), ..., pi_b(n_keep - 1)} for a
+// pseudo-random PERMUTATION pi_b of [0, N): a 6-round Feistel network on ceil(log2 N) bits (cycle-walking back into
+// [0, N)), keyed per sample and per draw by Philox4x32-10(counter = (b, draw), key = seed).  O(1) per index, no sort, no
+// B x N noise tensor; distinct by construction.  state (device, optional): {seed, draw} read on the device, so a
+// captured CUDA graph draws a fresh subset on every replay (the caller bumps `draw` with a one-element add).
+DPC_DEV void dpc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+DPC_DEV uint32_t dpc_mix32(uint32_t x) {      // finaliser of murmur3: the Feistel round function
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+#ifndef DPC_EMU
+__global__ void
+#else
+static void
+#endif
+dpc_dropout_indices_kernel(unsigned long long seed, unsigned long long draw, const unsigned long long* state,
+                           int N, int n_keep, int32_t* sel) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  dpc_grid_dep_wait();
+  if (i >= n_keep) return;
+  if (state) { seed = state[0]; draw = state[1]; }
+  uint32_t key[8];
+  dpc_philox4x32_10((uint32_t)b, (uint32_t)draw, (uint32_t)(draw >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), key);
+  dpc_philox4x32_10((uint32_t)b, (uint32_t)draw, (uint32_t)(draw >> 32), 1u, (uint32_t)seed, (uint32_t)(seed >> 32), key + 4);
+  int bits = 1;
+  while ((1u << bits) < (unsigned)N) ++bits;
+  if (bits < 2) bits = 2;
+  const int lb = bits / 2, hb = bits - lb;               // low half lb bits, high half hb bits (unbalanced when bits is odd)
+  const uint32_t lmask = (1u << lb) - 1u, hmask = (1u << hb) - 1u;
+  uint32_t x = (uint32_t)i;
+  do {
+    uint32_t lo = x & lmask, hi = x >> lb;
+#pragma unroll
+    for (int r = 0; r < 6; r += 2) {
+      hi = (hi ^ dpc_mix32(lo ^ key[r])) & hmask;
+      lo = (lo ^ dpc_mix32(hi ^ key[r + 1])) & lmask;
+    }
+    x = (hi << lb) | lo;
+  } while (x >= (uint32_t)N);
+  sel[(size_t)b * n_keep + i] = (int32_t)x;
 }

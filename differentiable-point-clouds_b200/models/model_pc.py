@@ -67,11 +67,11 @@ class ModelPointCloud(nn.Module):
         if cfg.bicubic_gt_downsampling:
             raise NotImplementedError("bicubic_gt_downsampling is not implemented (model_pc.py:394-395)")
         if cfg.pose_student_align_loss:
-            # 2000 reference points ~ N(0, 1) clipped to +-3 sigma; a (trainable) tf.Variable in the reference
-            # (model_pc.py:162-169), so a Parameter here
+            # 2000 reference points ~ N(0, 1) clipped to +-3 sigma (model_pc.py:162-169).  A tf.Variable outside the
+            # 'encoder' / 'decoder' scopes the optimizer trains (run/train.py:78,89), i.e. constant: a buffer here
             import numpy as np
             vals = np.clip(np.random.normal(loc=0.0, scale=1.0, size=(2000, 3)), -3.0, 3.0)
-            self.pc_for_alignloss = nn.Parameter(torch.tensor(vals, dtype=torch.float32))
+            self.register_buffer("pc_for_alignloss", torch.tensor(vals, dtype=torch.float32))
 
     # ------------------------------------------------------------------ prediction
     def model_predict(self, images):
@@ -99,18 +99,30 @@ class ModelPointCloud(nn.Module):
         all_points, all_rgb = outputs["all_points"], outputs["all_rgb"]
         camera_pose = outputs["poses"] if cfg.predict_pose else (
             inputs["camera_quaternion"] if cfg.pose_quaternion else inputs["matrices"])
+        sel = None
         if is_training and cfg.pc_point_dropout != 1:
             keep = get_dropout_prob(cfg, global_step)
-            all_points, all_rgb = point_cloud.pc_point_dropout(all_points, all_rgb, keep)
+            if all_rgb is None and all_points.is_cuda:
+                # the subset is consumed by the splat's load stage: dropped points are never read or copied
+                n_keep = point_cloud.num_points_after_dropout(all_points.shape[1], keep)
+                state = getattr(self, "dropout_state", None)      # device {seed, draw}: set by a Trainer (graph replays)
+                sel = point_cloud.dropout_indices(all_points.shape[0], all_points.shape[1], n_keep, all_points.device,
+                                                  state=state)
+                if state is not None:
+                    state[1] += 1
+            else:
+                all_points, all_rgb = point_cloud.pc_point_dropout(all_points, all_rgb, keep)
         # sigma is a function of the step count (model_pc.py:35-40): a host value, so the taps are built
         # on the CPU and the renderer receives them as launch parameters as well as a device buffer
-        kernel = gauss_kernel.smoothing_kernel(cfg, float(get_smooth_sigma(cfg, global_step)))
+        sigma_dev = getattr(self, "sigma_override", None)   # a device tensor holding the same value (captured steps)
+        kernel = gauss_kernel.smoothing_kernel(cfg, sigma_dev if sigma_dev is not None
+                                               else float(get_smooth_sigma(cfg, global_step)))
         trans = outputs.get("predicted_translation") if cfg.predict_translation else None
         with torch.autocast(device_type=all_points.device.type, enabled=False):   # the renderer is fp32
             proj_out = point_cloud.pointcloud_project_fast(
                 cfg, all_points.float(), camera_pose.float(), trans, all_rgb, kernel,
                 scaling_factor=None if outputs["all_scaling_factors"] is None else outputs["all_scaling_factors"].float(),
-                focal_length=outputs["all_focal_length"])
+                focal_length=outputs["all_focal_length"], point_indices=sel)
         outputs["projs"] = proj_out["proj"]
         outputs["projs_rgb"] = proj_out["proj_rgb"]
         outputs["proj_out"] = proj_out      # drc_probs / proj_depth stay lazy until a loss asks for them (get_loss)

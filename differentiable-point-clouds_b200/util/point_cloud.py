@@ -15,8 +15,10 @@ Differences a caller can observe (all documented in DESIGN.md):
   * a coordinate of exactly +0.5 is dropped like TF-GPU does (TF-CPU raises);
   * gradients w.r.t. the smoothing taps (i.e. dL/dsigma) are not produced -- sigma is a pure
     function of the step counter in the reference (model_pc.py:35-40), nothing consumes it;
-  * `pc_point_dropout` draws indices on the device (torch generator) instead of
-    np.random.choice on the host; the gather itself is identical.
+  * `pc_point_dropout` draws its subsets on the device (`dropout_indices`: a keyed pseudo-random permutation per
+    sample, no sort) instead of np.random.choice on the host; the gather itself is identical.
+Extension (a superset of the reference signature): `pointcloud_project_fast(..., point_indices=sel)` consumes a dropout
+index list inside the splat's load stage, so the dropped points are never read or copied.
 """
 import ctypes
 
@@ -323,7 +325,7 @@ class _ProjectFastFn(torch.autograd.Function):
     three; the clip masks travel as bit planes in a small per-call `saved` buffer."""
 
     @staticmethod
-    def forward(ctx, pc, pose, trans, focal, scale, taps_xy, taps_z, params):
+    def forward(ctx, pc, pose, trans, focal, scale, taps_xy, taps_z, params, sel=None):
         # Without this autograd hands the backward a 32 MiB grid of zeros for `voxels` and zeros for `tr_pc` whenever
         # the loss uses only `proj` (the training case): two fill launches, and the general backward kernel instead of
         # the silhouette-only one (34 vs 14 us at B=32; found in the ncu launch list of the e2e step).
@@ -343,7 +345,9 @@ class _ProjectFastFn(torch.autograd.Function):
         key, scratch = _scratch_for(dev, stream, scratch_bytes)
         params.flags = 0   # the forward zeroes the raw grid itself (the memset also warms L2 for the splat)
         saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
-        tr_pc = torch.empty_like(pc)
+        if sel is not None:          # f-2: the splat reads pc[b, sel[b, i]]; params.N = sel.shape[1], params.N_src = pc.shape[1]
+            params.sel, params.N_src = ptr(sel), pc.shape[1]
+        tr_pc = torch.empty(b, n, 3, dtype=torch.float32, device=dev)
         voxels = torch.empty(b, vz, v, v, dtype=torch.float32, device=dev)
         proj = torch.empty(b, v, v, dtype=torch.float32, device=dev)
         # drc_probs / proj_depth are NOT written here: the training loss consumes only `proj`
@@ -356,14 +360,14 @@ class _ProjectFastFn(torch.autograd.Function):
         except Exception:
             _SCRATCH.pop(key, None)
             raise
-        ctx.save_for_backward(pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc)
+        ctx.save_for_backward(pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc, sel)
         ctx.params = params
         return tr_pc, voxels, proj
 
     @staticmethod
     def backward(ctx, g_tr, g_vox, g_proj):
         L = _capi.lib()
-        pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc = ctx.saved_tensors
+        pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc, sel = ctx.saved_tensors
         params = ctx.params
         params.tr_pc = ptr(tr_pc)      # the cells the forward used: the backward's gathers run inside its x/y pass
         b = params.B
@@ -390,7 +394,7 @@ class _ProjectFastFn(torch.autograd.Function):
             d_focal = d_focal.reshape(b, 1)
         if d_scale is not None:
             d_scale = d_scale.reshape(b, 1)
-        return d_pc, d_pose, d_trans, d_focal, d_scale, None, None, None
+        return d_pc, d_pose, d_trans, d_focal, d_scale, None, None, None, None
 
 
 class ProjectionOutputs(dict):
@@ -445,14 +449,27 @@ def _fused_supported(cfg, point_cloud, kernel_parts):
 
 
 def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation,
-                            all_rgb, kernel=None, scaling_factor=None, focal_length=None):
+                            all_rgb, kernel=None, scaling_factor=None, focal_length=None, point_indices=None):
     """The reference's projection pipeline (point_cloud.py:229-290): camera transform -> trilinear
     splat -> clip -> separable smoothing -> * scaling_factor -> clip -> DRC (or max) projection
     along depth -> row flip.  Returns the same dict: proj [B,V,V,1], voxels [B,Vz,V,V,1] (not
     flipped), tr_pc [B,N,3], voxels_rgb, proj_rgb, drc_probs [Vz+1,B,V,V,1], proj_depth [B,V,V,1]
-    (None where the reference returns None)."""
+    (None where the reference returns None).
+    point_indices (extension, [B,k] integer, distinct per sample; see dropout_indices): render only the points
+    point_cloud[b, point_indices[b]] -- pc_point_dropout folded into the splat's load stage; tr_pc is then [B,k,3] and
+    the gradient of a dropped point is zero."""
     _check_pose(cfg, point_cloud, transform, predicted_translation, focal_length)
     b, n = point_cloud.shape[0], point_cloud.shape[1]
+    sel = None
+    if point_indices is not None:
+        if point_indices.dim() != 2 or point_indices.shape[0] != b or point_indices.shape[1] > n:
+            raise ValueError("point_indices must be [B,k] with k <= N")
+        if all_rgb is not None or not _fused_supported(cfg, point_cloud, None):
+            # routes without an indexed load stage: materialise the subset first (the reference's own order of operations)
+            point_cloud, all_rgb = pc_point_dropout(point_cloud, all_rgb, None, selected_indices=point_indices)
+        else:
+            sel = point_indices.to(device=point_cloud.device, dtype=torch.int32).contiguous()
+        n = point_indices.shape[1]
     vz, v = _grid_dims(cfg)
     dev = point_cloud.device
     if scaling_factor is not None and scaling_factor.numel() != b:
@@ -477,7 +494,7 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation,
             params._host_taps = (host_xy, host_z)
         tr_pc, voxels, proj = _ProjectFastFn.apply(
             point_cloud, transform, predicted_translation, focal_length, scaling_factor,
-            parts[0] if parts else None, parts[2] if parts else None, params)
+            parts[0] if parts else None, parts[2] if parts else None, params, sel)
         base = {"proj": proj.unsqueeze(-1), "voxels": voxels.unsqueeze(-1), "tr_pc": tr_pc,
                 "voxels_rgb": None, "proj_rgb": None, "drc_probs": None, "proj_depth": None}
         if cfg.ptn_max_projection:
@@ -568,16 +585,39 @@ def num_points_after_dropout(num_input_points, keep_prob):
     return int((torch.tensor(float(num_input_points), dtype=torch.float32) * kp).item())
 
 
+_DRAWS = [0]
+
+
+def dropout_indices(batch, num_points, n_keep, device, seed=None, draw=None, state=None):
+    """[batch, n_keep] int32 on `device`: for every sample a uniformly keyed pseudo-random subset of n_keep DISTINCT
+    indices of [0, num_points) -- what np.random.choice(N, n_keep, replace=False) draws per sample in the reference
+    (point_cloud.py:296-311), generated by `dpc_dropout_indices` (Philox-keyed Feistel permutation; no noise tensor,
+    no sort).  seed defaults to torch's initial seed, draw to a process-wide counter; state (device uint64 [2] =
+    {seed, draw}) makes the kernel read both on the device (CUDA-graph replays)."""
+    L = _capi.lib()
+    dev = torch.device(device)
+    sel = torch.empty(batch, n_keep, dtype=torch.int32, device=dev)
+    if seed is None:
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if draw is None:
+        draw = _DRAWS[0]
+        _DRAWS[0] += 1
+    stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else None
+    check(L.dpc_dropout_indices(int(seed), int(draw), ptr(state), batch, num_points, n_keep, ptr(sel), stream))
+    return sel
+
+
 def pc_point_dropout(points, rgb, keep_prob, generator=None, selected_indices=None):
     """Keep a random subset of int(N*keep_prob) points per sample, without replacement, same subset
     for points and rgb (point_cloud.py:293-319).  The reference draws with np.random.choice in a
-    tf.py_func on the host; here the draw is torch.rand().argsort on the device (pass
-    `selected_indices` [B,n_keep] int64 to inject a specific subset)."""
+    tf.py_func on the host; here the subsets come from `dropout_indices` on the device (pass
+    `selected_indices` [B,n_keep] to inject a specific subset; `generator` seeds the draw).  This is the materialising
+    form (a gather kernel); the training step hands the index list to pointcloud_project_fast instead."""
     b, n, _ = points.shape
     if selected_indices is None:
         k = num_points_after_dropout(n, keep_prob)
-        noise = torch.rand(b, n, device=points.device, generator=generator)
-        selected_indices = noise.argsort(dim=1)[:, :k].contiguous()
+        seed = generator.initial_seed() if generator is not None else None
+        selected_indices = dropout_indices(b, n, k, points.device, seed=seed)
     sel = selected_indices.to(device=points.device, dtype=torch.int64).contiguous()
     out_points = _GatherFn.apply(points, sel)
     out_rgb = _GatherFn.apply(rgb, sel) if rgb is not None else None

@@ -186,6 +186,11 @@ typedef struct {
                                   With it (64^3 grids, training case) the gathers of the splat backward run inside the
                                   x/y pass of the backward, on the cells the forward used; NULL = the splat backward
                                   recomputes the camera transform and runs as its own kernel behind that pass */
+  const int32_t* sel;          /* optional (device, [B,N] int32): point dropout consumed by the splat's load stage
+                                  (point_cloud.py:293-319).  pc and d_pc are then [B,N_src,3]; point i of sample b is
+                                  pc[b, sel[b*N + i]] (indices of a sample distinct), tr_pc stays [B,N,3]; dropped points
+                                  are never read and get a zero gradient.  NULL = pc is [B,N,3] */
+  int N_src;                   /* points per sample in pc when sel != NULL */
 } dpc_project_params;
 
 int64_t dpc_project_fast_scratch_bytes(const dpc_project_params* p);
@@ -206,7 +211,15 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                          float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_scale,
                          void* scratch, int64_t scratch_bytes, const void* saved, int64_t saved_bytes, void* stream);
 
-/* ---- f-2: point dropout gather (point_cloud.py:312-318): out[b,i,:] = in[b, sel[b,i], :] and its
+/* ---- f-2: the subsets of pc_point_dropout (point_cloud.py:296-311: np.random.choice(N, n_keep, replace=False) per
+ * sample, on the host, through tf.py_func) drawn on the device: sel[b, i] = pi_b(i), i < n_keep, with pi_b a pseudo-random
+ * permutation of [0, N) (Feistel network keyed by Philox4x32-10 of (b, draw) under `seed`).  Distinct by construction, no
+ * sort.  state (nullable, device, 2 x uint64 {seed, draw}): read on the device instead of the two arguments, so that a
+ * captured CUDA graph draws anew on every replay.  sel feeds dpc_project_params.sel. */
+int dpc_dropout_indices(unsigned long long seed, unsigned long long draw, const unsigned long long* state,
+                        int B, int N, int n_keep, int32_t* sel, void* stream);
+
+/* ---- f-2, materialising form: out[b,i,:] = in[b, sel[b,i], :] (point_cloud.py:312-318) and its
  * backward (scatter-add).  sel int64 [B,n_keep]. */
 int dpc_gather_points(const float* in, const int64_t* sel, int B, int N, int n_keep, int C,
                       float* out, void* stream);

@@ -1,5 +1,5 @@
 """SURVEY section 4 item 4, the gloo/CPU variant: a data-parallel train step over two processes -- objects sharded over the
-ranks (a rank keeps all views of its objects), the renderer local with no collective, DDP's gradient all-reduce -- gives
+ranks (a rank keeps all views of its objects), the renderer local with no collective, ONE all-reduce of the flat gradient buffer -- gives
 the gradients of the single-process step on the concatenated batch.  Tiny model, kernels under the CPU emulation
 (tests/emu); the NCCL variant is scripts/ddp_check.py (profiles/r01_n_ddp_check_*.json)."""
 import os
@@ -43,24 +43,21 @@ def _worker(rank, world, port, ret):
     mine = {k: (v[lo * s:hi * s] if k != "images_1" else v[lo:hi]).contiguous() for k, v in big.items()}
     torch.manual_seed(0)
     tr = Trainer(cfg, cpu, ddp=True, bf16=False)
-    out = tr.net(mine, 0, True)
-    # the per-rank loss is normalised by the rank's sample count and DDP averages over ranks: together that is the
-    # global 1/num_samples of model_pc.py:415 (equal shard sizes)
-    (tr.model.get_loss(mine, out) + tr.model.regularization_loss()).backward()
+    assert tr.world == world and tr.comm_bytes == tr.flat_g.numel() * 4
+    # forward, loss, backward, regulariser, then THE collective of the step: one all-reduce of the flat gradient buffer.
+    # The per-rank loss is normalised by the rank's sample count and the reduced sum is divided by the number of ranks:
+    # together that is the global 1/num_samples of model_pc.py:415 (equal shard sizes)
+    tr._forward_backward(mine)
     worst = None
     if rank == 0:
         torch.manual_seed(0)
         ref = Trainer(full, cpu, ddp=False, bf16=False)
-        ref.model.load_state_dict(tr.model.state_dict())
-        out_r = ref.net(big, 0, True)
-        (ref.model.get_loss(big, out_r) + ref.model.regularization_loss()).backward()
-        num = den = 0.0
-        for (_, p), (_, q) in zip(tr.model.named_parameters(), ref.model.named_parameters()):
-            if p.grad is None and q.grad is None:
-                continue
-            num += float(((p.grad - q.grad).double() ** 2).sum())
-            den += float((q.grad.double() ** 2).sum())
-        worst = (num / max(den, 1e-30)) ** 0.5
+        ref.load_flat(tr)
+        ref._forward_backward(big)
+        d = (tr.flat_g - ref.flat_g).double()
+        worst = float((d ** 2).sum() / max(float((ref.flat_g.double() ** 2).sum()), 1e-30)) ** 0.5
+        # every parameter's .grad is a view of the flat buffer
+        assert all(p.grad.data_ptr() >= tr.flat_g.data_ptr() for p in tr.model.parameters())
     D.barrier()
     ret[rank] = worst
     dist.destroy_process_group()
