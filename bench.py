@@ -434,7 +434,7 @@ def e2e_pipelined(pipe, steps):
     return dt, loss
 
 
-def e2e_graphed(pipe, steps, nbuf=4):
+def e2e_graphed(pipe, steps, nbuf=4, host_inputs=True):
     """End to end with HOST buffers, the way a throughput-minded caller would run it: ONE CUDA graph per buffer set holds
     the whole step -- H2D of the step's inputs from pinned memory, the step a user builds with the public API
     (pointcloud_project_fast -> loss -> autograd), D2H of loss + silhouettes + gradients into pinned memory -- and
@@ -454,16 +454,25 @@ def e2e_graphed(pipe, steps, nbuf=4):
     h_out = [torch.empty_like(pipe.h_out).pin_memory() for _ in range(nbuf)]
     h_parts = [torch.split(h, pipe.out_sizes) for h in h_out]
 
+    if not host_inputs:
+        # what a training step does: the decoder's points never leave HBM and only the loss value is read back
+        for k in range(nbuf):
+            d_in[k].copy_(pipe.h_in)
+
     def step_fn(k):
-        d_in[k].copy_(pipe.h_in, non_blocking=True)                                   # H2D, 3.6 MB
+        if host_inputs:
+            d_in[k].copy_(pipe.h_in, non_blocking=True)                               # H2D, 3.6 MB
         parts = torch.split(d_in[k], pipe.in_sizes)
         pc, q, sc, gt = [p.reshape(sh) for p, sh in zip(parts, pipe.in_shapes)]
         pc, q, sc = pc.detach().requires_grad_(True), q.detach().requires_grad_(True), sc.detach().requires_grad_(True)
         out = pcm.pointcloud_project_fast(pipe.cfg, pc, q, None, None, pipe.kernel, sc)
         l = proj_l2_loss(gt, out["proj"], B)              # sum((gt - proj)^2) / 2 / B, model_pc.py:414-415
         gpc, gq, gsc = torch.autograd.grad(l, (pc, q, sc))
-        for h, t in zip(h_parts[k], (l.detach(), out["proj"].detach(), gpc, gq, gsc)):    # D2H, 3.6 MB
-            h.copy_(t.reshape(-1), non_blocking=True)
+        if host_inputs:
+            for h, t in zip(h_parts[k], (l.detach(), out["proj"].detach(), gpc, gq, gsc)):    # D2H, 3.6 MB
+                h.copy_(t.reshape(-1), non_blocking=True)
+        else:
+            h_parts[k][0].copy_(l.detach().reshape(-1), non_blocking=True)                   # D2H, 4 bytes
 
     graphs = []
     torch.cuda.synchronize()
@@ -683,7 +692,24 @@ def run_ours(args, rank, local_rank, world):
             n_e2e = n_g
     except Exception as exc:  # capture not possible: keep the eager number
         print("graph capture failed: %r" % (exc,), file=sys.stderr)
+    # second, clearly labelled row: the same API-built step with DEVICE-resident inputs and only the loss read back (what the
+    # train step does: the decoder's points never leave HBM) -- separates the kernels + API from the host fabric
+    e2e_dev = None
+    try:
+        e2e_graphed(pipe, 10, host_inputs=False)
+        D.barrier()
+        t_d, loss_d = e2e_graphed(pipe, max(n_e2e, 100), host_inputs=False)
+        t_d = D.reduce_scalar(t_d, "max", dev)
+        e2e_dev = {"value": world * B * max(n_e2e, 100) / t_d, "unit": UNIT, "ms_per_step": 1000.0 * t_d / max(n_e2e, 100),
+                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4, "loss": loss_d,
+                   "mode": "same graphs, inputs resident in HBM, only the loss value crosses PCIe per step"}
+    except Exception as exc:
+        print("device-resident e2e failed: %r" % (exc,), file=sys.stderr)
 
+    # BASELINE configs 3 / 4 (the train step around this path) under the same launch: every rank takes part (all-reduce)
+    train = None
+    if not args.no_train and args.scaling == "weak":
+        train = train_rows(args, rank, local_rank, world)
     line = None
     if rank == 0:
         import json as _json
@@ -753,11 +779,15 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * t_e2e / n_e2e, "loss": loss,
                     "mode": e2e_mode, "eager_pipelined_value": e2e_eager,
-                    "serial_value": e2e_serial, "serial_ms_per_step": serial_ms},
+                    "serial_value": e2e_serial, "serial_ms_per_step": serial_ms,
+                    "note": "e2e may exceed `value`: four steps are in flight (their kernels fill each other's gaps) and L2 "
+                            "is not evicted between them, while `value` is one step at a time behind an L2 eviction"},
+            "e2e_device_resident_inputs": e2e_dev,
             "gpu_launches": Pipeline.LAUNCHES_PER_STEP * args.steps,
             "roofline": roofline,
             "roofline_step": {"algorithmic_bytes_per_projection": FULL_PATH_BYTES, "achieved": step_gbs,
                               "frac": (step_gbs / peak) if step_gbs else None, "unit": "GB/s"},
+            "train": train,
             "stages_ms": stages,
             "kernel_busy_us": busy,
             "roofline_in_step": roofline_busy,
@@ -781,45 +811,84 @@ def run_ours(args, rank, local_rank, world):
     D.barrier()
 
 
-def run_train(args, rank, local_rank, world):
-    """BASELINE configs 3/4: the full train step (CNN encoder/decoder under bf16 autocast -> fp32
-    renderer -> losses -> Adam), data parallel over ranks with DDP's gradient all-reduce."""
+def train_rows(args, rank, local_rank, world, steps=20):
+    """BASELINE configs 3 / 4 under the same launch: the full train step (CNN encoder / decoder / pose ensemble under bf16
+    autocast -> fp32 renderer -> losses -> one all-reduce of the flat gradient buffer -> fused Adam) as a replayed CUDA
+    graph.  chair_camera_supervision: 8 objects x 4 views per GPU (weak scaling); chair_unsupervised: 16 objects in total
+    (config 4: "B=16 on 8xB200"), 4 views x 4 pose candidates each, split over the ranks.  Device time (CUDA events,
+    max over ranks) of `steps` steps after the warm-up / capture steps."""
     from dpc_b200 import distributed as D
     from dpc_b200.train import Trainer, synthetic_batch
     from dpc_b200.util.config import experiment_config
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    name = "chair_camera_supervision" if args.workload == "train_supervised" else "chair_unsupervised"
-    cfg = experiment_config(name)
-    if args.objects_per_rank:
-        cfg.batch_size = args.objects_per_rank
-    torch.manual_seed(0)
-    tr = Trainer(cfg, dev, ddp=world > 1, bf16=True)
-    batch = synthetic_batch(cfg, dev, seed=rank)
-    for _ in range(max(3, args.warmup)):
-        tr.step(batch)
-    torch.cuda.synchronize()
-    D.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = tr.step(batch)
-    e1.record()
-    torch.cuda.synchronize()
-    D.barrier()
-    ms = D.reduce_scalar(e0.elapsed_time(e1), "max", dev)
-    views = cfg.batch_size * cfg.step_size
+    rows = {}
+    for name in ("chair_camera_supervision", "chair_unsupervised"):
+        row = {}
+        try:
+            cfg = experiment_config(name)
+            if name == "chair_unsupervised":
+                if 16 % world != 0:
+                    raise RuntimeError("16 objects do not split over %d ranks" % world)
+                cfg.batch_size = 16 // world
+            torch.manual_seed(0)
+            batch = synthetic_batch(cfg, dev, seed=rank)
+            for mode in ("graph", "eager"):
+                tr = Trainer(cfg, dev, ddp=world > 1, bf16=True, graph=(mode == "graph"))
+                for _ in range(max(3, args.warmup)):
+                    loss = tr.step(batch)
+                torch.cuda.synchronize()
+                D.barrier()
+                n = steps if mode == "graph" else max(3, steps // 4)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    loss = tr.step(batch)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = D.reduce_scalar(e0.elapsed_time(e1), "max", dev) / n
+                views = cfg.batch_size * cfg.step_size * world
+                row[mode] = {"ms_per_step": ms, "object_views_per_s": views / (ms * 1e-3), "loss": float(loss)}
+                if mode == "graph":
+                    row.update(objects_per_gpu=cfg.batch_size, views=cfg.step_size, pose_candidates=cfg.pose_predict_num_candidates,
+                               renderer_batch_per_gpu=cfg.batch_size * cfg.step_size * cfg.pose_predict_num_candidates,
+                               points_kept_by_dropout=tr.n_keep(), parameters=tr.flat_p.numel(),
+                               allreduce_bytes_per_step=tr.comm_bytes)
+                    if world > 1:          # the step's one collective on its own: NCCL all-reduce of the flat gradient buffer
+                        import torch.distributed as dist
+                        for _ in range(3):
+                            dist.all_reduce(tr.flat_g)
+                        torch.cuda.synchronize()
+                        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a0.record()
+                        for _ in range(10):
+                            dist.all_reduce(tr.flat_g)
+                        a1.record()
+                        torch.cuda.synchronize()
+                        ar = D.reduce_scalar(a0.elapsed_time(a1), "max", dev) / 10
+                        row["allreduce_ms"] = ar
+                        row["allreduce_busbw_gbs"] = tr.comm_bytes * 2 * (world - 1) / world / (ar * 1e-3) / 1e9
+                del tr
+            row["dtype"] = "bf16 (CNN, autocast) + f32 (renderer, losses, optimizer state)"
+            row["parallelism"] = "dp%d: objects sharded over ranks, one NCCL all-reduce of the flat fp32 gradient buffer per step" % world
+        except Exception as exc:  # keep the projection line even if a train phase fails
+            row["error"] = repr(exc)
+            print("train row %s failed: %r" % (name, exc), file=sys.stderr)
+        rows[name] = row
+        torch.cuda.empty_cache()
+    return rows
+
+
+def run_train(args, rank, local_rank, world):
+    """--workload train: only the train rows (BASELINE configs 3 / 4), as their own JSON line."""
+    torch.cuda.set_device(local_rank)
+    rows = train_rows(args, rank, local_rank, world, steps=args.steps)
     if rank == 0:
-        emit(({
-            "metric": "train step: object-views/sec (%s)" % name, "value": world * views * args.steps / (ms / 1000.0),
-            "unit": "object-views/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 (CNN) + f32 (renderer)", "data": "synthetic",
-            "config": {"workload": name, "objects_per_gpu": cfg.batch_size, "views": cfg.step_size,
-                       "pose_candidates": cfg.pose_predict_num_candidates,
-                       "renderer_batch_per_gpu": views * cfg.pose_predict_num_candidates,
-                       "parallelism": "dp%d (DDP, one bucketed NCCL all-reduce of the CNN gradients)" % world},
-            "loss": float(loss)}))
+        sup = rows.get("chair_camera_supervision", {}).get("graph", {})
+        emit({"metric": "train step: object-views/sec (chair_camera_supervision)", "value": sup.get("object_views_per_s"),
+              "unit": "object-views/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+              "ms_per_step": sup.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "bf16 (CNN) + f32 (renderer)", "data": "synthetic", "config": {"workload": "train"}, "train": rows})
+    from dpc_b200 import distributed as D
     D.barrier()
 
 
@@ -851,8 +920,8 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     _quiet_stdout()
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="projection", choices=["projection", "train_supervised", "train_unsupervised"])
-    ap.add_argument("--objects-per-rank", type=int, default=0)
+    ap.add_argument("--workload", default="projection", choices=["projection", "train"])
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step rows (BASELINE configs 3 / 4) of the JSON line")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (the driver's contract): B=32 per GPU; strong: the B=32 batch is split over the ranks (SURVEY 8e)")

@@ -24,7 +24,8 @@ def quaternion_multiply(a, b):
 
 
 def quaternion_conjugate(q):
-    return q * torch.tensor([1.0, -1.0, -1.0, -1.0], dtype=q.dtype, device=q.device)
+    # (w, -x, -y, -z) without a host-built constant: a host -> device copy cannot be captured in a CUDA graph
+    return torch.cat([q[..., :1], -q[..., 1:]], dim=-1)
 
 
 def quaternion_normalise(q):
