@@ -1,7 +1,14 @@
 #!/usr/bin/env python
-"""BASELINE config 5: N in {2k,8k,16k,32k} x V in {32,64,128}, K=21, B=32, forward+backward
-through the C-ABI with resident inputs (CUDA events).  Writes gpurun_out/sweep.json."""
-import ctypes
+"""BASELINE config 5: N in {2k, 8k, 16k, 32k} x V in {32, 64, 128}, K = 21, B = 32 per GPU, forward + backward of the
+fused path, timed exactly like bench.py's headline (the C-ABI step captured in a CUDA graph with the timing events as its
+first / last nodes, L2 evicted between steps), at 1 / 2 / 4 / 8 GPUs (weak scaling, no data-path collective; launch with
+torchrun for N > 1), with the reference's CPU path (oracle port, a bounded B = 4 sample) beside every cell (--cpu).
+
+    python scripts/sweep.py --cpu                                                    # 1 GPU
+    python -m torch.distributed.run --nproc-per-node 8 ... scripts/sweep.py --gpus 8
+Prints one JSON object (rank 0); `frac` = algorithmic bytes of the full path / step time / HBM peak.
+"""
+import argparse
 import json
 import os
 import sys
@@ -10,67 +17,78 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from dpc_b200 import _capi  # noqa: E402
-from dpc_b200.util import gauss_kernel as gk  # noqa: E402
-from dpc_b200.util.config import default_config  # noqa: E402
-
-B, K = 32, 21
+import bench  # noqa: E402
+from dpc_b200 import distributed as D  # noqa: E402
 
 
-def run(n, v, steps=20):
-    dev = torch.device("cuda", 0)
-    L = _capi.lib()
-    cfg = default_config(vox_size=v, pc_gauss_kernel_size=K)
-    g = torch.Generator().manual_seed(1234)
-    pc = (torch.tanh(0.5 * torch.randn(B, n, 3, generator=g)) / 2).to(dev)
-    q = torch.randn(B, 4, generator=g).to(dev)
-    sc = torch.sigmoid(torch.randn(B, generator=g)).to(dev)
-    gt = (torch.rand(B, v, v, generator=g) > 0.5).float().to(dev)
-    taps = gk.smoothing_kernel(cfg, torch.tensor(3.0, device=dev)).taps_xy
-    p = _capi.ProjectParams(B=B, N=n, Vz=v, V=v, pose_kind=0, mode=0, K=K, Kz=K, focal_const=1.875, cam_dist=2.0,
-                            clip_eps=1e-5, max_depth=10.0, flags=0)
-    sb, vb = L.dpc_project_fast_scratch_bytes(ctypes.byref(p)), L.dpc_project_fast_saved_bytes(ctypes.byref(p))
-    scratch = torch.zeros(sb, dtype=torch.uint8, device=dev)
-    saved = torch.empty(vb, dtype=torch.uint8, device=dev)
-    f = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
-    tr, vox, proj, gp, dpc, dq, dsc = f(B, n, 3), f(B, v, v, v), f(B, v, v), f(B, v, v), f(B, n, 3), f(B, 4), f(B)
-    st = torch.cuda.current_stream().cuda_stream
-
-    def step():
-        _capi.check(L.dpc_project_fast_fwd(ctypes.byref(p), pc.data_ptr(), q.data_ptr(), None, None, sc.data_ptr(),
-                                           taps.data_ptr(), taps.data_ptr(), tr.data_ptr(), vox.data_ptr(), proj.data_ptr(),
-                                           None, None, scratch.data_ptr(), sb, saved.data_ptr(), vb, st))
-        torch.sub(proj, gt, out=gp)
-        gp.mul_(1.0 / B)
-        _capi.check(L.dpc_project_fast_bwd(ctypes.byref(p), pc.data_ptr(), q.data_ptr(), None, None, sc.data_ptr(),
-                                           taps.data_ptr(), taps.data_ptr(), vox.data_ptr(), gp.data_ptr(), None, None, None,
-                                           None, dpc.data_ptr(), dq.data_ptr(), None, None, dsc.data_ptr(),
-                                           scratch.data_ptr(), sb, saved.data_ptr(), vb, st))
-
+def run_cell(dev, n, v, steps, flush, rank):
+    bench.N, bench.V = n, v
+    bench.G_BYTES = v * v * v * 4
+    pipe = bench.Pipeline(dev, seed_shift=rank)
     for _ in range(3):
-        step()
+        pipe.step()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
+    e0 = torch.cuda.Event(enable_timing=True, external=True)
+    e1 = torch.cuda.Event(enable_timing=True, external=True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        e0.record()
+        pipe.step()
+        e1.record()
+    total = 0.0
+    D.barrier()
+    for it in range(steps + 2):
+        flush.fill_(it & 0xff)
+        g.replay()
+        e1.synchronize()
+        if it >= 2:
+            total += e0.elapsed_time(e1)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    gbytes = 4 * v ** 3
-    alg = 6 * gbytes + 4 * 12 * n + 64 * n + 2 * 4 * v * v
-    return {"N": n, "V": v, "ms_per_step": ms, "proj_per_s": B / (ms * 1e-3), "alg_bytes_per_proj": alg,
-            "alg_GBps": alg * B / (ms * 1e-3) / 1e9}
+    del g, pipe
+    torch.cuda.empty_cache()
+    return total / steps
 
 
 def main():
-    out = []
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--cpu", action="store_true", help="time the CPU port beside every cell (rank 0, B = 4 sample)")
+    args = ap.parse_args()
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    bench._quiet_stdout()
+    rank, local_rank, world = D.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    flush = bench.L2Flush(dev, "write+read")
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    threads = bench.pick_threads() if (args.cpu and rank == 0) else None
+    cells = []
     for v in (32, 64, 128):
         for n in (2000, 8000, 16000, 32000):
-            r = run(n, v)
-            out.append(r)
-            print(r, flush=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)
+            ms = run_cell(dev, n, v, args.steps, flush, rank)
+            ms = D.reduce_scalar(ms, "max", dev)
+            alg = 6 * 4 * v ** 3 + 4 * 12 * n + 64 * n + 2 * 4 * v * v
+            cell = {"N": n, "V": v, "B_per_gpu": bench.B, "ms_per_step": ms, "proj_per_s": world * bench.B / (ms * 1e-3),
+                    "alg_bytes_per_proj": alg, "alg_GBps_per_gpu": alg * bench.B / (ms * 1e-3) / 1e9,
+                    "frac": alg * bench.B / (ms * 1e-3) / 1e9 / peak,
+                    "smoothing_kernels": "tcgen05 pipelines" if v == 64 else "FFMA2 (CUDA cores)"}
+            if threads is not None:
+                total, k = bench.time_oracle(4, 2, 1, threads)
+                cell["cpu_port_proj_per_s"] = 4 * k / total
+                cell["cpu_cores"] = threads
+            cells.append(cell)
+            if rank == 0:
+                print(cell, file=sys.stderr, flush=True)
+    if rank == 0:
+        bench.emit({"workload": "config 5 sweep: fused fwd+bwd, B=32 per GPU, K=21, sigma_rel=3, DRC, graph replay, L2 evicted between steps",
+                    "n_gpus": world, "scaling": "weak", "hbm_peak_gbs": peak, "cells": cells})
+    D.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
