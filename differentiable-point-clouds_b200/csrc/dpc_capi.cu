@@ -623,6 +623,18 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   return DPC_OK;
 }
 
+int dpc_tap_corr(const float* a, const float* g, int axis, int B, int Vz, int V, int K, int pad_lo, float* out, void* stream) {
+  if (!a || !g || !out) return DPC_ERR_NULL;
+  if (!shape_ok(B, Vz, V) || K < 1 || K > DPC_MAX_TAPS) return DPC_ERR_SHAPE;
+  if (axis < 0 || axis > 2 || pad_lo < 0 || pad_lo >= K) return DPC_ERR_ARG;
+  const long long nvox = (long long)B * Vz * V * V;
+  DPC_CUDA(cudaMemsetAsync(out, 0, (size_t)K * 4, (cudaStream_t)stream));
+  const long long ctas = (nvox + DPC_TAPCORR_CHUNK - 1) / DPC_TAPCORR_CHUNK;
+  if (ctas > 2147483647LL) return DPC_ERR_SHAPE;
+  DPC_LAUNCH(dpc_tap_corr_kernel, dim3((unsigned)ctas), dim3(DPC_TAPCORR_THREADS), 0, stream, a, g, axis, nvox, Vz, V, K, pad_lo, out);
+  return dpc_check_launch();
+}
+
 int dpc_dropout_indices(unsigned long long seed, unsigned long long draw, const unsigned long long* state,
                         int B, int N, int n_keep, int32_t* sel, void* stream) {
   if (!sel) return DPC_ERR_NULL;

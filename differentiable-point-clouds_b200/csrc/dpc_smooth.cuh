@@ -315,3 +315,45 @@ dpc_conv_z_bwd_kernel(DpcConvZBwdArgs a) {
     }
   }
 }
+
+// ------------------------------------------------------------------------------ N1: dL/d(taps), hence dL/d(sigma)
+// out[j] += sum over voxels of g[pos] * a[pos + (j - pad_lo) along `axis`]   (a taken as 0 outside the grid):
+// the gradient of a zero-padded correlation  out = corr(a, taps)  w.r.t. its taps, given g = dL/d(out).  sigma is a
+// pure function of the step in the reference (model_pc.py:35-40) and nothing there consumes dL/dsigma, so this is an
+// optional output off the hot path (the composed route of util/point_cloud.py uses it when the taps require a gradient).
+// axis: 0 = depth, 1 = y, 2 = x.  One CTA = DPC_TAPCORR_CHUNK consecutive voxels; per tap: thread partial -> warp
+// shuffle -> shared memory -> one atomicAdd per CTA and tap.
+#define DPC_TAPCORR_THREADS 256
+#define DPC_TAPCORR_CHUNK 4096
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(DPC_TAPCORR_THREADS)
+#else
+static void
+#endif
+dpc_tap_corr_kernel(const float* a, const float* g, int axis, long long nvox, int Vz, int V, int K, int pad_lo, float* out) {
+  __shared__ float part[DPC_TAPCORR_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long first = (long long)blockIdx.x * DPC_TAPCORR_CHUNK;
+  const int len = axis == 0 ? Vz : V;
+  const long long stride = axis == 0 ? (long long)V * V : (axis == 1 ? V : 1);
+  dpc_grid_dep_wait();
+  for (int j = 0; j < K; ++j) {
+    const int off = j - pad_lo;
+    float s = 0.0f;
+    for (int i = tid; i < DPC_TAPCORR_CHUNK; i += DPC_TAPCORR_THREADS) {
+      const long long pos = first + i;
+      if (pos >= nvox) break;
+      const int c = (int)((pos / stride) % len) + off;        // coordinate along the axis of the shifted read
+      if (c >= 0 && c < len) s = fmaf(g[pos], a[pos + (long long)off * stride], s);
+    }
+    s = dpc_warp_sum(s);
+    if (lane == 0) part[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.0f;
+      for (int w = 0; w < DPC_TAPCORR_THREADS / 32; ++w) t += part[w];
+      atomicAdd(out + j, t);
+    }
+    __syncthreads();
+  }
+}

@@ -13,8 +13,9 @@ outputs, picks the fused or the composed route and wires autograd.  There is no 
 
 Differences a caller can observe (all documented in DESIGN.md):
   * a coordinate of exactly +0.5 is dropped like TF-GPU does (TF-CPU raises);
-  * gradients w.r.t. the smoothing taps (i.e. dL/dsigma) are not produced -- sigma is a pure
-    function of the step counter in the reference (model_pc.py:35-40), nothing consumes it;
+  * gradients w.r.t. the smoothing taps (i.e. dL/dsigma) are produced when the kernel's tensors require them
+    (sigma.requires_grad); the call then takes the composed route (separate kernels) -- sigma is a pure
+    function of the step counter in the reference (model_pc.py:35-40), nothing there consumes it;
   * `pc_point_dropout` draws its subsets on the device (`dropout_indices`: a keyed pseudo-random permutation per
     sample, no sort) instead of np.random.choice on the host; the gather itself is identical.
 Extension (a superset of the reference signature): `pointcloud_project_fast(..., point_indices=sel)` consumes a dropout
@@ -115,6 +116,18 @@ def _dev_taps(t, device):
     return t if t.device == device else t.to(device)
 
 
+def _taps_need_grad(kernel):
+    return kernel is not None and any(torch.is_tensor(k) and k.requires_grad for k in kernel)
+
+
+def _grad_taps(kernel, device):
+    """(tx, ty, tz) as 1-D fp32 tensors on `device` that stay connected to autograd (sigma -> taps), for _SmoothFn."""
+    if _taps_need_grad(kernel):
+        return tuple(_dev_taps(k.reshape(-1).to(torch.float32), device).contiguous() for k in kernel)
+    tx, ty, tz, _ = _split_kernel(kernel, device)
+    return _dev_taps(tx, device), _dev_taps(ty, device), _dev_taps(tz, device)
+
+
 # --------------------------------------------------------------------------- K1: transform + splat
 class _SplatFn(torch.autograd.Function):
     """(pc, pose, trans, focal, rgb) -> (tr_pc, vox, vox_rgb) through dpc_splat_fwd/bwd."""
@@ -201,8 +214,17 @@ def _conv_xy(L, x, tx, ty, plx, ply, clip_in=False, mask_out=None, mask_in=None)
     return out
 
 
+def _tap_corr(L, a, g, axis, k, pad_lo):
+    """dL/d(taps) of one zero-padded correlation pass: a = its input, g = the gradient at its output (dpc_tap_corr)."""
+    b, vz, v = a.shape[0], a.shape[1], a.shape[2]
+    out = torch.empty(k, dtype=torch.float32, device=a.device)
+    check(L.dpc_tap_corr(ptr(a), ptr(g), axis, b, vz, v, k, pad_lo, ptr(out), stream_of(a)))
+    return out
+
+
 class _SmoothFn(torch.autograd.Function):
-    """[B,Vz,V,V] -> same: correlate along x, then y, then depth (point_cloud.py:141-142)."""
+    """[B,Vz,V,V] -> same: correlate along x, then y, then depth (point_cloud.py:141-142).  Differentiable w.r.t. the
+    grid and -- when a tap tensor requires a gradient, i.e. when sigma does -- w.r.t. the taps of every pass (N1)."""
 
     @staticmethod
     def forward(ctx, vox, tx, ty, tz):
@@ -214,23 +236,38 @@ class _SmoothFn(torch.autograd.Function):
         kz = tz.numel()
         check(L.dpc_conv_z_fwd(ptr(tmp), ptr(tz), kz, (kz - 1) // 2, None, PROJ_NONE, 0.0, 0.0, 0.0, 0, b, vz, v,
                                ptr(out), None, None, None, None, stream_of(vox)))
-        ctx.save_for_backward(tx, ty, tz)
+        want_taps = any(ctx.needs_input_grad[1:4])
+        ctx.want_taps = want_taps
+        # the tap gradients need the input of every pass: the grid itself and the x/y-smoothed grid (the x-smoothed one
+        # is recomputed in the backward)
+        ctx.save_for_backward(tx, ty, tz, *((vox, tmp) if want_taps else ()))
         return out
 
     @staticmethod
     def backward(ctx, g):
         L = _capi.lib()
-        tx, ty, tz = ctx.saved_tensors
+        tx, ty, tz = ctx.saved_tensors[:3]
         g = f32c(g)
         b, vz, v = g.shape[0], g.shape[1], g.shape[2]
         rx, ry, rz = tx.flip(0).contiguous(), ty.flip(0).contiguous(), tz.flip(0).contiguous()
         kx, ky, kz = tx.numel(), ty.numel(), tz.numel()
-        tmp = torch.empty_like(g)
+        h2 = torch.empty_like(g)
         # mode NONE: the "voxels" operand is never read for values, only d(out) = g flows
         check(L.dpc_conv_z_bwd(ptr(g), None, None, ptr(rz), kz, kz - 1 - (kz - 1) // 2, PROJ_NONE, 0.0, 0.0, 0.0, 0,
-                               b, vz, v, None, ptr(g), None, None, ptr(tmp), None, stream_of(g)))
-        d = _conv_xy(L, tmp, rx, ry, kx - 1 - (kx - 1) // 2, ky - 1 - (ky - 1) // 2)
-        return d, None, None, None
+                               b, vz, v, None, ptr(g), None, None, ptr(h2), None, stream_of(g)))
+        if not ctx.want_taps:
+            d = _conv_xy(L, h2, rx, ry, kx - 1 - (kx - 1) // 2, ky - 1 - (ky - 1) // 2)
+            return d, None, None, None
+        a0, a2 = ctx.saved_tensors[3:5]
+        one = torch.ones(1, dtype=torch.float32, device=g.device)          # a 1-tap identity filter
+        a1 = _conv_xy(L, a0, tx, one, (kx - 1) // 2, 0)                      # input of the y pass
+        gx = _conv_xy(L, h2, one, ry, 0, ky - 1 - (ky - 1) // 2)             # gradient at the output of the x pass
+        d = _conv_xy(L, gx, rx, one, kx - 1 - (kx - 1) // 2, 0)
+        need = ctx.needs_input_grad
+        dtz = _tap_corr(L, a2, g, 0, kz, (kz - 1) // 2) if need[3] else None
+        dty = _tap_corr(L, a1, h2, 1, ky, (ky - 1) // 2) if need[2] else None
+        dtx = _tap_corr(L, a0, gx, 2, kx, (kx - 1) // 2) if need[1] else None
+        return d, dtx, dty, dtz
 
 
 def smoothen_voxels3d(cfg, voxels, kernel):
@@ -241,18 +278,18 @@ def smoothen_voxels3d(cfg, voxels, kernel):
     if voxels.dim() != 5 or voxels.shape[-1] != 1:
         raise ValueError("voxels must be [B,Vz,V,V,1]")
     dev = voxels.device
-    tx, ty, tz, _ = _split_kernel(kernel, dev)
-    out = _SmoothFn.apply(voxels.squeeze(-1), _dev_taps(tx, dev), _dev_taps(ty, dev), _dev_taps(tz, dev))
+    tx, ty, tz = _grad_taps(kernel, dev)
+    out = _SmoothFn.apply(voxels.squeeze(-1), tx, ty, tz)
     return out.unsqueeze(-1)
 
 
 def convolve_rgb(cfg, voxels_rgb, kernel):
     """[B,Vz,V,V,3] -> same: each colour channel smoothed separately (point_cloud.py:148-154)."""
     dev = voxels_rgb.device
-    tx, ty, tz, _ = _split_kernel(kernel, dev)
+    tx, ty, tz = _grad_taps(kernel, dev)
     b = voxels_rgb.shape[0]
     chans = voxels_rgb.permute(4, 0, 1, 2, 3).reshape((3 * b,) + tuple(voxels_rgb.shape[1:4])).contiguous()
-    out = _SmoothFn.apply(chans, _dev_taps(tx, dev), _dev_taps(ty, dev), _dev_taps(tz, dev))
+    out = _SmoothFn.apply(chans, tx, ty, tz)
     return out.reshape((3, b) + tuple(voxels_rgb.shape[1:4])).permute(1, 2, 3, 4, 0).contiguous()
 
 
@@ -464,7 +501,7 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation,
     if point_indices is not None:
         if point_indices.dim() != 2 or point_indices.shape[0] != b or point_indices.shape[1] > n:
             raise ValueError("point_indices must be [B,k] with k <= N")
-        if all_rgb is not None or not _fused_supported(cfg, point_cloud, None):
+        if all_rgb is not None or not _fused_supported(cfg, point_cloud, None) or _taps_need_grad(kernel):
             # routes without an indexed load stage: materialise the subset first (the reference's own order of operations)
             point_cloud, all_rgb = pc_point_dropout(point_cloud, all_rgb, None, selected_indices=point_indices)
         else:
@@ -483,6 +520,10 @@ def pointcloud_project_fast(cfg, point_cloud, transform, predicted_translation,
         parts = (_dev_taps(tx, dev), _dev_taps(ty, dev), _dev_taps(tz, dev), shared)
         host_xy = getattr(kernel, "host_taps_xy", None)
         host_z = getattr(kernel, "host_taps_z", None)
+    if _taps_need_grad(kernel):
+        # N1, dL/dsigma: the composed route (its smoothing Function returns the gradients of the taps of every pass)
+        return _project_composed(cfg, point_cloud, transform, predicted_translation, all_rgb, kernel,
+                                 _grad_taps(kernel, dev) + (False,), scaling_factor, focal_length)
     if all_rgb is None and _fused_supported(cfg, point_cloud, parts):
         params = ProjectParams(B=b, N=n, Vz=vz, V=v, pose_kind=_pose_kind(cfg), mode=_proj_mode(cfg),
                                K=parts[0].numel() if parts else 0, Kz=parts[2].numel() if parts else 0,

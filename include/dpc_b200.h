@@ -211,6 +211,13 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                          float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_scale,
                          void* scratch, int64_t scratch_bytes, const void* saved, int64_t saved_bytes, void* stream);
 
+/* ---- N1: gradient of a zero-padded correlation w.r.t. its taps, out[j] = sum_pos g[pos] * a[pos + (j - pad_lo) along
+ * axis] (axis 0 = depth, 1 = y, 2 = x; a = the pass's input, g = the gradient at its output, both [B,Vz,V,V]).  With the
+ * closed form of d taps / d sigma (gauss_kernel.py:5-11) this gives dL/dsigma of smoothen_voxels3d
+ * (point_cloud.py:139-145); out [K] is zeroed by the callee.  Optional, off the hot path: sigma is a function of the
+ * step count in the reference and nothing consumes its gradient. */
+int dpc_tap_corr(const float* a, const float* g, int axis, int B, int Vz, int V, int K, int pad_lo, float* out, void* stream);
+
 /* ---- f-2: the subsets of pc_point_dropout (point_cloud.py:296-311: np.random.choice(N, n_keep, replace=False) per
  * sample, on the host, through tf.py_func) drawn on the device: sel[b, i] = pi_b(i), i < n_keep, with pi_b a pseudo-random
  * permutation of [0, N) (Feistel network keyed by Philox4x32-10 of (b, draw) under `seed`).  Distinct by construction, no
