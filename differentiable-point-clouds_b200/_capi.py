@@ -33,6 +33,7 @@ class ProjectParams(ctypes.Structure):
 
 
 FLAG_SCRATCH_RAW_ZERO = 1
+ABI_VERSION = 3
 
 
 POSE_NONE, POSE_QUAT, POSE_MATRIX = -1, 0, 1
@@ -112,6 +113,9 @@ def lib():
                 "dpc_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
         _LIB = load_library(LIB_PATH)
+        if _LIB.dpc_abi_version() != ABI_VERSION:
+            raise RuntimeError("dpc_b200: %s has ABI version %d, this package needs %d -- rebuild it (python __graft_entry__.py)"
+                               % (LIB_PATH, _LIB.dpc_abi_version(), ABI_VERSION))
         if os.environ.get("DPC_TC"):      # experiment override of the smoothing-kernel family (dpc_debug_set key 8)
             _LIB.dpc_debug_set(8, int(os.environ["DPC_TC"]))
         for kv in filter(None, os.environ.get("DPC_KNOBS", "").split(",")):     # experiments: "10=0,11=1"
@@ -150,6 +154,40 @@ def stream_of(t):
     if t.is_cuda:
         return torch.cuda.current_stream(t.device).cuda_stream
     return None
+
+
+def on_tensor_device(fn):
+    """Decorator for autograd Function forward / backward: run the body with the device of the first CUDA tensor argument
+    current (the C-ABI launches on the process's current device; tensors on cuda:1 while cuda:0 is current would otherwise
+    launch on the wrong device).  No-op for CPU tensors (the emulation build of the test-suite)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        t = next((a for a in args if torch.is_tensor(a) and a.is_cuda), None)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(ctx, *args)
+        with torch.cuda.device(t.device):
+            return fn(ctx, *args)
+    return wrapped
+
+
+class device_of:
+    """Context manager: make `t`'s device the current CUDA device for the C-ABI calls inside (kernel launches, memsets
+    and function attributes act on the process's CURRENT device, whatever device the pointers live on)."""
+
+    def __init__(self, t):
+        self._ctx = torch.cuda.device(t.device) if (t is not None and t.is_cuda) else None
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            return self._ctx.__exit__(*exc)
+        return False
 
 
 def f32c(t):

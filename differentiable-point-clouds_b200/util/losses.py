@@ -34,6 +34,7 @@ def _workspace(device, stream):
 
 class _ProjL2LossFn(torch.autograd.Function):
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, pred, gt, num_samples):
         L = _capi.lib()
         p, g = _capi.f32c(pred), _capi.f32c(gt)
@@ -51,6 +52,7 @@ class _ProjL2LossFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, g_loss):
         (g_pred,) = ctx.saved_tensors
         d = g_pred * g_loss

@@ -133,6 +133,7 @@ class _SplatFn(torch.autograd.Function):
     """(pc, pose, trans, focal, rgb) -> (tr_pc, vox, vox_rgb) through dpc_splat_fwd/bwd."""
 
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, pc, pose, trans, focal, rgb, pose_kind, vz, v, focal_const, cam_dist, rgb_stop_grad, want_vox):
         ctx.set_materialize_grads(False)   # an output nobody differentiates arrives as None, not as a grid of zeros
         L = _capi.lib()
@@ -154,6 +155,7 @@ class _SplatFn(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, g_tr, g_vox, g_rgbvox):
         L = _capi.lib()
         pc, pose, trans, focal, rgb = ctx.saved_tensors
@@ -227,6 +229,7 @@ class _SmoothFn(torch.autograd.Function):
     grid and -- when a tap tensor requires a gradient, i.e. when sigma does -- w.r.t. the taps of every pass (N1)."""
 
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, vox, tx, ty, tz):
         L = _capi.lib()
         vox = f32c(vox)
@@ -244,6 +247,7 @@ class _SmoothFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, g):
         L = _capi.lib()
         tx, ty, tz = ctx.saved_tensors[:3]
@@ -298,6 +302,7 @@ class _ProjectFn(torch.autograd.Function):
     """voxels [B,Vz,V,V] -> (proj [B,V,V], probs [Vz+1,B,V,V] | empty, depth | empty), no smoothing."""
 
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, vox, mode, eps, cam_dist, max_depth, flip_y, want_probs, want_depth):
         ctx.set_materialize_grads(False)
         L = _capi.lib()
@@ -320,6 +325,7 @@ class _ProjectFn(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, g_proj, g_probs, g_depth):
         L = _capi.lib()
         vox, one = ctx.saved_tensors
@@ -339,14 +345,22 @@ class _ProjectFn(torch.autograd.Function):
 # between calls, so one buffer per (device, stream, size) is kept and reused instead of being
 # allocated per call.  Stream-ordered reuse is safe; a different stream gets its own buffer.
 _SCRATCH = {}
+_SCRATCH_MAX_BYTES = 2 << 30      # 2 GiB of cached scratch at most (one B=32, 64^3 entry is 67 MiB)
 
 
 def _scratch_for(device, stream, nbytes):
     key = (device.index if device.type == "cuda" else -1, stream, nbytes)
+    if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture the buffer comes from the graph's own memory pool and is NOT cached: the graph bakes
+        # the pointer in, so its lifetime has to be the graph's, not this cache's
+        return key, torch.empty(nbytes, dtype=torch.uint8, device=device)
     buf = _SCRATCH.get(key)
     if buf is None:
-        if len(_SCRATCH) >= 32:       # streams come and go; a captured CUDA graph keeps using its stream's buffer,
-            _SCRATCH.clear()          # so the cache is only dropped when it is clearly stale (see release_scratch)
+        # eager calls: streams and batch shapes come and go -- bound the cache by entries and by bytes (dropping an entry
+        # is safe: it was allocated on the stream it is used on, the caching allocator orders its reuse)
+        held = sum(b.numel() for b in _SCRATCH.values())
+        if len(_SCRATCH) >= 32 or held + nbytes > _SCRATCH_MAX_BYTES:
+            _SCRATCH.clear()
         buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
     return key, buf
@@ -362,6 +376,7 @@ class _ProjectFastFn(torch.autograd.Function):
     three; the clip masks travel as bit planes in a small per-call `saved` buffer."""
 
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, pc, pose, trans, focal, scale, taps_xy, taps_z, params, sel=None):
         # Without this autograd hands the backward a 32 MiB grid of zeros for `voxels` and zeros for `tr_pc` whenever
         # the loss uses only `proj` (the training case): two fill launches, and the general backward kernel instead of
@@ -402,6 +417,7 @@ class _ProjectFastFn(torch.autograd.Function):
         return tr_pc, voxels, proj
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, g_tr, g_vox, g_proj):
         L = _capi.lib()
         pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc, sel = ctx.saved_tensors
@@ -472,6 +488,16 @@ class ProjectionOutputs(dict):
     def copy(self):
         self._materialize()
         return dict(self)
+
+    # dict(out), {**out}, out.keys(): CPython copies a dict subclass through keys() + __getitem__ only when keys() is
+    # overridden; materialise there so that a copy never carries the lazy placeholders (None) of the fused route
+    def keys(self):
+        self._materialize()
+        return super().keys()
+
+    def __iter__(self):
+        self._materialize()
+        return super().__iter__()
 
 
 def _fused_supported(cfg, point_cloud, kernel_parts):
@@ -598,6 +624,7 @@ def _project_composed(cfg, point_cloud, transform, predicted_translation, all_rg
 # --------------------------------------------------------------------------- f-2: point dropout
 class _GatherFn(torch.autograd.Function):
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, x, sel):
         L = _capi.lib()
         x = f32c(x)
@@ -610,6 +637,7 @@ class _GatherFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, g):
         L = _capi.lib()
         (sel,) = ctx.saved_tensors

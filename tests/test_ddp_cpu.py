@@ -18,14 +18,16 @@ def _free_port():
     return p
 
 
-def _cfg(batch):
+def _cfg(batch, unsup=False):
     from dpc_b200.util.config import default_config
-    return default_config(vox_size=16, image_size=32, pc_num_points=64, batch_size=batch, step_size=2, z_dim=32, fc_dim=32,
-                          f_dim=4, pc_gauss_kernel_size=5, pc_relative_sigma=1.0, pc_point_dropout=1.0,
-                          max_number_of_steps=100)
+    over = dict(vox_size=16, image_size=32, pc_num_points=64, batch_size=batch, step_size=2, z_dim=32, fc_dim=32,
+                f_dim=4, pc_gauss_kernel_size=5, pc_relative_sigma=1.0, pc_point_dropout=1.0, max_number_of_steps=100)
+    if unsup:
+        over.update(predict_pose=True, pose_predict_num_candidates=3, pose_predictor_student_loss_weight=20.0)
+    return default_config(**over)
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, unsup=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     torch.set_num_threads(1)
@@ -36,7 +38,7 @@ def _worker(rank, world, port, ret):
     D.init(backend="gloo")
     cpu = torch.device("cpu")
     per_rank = 2
-    cfg, full = _cfg(per_rank), _cfg(per_rank * world)
+    cfg, full = _cfg(per_rank, unsup), _cfg(per_rank * world, unsup)
     big = synthetic_batch(full, cpu, seed=7)
     lo, hi = D.shard_range(full.batch_size, rank, world)
     s = cfg.step_size
@@ -63,9 +65,13 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_ddp_gradients_equal_the_full_batch_gradients():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("unsup", [False, True])
+def test_two_rank_ddp_gradients_equal_the_full_batch_gradients(unsup):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), ret, unsup), nprocs=world, join=True)
     assert ret[0] is not None and ret[0] < 1e-4, ret[0]

@@ -74,17 +74,20 @@ def _worker(rank, world, port, name, ret):
     k = int(cfg.pose_predict_num_candidates)
     rows = {"points_1": (lo, hi), "scaling_factor": (lo, hi), "poses": (lo * s * k, hi * s * k), "pose_student": (lo * s, hi * s)}
 
-    def pin(sl):
+    upstream = {}                 # gradients arriving at the pinned predictions: localises a mismatch (renderer vs networks)
+
+    def pin(sl, tag):
         def hook(out):
             for key, (a, b) in rows.items():
                 if out.get(key) is not None:
                     want = pinned[key] if sl is None else pinned[key][a:b]
                     out[key] = _Pin.apply(out[key], want.to(out[key].dtype))
+                    out[key].register_hook(lambda g, key=key: upstream.__setitem__((tag, key), g.detach().clone()))
             return out
         return hook
 
-    tr.model.predict_hook = pin(True)
-    ref.model.predict_hook = pin(None)
+    tr.model.predict_hook = pin(True, "shard")
+    ref.model.predict_hook = pin(None, "full")
     loss = tr._forward_backward(mine)              # includes the NCCL all-reduce of tr.flat_g
     torch.cuda.synchronize()
     res = None
@@ -98,11 +101,29 @@ def _worker(rank, world, port, name, ret):
             g = ref.flat_g[off:off + n]
             worst = max(worst, float(d[off:off + n].abs().max()) / max(1e-12, float(g.abs().max())))
             off += n
+        # the gradients the renderer + losses hand to the networks, rank 0's rows of the full batch vs its own shard
+        # (the full-batch loss is a mean over world x as many samples: scale by world)
+        up = {}
+        for key, (a, b) in rows.items():
+            if ("shard", key) in upstream:
+                gs, gf = upstream[("shard", key)].double(), upstream[("full", key)][a:b].double() * world
+                up[key] = float((gs - gf).abs().max()) / max(1e-30, float(gf.abs().max()))
+        per, off = [], 0
+        for n_, p in ref.model.named_parameters():
+            n = p.numel()
+            g = ref.flat_g[off:off + n]
+            per.append((float(d[off:off + n].abs().max()) / max(1e-12, float(g.abs().max())), n_))
+            off += n
+        per.sort(reverse=True)
         res = {"rel_l2": rel, "worst_param_rel_max": worst, "loss_rank0": float(loss), "loss_full": float(loss_r),
-               "allreduce_bytes": tr.comm_bytes}
+               "allreduce_bytes": tr.comm_bytes, "upstream_rel_max": up, "worst_params": per[:5]}
     D.barrier()
     ret[rank] = res
     dist.destroy_process_group()
+
+
+# (global relative L2, worst parameter relative to its largest element)
+TOL = {"chair_camera_supervision": (1e-4, 1e-3), "chair_unsupervised": (1e-4, 1e-3)}
 
 
 @pytest.mark.parametrize("name", ["chair_camera_supervision", "chair_unsupervised"])
@@ -116,5 +137,5 @@ def test_two_rank_nccl_gradients_equal_the_full_batch_gradients(name):
     print(name, r)
     assert r is not None
     assert r["allreduce_bytes"] > 100e6
-    assert r["rel_l2"] <= 1e-4, r
-    assert r["worst_param_rel_max"] <= 1e-3, r
+    assert r["rel_l2"] <= TOL[name][0], r
+    assert r["worst_param_rel_max"] <= TOL[name][1], r
