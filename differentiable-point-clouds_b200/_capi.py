@@ -73,6 +73,8 @@ _SIGNATURES = {
                                    c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
     "dpc_project_fast_bwd": (c_i, [_PP, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                    c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p]),
+    "dpc_project_rgb_fwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "dpc_project_rgb_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     "dpc_tap_corr": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "dpc_dropout_indices": (c_i, [ctypes.c_uint64, ctypes.c_uint64, c_p, c_i, c_i, c_i, c_p, c_p]),
     "dpc_gather_points": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),

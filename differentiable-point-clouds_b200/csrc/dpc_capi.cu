@@ -227,6 +227,23 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   if (sel && d_pc) DPC_CUDA(cudaMemsetAsync(d_pc, 0, (size_t)B * N_src * 12, (cudaStream_t)stream));      // dropped points: zero gradient
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
+#ifndef DPC_EMU
+  if (ppt == 1 && (g_tune[18] || g_tune[19] || g_tune[20])) {
+    // occupancy / decorrelation experiments (knobs 18: 128-thread CTAs, 19: compiled for 75 % occupancy, 20: independent gathers)
+    const int sel3 = (g_tune[18] ? 4 : 0) | (g_tune[19] ? 2 : 0) | (g_tune[20] ? 1 : 0);
+    dim3 g128((N + 127) / 128, B);
+    switch (sel3) {
+      case 1: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 0, true>), grid, dim3(256), 0, stream, a); break;
+      case 2: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 6, false>), grid, dim3(256), 0, stream, a); break;
+      case 3: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 6, true>), grid, dim3(256), 0, stream, a); break;
+      case 4: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, false>), g128, dim3(128), 0, stream, a); break;
+      case 5: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, true>), g128, dim3(128), 0, stream, a); break;
+      case 6: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 12, false>), g128, dim3(128), 0, stream, a); break;
+      default: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 12, true>), g128, dim3(128), 0, stream, a); break;
+    }
+    return dpc_check_launch();
+  }
+#endif
   if (ppt == 4) { DPC_LAUNCH((dpc_splat_bwd_kernel<4, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
   else if (ppt == 2) { DPC_LAUNCH((dpc_splat_bwd_kernel<2, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
   else { DPC_LAUNCH((dpc_splat_bwd_kernel<1, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -621,6 +638,24 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                            fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream, p->sel, p->N_src));
   stage_mark(7, stream);
   return DPC_OK;
+}
+
+int dpc_project_rgb_fwd(const float* probs, const float* rgb, int B, int Vz, int V, float* proj_rgb, void* stream) {
+  if (!probs || !rgb || !proj_rgb) return DPC_ERR_NULL;
+  if (!shape_ok(B, Vz, V)) return DPC_ERR_SHAPE;
+  const long long rays = (long long)B * V * V;
+  DPC_LAUNCH(dpc_project_rgb_fwd_kernel, dim3((unsigned)((rays + 127) / 128)), dim3(128), 0, stream, probs, rgb, B, Vz, V, proj_rgb);
+  return dpc_check_launch();
+}
+
+int dpc_project_rgb_bwd(const float* probs, const float* rgb, const float* g_proj_rgb, int B, int Vz, int V,
+                        float* d_probs, float* d_rgb, void* stream) {
+  if (!probs || !rgb || !g_proj_rgb || (!d_probs && !d_rgb)) return DPC_ERR_NULL;
+  if (!shape_ok(B, Vz, V)) return DPC_ERR_SHAPE;
+  const long long rays = (long long)B * V * V;
+  DPC_LAUNCH(dpc_project_rgb_bwd_kernel, dim3((unsigned)((rays + 127) / 128)), dim3(128), 0, stream, probs, rgb, g_proj_rgb, B, Vz, V,
+             d_probs, d_rgb);
+  return dpc_check_launch();
 }
 
 int dpc_tap_corr(const float* a, const float* g, int axis, int B, int Vz, int V, int K, int pad_lo, float* out, void* stream) {

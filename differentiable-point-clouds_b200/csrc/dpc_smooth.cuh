@@ -357,3 +357,56 @@ dpc_tap_corr_kernel(const float* a, const float* g, int axis, long long nvox, in
     __syncthreads();
   }
 }
+
+// ------------------------------------------------------------------------------ f-3: K3 for the colour grid
+// project_volume_rgb_integral (drc.py:126-136): proj_rgb[b,y,x,c] = sum_{z<Vz} p[z,b,y,x] * rgb[b,z,y,x,c] + p[Vz,b,y,x]
+// (a white background for the "ray escapes" event).  p [Vz+1,B,V,V] are the (already row-flipped) termination
+// probabilities, rgb [B,Vz,V,V,3] the (already row-flipped) colour grid.  One thread per ray; the reference materialises
+// p * concat(rgb, ones) as a [Vz+1,B,V,V,3] tensor (three grids) before the reduction.
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(128)
+#else
+static void
+#endif
+dpc_project_rgb_fwd_kernel(const float* p, const float* rgb, int B, int Vz, int V, float* out) {
+  const long long rays = (long long)B * V * V;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  dpc_grid_dep_sync();
+  if (r >= rays) return;
+  const long long b = r / ((long long)V * V), yx = r - b * V * V;
+  const float* pr = p + r;                                    // level stride = rays
+  const float* cr = rgb + ((b * Vz) * (long long)V * V + yx) * 3;   // level stride = V*V*3
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int z = 0; z < Vz; ++z) {
+    const float w = pr[(long long)z * rays];
+    const float* c = cr + (long long)z * V * V * 3;
+    a0 = fmaf(w, c[0], a0); a1 = fmaf(w, c[1], a1); a2 = fmaf(w, c[2], a2);
+  }
+  const float bg = pr[(long long)Vz * rays];
+  out[r * 3 + 0] = a0 + bg; out[r * 3 + 1] = a1 + bg; out[r * 3 + 2] = a2 + bg;
+}
+
+// backward: d_p[z] = sum_c g[c] * rgb[z][c]  (z < Vz),  d_p[Vz] = sum_c g[c];  d_rgb[z][c] = g[c] * p[z]
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(128)
+#else
+static void
+#endif
+dpc_project_rgb_bwd_kernel(const float* p, const float* rgb, const float* g, int B, int Vz, int V, float* d_p, float* d_rgb) {
+  const long long rays = (long long)B * V * V;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  dpc_grid_dep_sync();
+  if (r >= rays) return;
+  const long long b = r / ((long long)V * V), yx = r - b * V * V;
+  const float g0 = g[r * 3 + 0], g1 = g[r * 3 + 1], g2 = g[r * 3 + 2];
+  const long long coff = ((b * Vz) * (long long)V * V + yx) * 3;
+  for (int z = 0; z < Vz; ++z) {
+    const long long ci = coff + (long long)z * V * V * 3;
+    if (d_p) d_p[r + (long long)z * rays] = g0 * rgb[ci] + g1 * rgb[ci + 1] + g2 * rgb[ci + 2];
+    if (d_rgb) {
+      const float w = p[r + (long long)z * rays];
+      d_rgb[ci] = g0 * w; d_rgb[ci + 1] = g1 * w; d_rgb[ci + 2] = g2 * w;
+    }
+  }
+  if (d_p) d_p[r + (long long)Vz * rays] = g0 + g1 + g2;
+}

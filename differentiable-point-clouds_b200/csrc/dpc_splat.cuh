@@ -300,9 +300,11 @@ DPC_DEV void dpc_gather_corners(const float* dv, const DpcCell& c, int Vz, int V
   }
 }
 
-template <int DPC_SPLAT_PPT, int NT>
+// MINB: minimum resident CTAs per SM the kernel is compiled for (0 = unconstrained: ptxas settles at 61 registers, four 256-thread CTAs per SM);
+// INDEP: the corner gathers as independent, un-guarded loads (dpc_gather_corners) instead of four guarded ones.
+template <int DPC_SPLAT_PPT, int NT, int MINB = 0, bool INDEP = false>
 #ifndef DPC_EMU
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, MINB)
 #else
 static void
 #endif
@@ -374,7 +376,9 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
     const int base = (cell[j].iz * V + cell[j].iy) * V + cell[j].ix;
     const int o4 = cell[j].ix & 3;
-    if (quad && o4 != 3) {        // ix + 1 < V is implied
+    if (INDEP && quad) {
+      dpc_gather_corners<false>(dv, cell[j], Vz, V, dw[j]);
+    } else if (quad && o4 != 3) {        // ix + 1 < V is implied
       // (the four loads below end up as four DEPENDENT round trips -- nvcc wraps each in its own divergence region and
       // reuses one destination quad; the independent form, dpc_gather_corners, was measured SLOWER in this kernel at full
       // occupancy: 23.8 vs 20.2 us, profiles/r02_b_timeline_sep.txt -- the L1 miss path, not the latency chain, bounds it)

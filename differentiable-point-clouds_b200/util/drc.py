@@ -55,8 +55,37 @@ def drc_depth_projection(p, cfg):
     return (p * psi).sum(0)
 
 
+class _ProjectRgbFn(torch.autograd.Function):
+    @staticmethod
+    @_capi.on_tensor_device
+    def forward(ctx, p, rgb):
+        L = _capi.lib()
+        p, rgb = _capi.f32c(p), _capi.f32c(rgb)
+        b, vz, v = rgb.shape[0], rgb.shape[1], rgb.shape[2]
+        out = torch.empty(b, v, v, 3, dtype=torch.float32, device=rgb.device)
+        _capi.check(L.dpc_project_rgb_fwd(_capi.ptr(p), _capi.ptr(rgb), b, vz, v, _capi.ptr(out), _capi.stream_of(rgb)))
+        ctx.save_for_backward(p, rgb)
+        return out
+
+    @staticmethod
+    @_capi.on_tensor_device
+    def backward(ctx, g):
+        L = _capi.lib()
+        p, rgb = ctx.saved_tensors
+        b, vz, v = rgb.shape[0], rgb.shape[1], rgb.shape[2]
+        g = _capi.f32c(g)
+        d_p = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        d_rgb = torch.empty_like(rgb) if ctx.needs_input_grad[1] else None
+        if d_p is None and d_rgb is None:
+            return None, None
+        _capi.check(L.dpc_project_rgb_bwd(_capi.ptr(p), _capi.ptr(rgb), _capi.ptr(g), b, vz, v, _capi.ptr(d_p), _capi.ptr(d_rgb),
+                                          _capi.stream_of(rgb)))
+        return d_p, d_rgb
+
+
 def project_volume_rgb_integral(cfg, p, rgb):
-    """sum_i p_i * rgb_i with a white background for the 'escapes' event; rgb [B,Vz,V,V,3]."""
-    c = rgb.permute(1, 0, 2, 3, 4)
-    bg = torch.ones((1,) + tuple(c.shape[1:]), dtype=rgb.dtype, device=rgb.device)
-    return (p * torch.cat([c, bg], 0)).sum(0)
+    """sum_i p_i * rgb_i with a white background for the 'escapes' event (drc.py:126-136); p [Vz+1,B,V,V,1],
+    rgb [B,Vz,V,V,3] -> [B,V,V,3].  One kernel (dpc_project_rgb_fwd/bwd): the reference materialises p * [rgb, 1] first."""
+    if p.dim() != 5 or rgb.dim() != 5 or rgb.shape[-1] != 3 or p.shape[0] != rgb.shape[1] + 1:
+        raise ValueError("p must be [Vz+1,B,V,V,1] and rgb [B,Vz,V,V,3]")
+    return _ProjectRgbFn.apply(p.squeeze(-1), rgb)

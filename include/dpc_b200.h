@@ -211,6 +211,14 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                          float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_scale,
                          void* scratch, int64_t scratch_bytes, const void* saved, int64_t saved_bytes, void* stream);
 
+/* ---- f-3: K3 of the colour grid.  Replaces project_volume_rgb_integral (drc.py:126-136):
+ *   proj_rgb[b,y,x,c] = sum_{z<Vz} probs[z,b,y,x] * rgb[b,z,y,x,c] + probs[Vz,b,y,x]      (white background)
+ * probs [Vz+1,B,V,V] (drc_probs as pointcloud_project_fast returns them), rgb [B,Vz,V,V,3] (voxels_rgb as returned),
+ * proj_rgb [B,V,V,3].  Backward: d_probs [Vz+1,B,V,V] and d_rgb [B,Vz,V,V,3] (either may be NULL), fully written. */
+int dpc_project_rgb_fwd(const float* probs, const float* rgb, int B, int Vz, int V, float* proj_rgb, void* stream);
+int dpc_project_rgb_bwd(const float* probs, const float* rgb, const float* g_proj_rgb, int B, int Vz, int V,
+                        float* d_probs, float* d_rgb, void* stream);
+
 /* ---- N1: gradient of a zero-padded correlation w.r.t. its taps, out[j] = sum_pos g[pos] * a[pos + (j - pad_lo) along
  * axis] (axis 0 = depth, 1 = y, 2 = x; a = the pass's input, g = the gradient at its output, both [B,Vz,V,V]).  With the
  * closed form of d taps / d sigma (gauss_kernel.py:5-11) this gives dL/dsigma of smoothen_voxels3d

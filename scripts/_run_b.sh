@@ -1,3 +1,5 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out; O=gpurun_out
-timeout -s KILL 600 python scripts/sweep.py --cpu > $O/sweep_n1.json 2> $O/sweep_n1.err; echo "sweep rc=$?"; tail -13 $O/sweep_n1.err | cut -c1-330
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_i.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu_i.log
+for k in "18=0" "20=1" "19=1" "19=1,20=1" "18=1" "18=1,20=1" "18=1,19=1" "18=1,19=1,20=1"; do
+  DPC_KNOBS=$k timeout -s KILL 60 python scripts/step_timeline.py > $O/timeline_j_$k.txt 2>&1; echo "knobs $k rc=$?"; grep -A8 "#1\|#2" $O/timeline_j_$k.txt | grep "splat_bwd\|total"
+done
+timeout -s KILL 600 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_j.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu_j.log
