@@ -14,6 +14,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC_DIR, "libdpc_b200.so")
+# the LAB build of the same sources (-DDPC_EXPERIMENTS): experiment knobs (dpc_debug_set) and the experimental kernels.
+# Loaded only when DPC_LAB=1 is set or a test asks for it (lab_lib()); the package itself always uses the product build.
+LAB_LIB_PATH = os.path.join(CSRC_DIR, "libdpc_b200_lab.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -49,10 +52,8 @@ _SIGNATURES = {
     "dpc_is_cuda_build": (c_i, []),
     "dpc_debug_set": (c_i, [c_i, c_i]),
     "dpc_debug_stage_ms": (c_i, [c_p]),
-    "dpc_debug_trace_read": (c_i, [c_p]),
     "dpc_debug_ktrace_read": (c_i, [c_p]),
-    "dpc_debug_phase_read": (c_i, [c_p]),
-    "dpc_debug_mma_bench": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "dpc_is_lab_build": (c_i, []),
     "dpc_proj_l2_loss_workspace_bytes": (c_i64, []),
     "dpc_proj_l2_loss": (c_i, [c_p, c_p, c_i64, c_f, c_p, c_p, c_p, c_i64, c_p]),
     "dpc_point_cloud_distance_workspace_bytes": (c_i64, [c_i, c_i, c_i]),
@@ -81,18 +82,30 @@ _SIGNATURES = {
     "dpc_gather_points_bwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+# additional exports of the lab build only (diagnostics of the experiments)
+_LAB_SIGNATURES = {
+    "dpc_debug_trace_read": (c_i, [c_p]),
+    "dpc_debug_phase_read": (c_i, [c_p]),
+    "dpc_debug_mma_bench": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+}
 
 
-def build(verbose=False):
-    """Compile csrc/dpc_capi.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+def build(verbose=False, lab=None):
+    """Compile csrc/dpc_capi.cu for sm_100a with nvcc (cross-compiles without a GPU): the product library and (lab=True,
+    or lab=None for both) the lab build with the experiment knobs."""
     src = os.path.join(CSRC_DIR, "dpc_capi.cu")
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
-    return res.stderr if verbose else LIB_PATH
+    out = None
+    for is_lab in ((False, True) if lab is None else (bool(lab),)):
+        path = LAB_LIB_PATH if is_lab else LIB_PATH
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-DDPC_EXPERIMENTS"] if is_lab else []) + ["-o", path, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
+        if not is_lab:
+            out = res.stderr if verbose else path
+    return out if out is not None else LAB_LIB_PATH
 
 
 def _declare(lib):
@@ -104,7 +117,25 @@ def _declare(lib):
 
 
 def load_library(path):
-    return _declare(ctypes.CDLL(path))
+    lib = _declare(ctypes.CDLL(path))
+    if lib.dpc_is_lab_build():
+        for name, (restype, argtypes) in _LAB_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = restype, argtypes
+    return lib
+
+
+_LAB = None
+
+
+def lab_lib():
+    """The lab build (experiment knobs).  Test / experiment infrastructure: nothing in the package calls this."""
+    global _LAB
+    if _LAB is None:
+        if not os.path.isfile(LAB_LIB_PATH):
+            raise RuntimeError("dpc_b200: %s is missing (python __graft_entry__.py builds it)" % LAB_LIB_PATH)
+        _LAB = load_library(LAB_LIB_PATH)
+    return _LAB
 
 
 def lib():
@@ -114,15 +145,16 @@ def lib():
             raise RuntimeError(
                 "dpc_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-        _LIB = load_library(LIB_PATH)
+        lab = os.environ.get("DPC_LAB") == "1" or bool(os.environ.get("DPC_KNOBS"))
+        _LIB = lab_lib() if lab else load_library(LIB_PATH)
         if _LIB.dpc_abi_version() != ABI_VERSION:
             raise RuntimeError("dpc_b200: %s has ABI version %d, this package needs %d -- rebuild it (python __graft_entry__.py)"
                                % (LIB_PATH, _LIB.dpc_abi_version(), ABI_VERSION))
-        if os.environ.get("DPC_TC"):      # experiment override of the smoothing-kernel family (dpc_debug_set key 8)
+        if os.environ.get("DPC_TC"):      # override of the smoothing-kernel family (dpc_debug_set key 8)
             _LIB.dpc_debug_set(8, int(os.environ["DPC_TC"]))
-        for kv in filter(None, os.environ.get("DPC_KNOBS", "").split(",")):     # experiments: "10=0,11=1"
+        for kv in filter(None, os.environ.get("DPC_KNOBS", "").split(",")):     # experiments (lab build): "10=0,11=1"
             k, v = kv.split("=")
-            _LIB.dpc_debug_set(int(k), int(v))
+            check(_LIB.dpc_debug_set(int(k), int(v)))
     return _LIB
 
 

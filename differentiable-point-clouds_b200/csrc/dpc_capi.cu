@@ -7,7 +7,9 @@
 #include "dpc_smooth.cuh"
 #include "dpc_smooth_fast.cuh"
 #include "dpc_smooth_tc.cuh"
+#ifdef DPC_EXPERIMENTS
 #include "dpc_fused_bwd.cuh"
+#endif
 #include "dpc_chamfer.cuh"
 #include "dpc_loss.cuh"
 
@@ -21,8 +23,10 @@ static int dpc_check_launch() {
 #define DPC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_last_cuda_error = (int)e__; return DPC_ERR_CUDA; } } while (0)
 #define DPC_TRY(call) do { int r__ = (call); if (r__ != DPC_OK) return r__; } while (0)
 
-// Experiment knobs (benchmark sweeps only; not part of the stable ABI contract, not thread-safe).
-static int g_tune[24] = {4, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
+// Experiment knobs: mutable in the lab build only (benchmark sweeps; not thread-safe); compile-time constants in the
+// product build, where only the diagnostics switches below can change.
+static int g_diag_stage = 0;     // key 3: CUDA events around every stage of the fused path
+static DPC_KNOB_T g_tune[24] = {4, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] points/thread splat fwd, [1] splat bwd
 // [10] 1 = the raw grid is zeroed by dpc_zero_kernel and the forward splat runs its transform ahead of the grid
 //      dependency (default 0 = cudaMemsetAsync + wait-first splat: the reductions run ~4 us faster behind the driver's
 //      memset than behind a store kernel, profiles/r01_k_step_timeline.txt); [11] 1 = 16-byte red.v4 / gathers in the
@@ -46,7 +50,7 @@ static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2
 static cudaEvent_t g_ev[8];
 static bool g_ev_ready = false;
 static void stage_mark(int i, void* stream) {
-  if (!g_tune[3]) return;
+  if (!g_diag_stage) return;
   if (!g_ev_ready) { for (int k = 0; k < 8; ++k) cudaEventCreate(&g_ev[k]); g_ev_ready = true; }
   cudaEventRecord(g_ev[i], (cudaStream_t)stream);
 }
@@ -54,8 +58,6 @@ static void stage_mark(int i, void* stream) {
 static void stage_mark(int, void*) {}
 #endif
 
-// set by the fused forward right before it calls dpc_splat_fwd: the stream predecessor is the grid-zeroing kernel
-static thread_local int g_splat_early_next = 0;
 
 static bool shape_ok(int B, int Vz, int V) {
   return B >= 1 && B <= 65535 && V >= 1 && V <= DPC_MAX_V && Vz >= 1 && Vz <= DPC_MAX_V;
@@ -82,24 +84,41 @@ int dpc_debug_stage_ms(float* out6) {
 
 int dpc_debug_set(int key, int value) {
   if (key < 0 || key >= 24) return DPC_ERR_ARG;
-  g_tune[key] = value;
-  if (key == 5) dpc_ignore_host_taps = value ? 1 : 0;
-  if (key == 6) dpc_z_tile_cpasync = value ? 1 : 0;
-  if (key == 7) dpc_xy_dbg = value;
+  if (key == 3) { g_diag_stage = value; return DPC_OK; }
 #ifndef DPC_EMU
-  if (key == 8) dpc_tc_enable = value;
-  if (key == 2) { dpc_tcp_pdrain = (value == 1) ? 1 : 0; dpc_tcp_ns3 = (value == 2) ? 1 : 0; }
-  if (key == 9) { int v = value; cudaMemcpyToSymbol(dpc_tcp_trace_on, &v, sizeof(int)); }
+  if (key == 8) { dpc_tc_enable = value; return DPC_OK; }      // kernel family of the 64^3 smoothing passes (tests)
   if (key == 12) {     // (re)arm the per-kernel timeline: minima to ~0, maxima to 0
     unsigned long long init[64];
     for (int i = 0; i < 64; ++i) init[i] = ((i & 3) < 2) ? ~0ull : 0ull;
     cudaMemcpyToSymbol(dpc_kt, init, sizeof(init));
     int v = value; cudaMemcpyToSymbol(dpc_kt_on, &v, sizeof(int));
+    return DPC_OK;
   }
 #endif
+#ifdef DPC_EXPERIMENTS
+  g_tune[key] = value;
+  if (key == 5) dpc_ignore_host_taps = value ? 1 : 0;
+  if (key == 6) dpc_z_tile_cpasync = value ? 1 : 0;
+  if (key == 7) dpc_xy_dbg = value;
+#ifndef DPC_EMU
+  if (key == 2) { dpc_tcp_pdrain = (value == 1) ? 1 : 0; dpc_tcp_ns3 = (value == 2) ? 1 : 0; }
+  if (key == 9) { int v = value; cudaMemcpyToSymbol(dpc_tcp_trace_on, &v, sizeof(int)); }
+#endif
   return DPC_OK;
+#else
+  (void)value;
+  return DPC_ERR_ARG;          // an experiment knob: only the lab build (-DDPC_EXPERIMENTS) has it
+#endif
+}
+int dpc_is_lab_build(void) {
+#ifdef DPC_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
 }
 int dpc_last_cuda_error(void) { return g_last_cuda_error; }
+#ifdef DPC_EXPERIMENTS
 /* diagnostics: copy the 16 x 16 pipeline trace of CTA 0 (clock64 values) to host memory (synchronises) */
 int dpc_debug_trace_read(long long* host_out) {
 #ifndef DPC_EMU
@@ -110,6 +129,7 @@ int dpc_debug_trace_read(long long* host_out) {
   return DPC_ERR_ARG;
 #endif
 }
+#endif  // DPC_EXPERIMENTS
 /* diagnostics: the per-kernel timeline (16 kernels x {first entry, first/last CTA past its dependency, last exit}, ns) */
 int dpc_debug_ktrace_read(unsigned long long* host_out) {
 #ifndef DPC_EMU
@@ -120,6 +140,7 @@ int dpc_debug_ktrace_read(unsigned long long* host_out) {
   return DPC_ERR_ARG;
 #endif
 }
+#ifdef DPC_EXPERIMENTS
 /* diagnostics: per-CTA phase stamps of the splat kernels (2 kernels x 512 CTAs x 8 slots, ns) */
 int dpc_debug_phase_read(unsigned long long* host_out) {
 #ifndef DPC_EMU
@@ -141,6 +162,7 @@ int dpc_debug_mma_bench(long long* out, int nctas, int threads, int reps, int nm
   return DPC_ERR_ARG;
 #endif
 }
+#endif  // DPC_EXPERIMENTS
 int dpc_is_cuda_build(void) {
 #ifdef DPC_EMU
   return 0;
@@ -166,7 +188,8 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
                             const float* focal, float focal_const, float cam_dist, const float* rgb,
                             int B, int N, int Vz, int V,
                             float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
-                            const int32_t* sel, int N_src, void* stream) {
+                            const int32_t* sel, int N_src, void* stream, int early = 0) {
+  // early (lab build): the stream predecessor is a grid-zeroing KERNEL; the splat then transforms ahead of its dependency
   if (!pc) return DPC_ERR_NULL;
   if (sel && (N_src < N || rgb)) return DPC_ERR_ARG;
   if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
@@ -179,7 +202,7 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.pose_kind = pose_kind; a.focal_const = focal_const; a.cam_dist = cam_dist;
   a.B = B; a.N = N; a.Vz = Vz; a.V = V;
   a.tr_pc = tr_pc; a.vox = vox; a.vox_rgb = vox_rgb; a.idx_out = idx_out; a.valid_out = valid_out;
-  a.early = sel ? 0 : g_splat_early_next; g_splat_early_next = 0;
+  a.early = sel ? 0 : early;
   a.red4 = g_tune[11] ? 1 : 0;
   a.sel = sel; a.N_src = N_src;
   const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
@@ -227,7 +250,7 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   if (sel && d_pc) DPC_CUDA(cudaMemsetAsync(d_pc, 0, (size_t)B * N_src * 12, (cudaStream_t)stream));      // dropped points: zero gradient
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
-#ifndef DPC_EMU
+#if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
   if (ppt == 1 && (g_tune[18] || g_tune[19] || g_tune[20])) {
     // occupancy / decorrelation experiments (knobs 18: 128-thread CTAs, 19: compiled for 75 % occupancy, 20: independent gathers)
     const int sel3 = (g_tune[18] ? 4 : 0) | (g_tune[19] ? 2 : 0) | (g_tune[20] ? 1 : 0);
@@ -246,7 +269,12 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
 #endif
   if (ppt == 4) { DPC_LAUNCH((dpc_splat_bwd_kernel<4, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
   else if (ppt == 2) { DPC_LAUNCH((dpc_splat_bwd_kernel<2, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
-  else { DPC_LAUNCH((dpc_splat_bwd_kernel<1, DPC_SPLAT_THREADS>), grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
+  else {
+    // one point per thread in 128-thread CTAs: 20.2 us against 21.1 us with 256-thread CTAs at B=32, N=8000
+    // (profiles/r02_j_splat_bwd_occupancy.md; compiling for more resident CTAs or issuing the gathers independently is slower)
+    dim3 g128((N + 127) / 128, B);
+    DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128>), g128, dim3(128), 0, stream, a);
+  }
   return dpc_check_launch();
 }
 
@@ -504,14 +532,16 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   // gpurun round 7), so the driver's memset stays.
   // Round 8: a zeroing KERNEL again, now as the first half of a PDL pair -- it waits for everything older, lets the
   // splat start, and the splat stages + transforms + writes tr_pc while the grid is being zeroed (knob 10).
+  int splat_early = 0;
   if (!(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO)) {
-#ifndef DPC_EMU
+#if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
     if (g_tune[10] == 2 && ((size_t)g * 4) % 16384 == 0) {
       DPC_LAUNCH(dpc_zero_bulk_kernel, dim3(148 * 2), dim3(128), 0, stream, (unsigned char*)w.raw, (size_t)g * 4);
       DPC_TRY(dpc_check_launch());
-      g_splat_early_next = 1;
+      splat_early = 1;
     } else
 #endif
+#ifdef DPC_EXPERIMENTS
     if (g_tune[10]) {
       const size_t n4 = (size_t)g / 4;
 #ifdef DPC_EMU
@@ -521,14 +551,16 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
 #endif
       DPC_LAUNCH(dpc_zero_kernel, dim3(zgrid), dim3(256), 0, stream, (float4*)w.raw, n4, w.raw + n4 * 4, (int)(g - (int64_t)n4 * 4));
       DPC_TRY(dpc_check_launch());
-      g_splat_early_next = 1;
-    } else {
+      splat_early = 1;
+    } else
+#endif
+    {
       DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
     }
   }
   if (p->sel && p->N_src < p->N) return DPC_ERR_ARG;
   DPC_TRY(splat_fwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
-                           p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, p->sel, p->N_src, stream));
+                           p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, p->sel, p->N_src, stream, splat_early));
   stage_mark(1, stream);
   // clip + x/y smoothing.  With DPC_FLAG_SCRATCH_RAW_ZERO the pass also hands the raw grid back
   // all-zero (so the next forward needs no memset).  Measured on B200 (profiles/r01_d): not a win --
@@ -587,7 +619,7 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   // knob 4 (default): the splat backward runs inside the x/y pass (gather warps next to the pipeline warps) and starts
   // on a sample as soon as that pass has published it (per-sample counters, zeroed by the depth pass like the other targets)
   bool fused_gather = false;
-#ifndef DPC_EMU
+#if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
   fused_gather = fold_scale && p->tr_pc && g_tune[4] && g_tune[15] && !(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO);
 #endif
   if (fold_scale) {
@@ -610,7 +642,7 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                               g_proj, g_voxels, g_probs, g_depth, G, d_scale, stream, hz,
                               fold_scale ? w.part : nullptr, fold_scale ? &z : nullptr));
     stage_mark(5, stream);
-#ifndef DPC_EMU
+#if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
     if (fused_gather) {
       // x/y pass + the gathers in one kernel (dL/d(tr_pc) of every point into scratch), then the chain rule through the
       // camera: the splat backward without a grid to read (d_vox = NULL, d_tr_pc_in = the gathered gradients)

@@ -15,6 +15,16 @@
 
 #include "../../include/dpc_b200.h"
 
+// Experiment knobs (dpc_debug_set) exist only in the LAB build (-DDPC_EXPERIMENTS: libdpc_b200_lab.so, and the CPU
+// emulation build of the test-suite).  In the product build every knob is a compile-time constant (its default), the
+// experimental kernels are not compiled, and the library has no process-wide mutable state besides the two diagnostics
+// switches (stage events, kernel timeline) and the kernel-family selector.
+#ifdef DPC_EXPERIMENTS
+#define DPC_KNOB_T int
+#else
+#define DPC_KNOB_T const int
+#endif
+
 #define DPC_WARP 32
 #define DPC_FULL 0xffffffffu
 

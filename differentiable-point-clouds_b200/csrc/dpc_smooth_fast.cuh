@@ -257,7 +257,7 @@ DPC_DEV void dpc_warp_bulk_rows(float* dst, int dst_pitch, const float* src, siz
 
 // Alternative tile load: the whole CTA copies nrows x 512 B with 16-byte cp.async (LDGSTS), no TMA op
 // per row.  Returns after the data is visible to every thread.
-static int dpc_z_tile_cpasync = 0;   // experiment knob (dpc_debug_set key 6)
+static DPC_KNOB_T dpc_z_tile_cpasync = 0;   // experiment knob (dpc_debug_set key 6)
 DPC_DEV void dpc_cta_cpasync_rows(float* dst, const float* src, size_t src_pitch, int nrows) {
   // rows of 128 floats = 32 chunks of 16 bytes; thread t copies chunk (t & 31) of rows (t >> 5), +8, ...
   const int ch = threadIdx.x & 31;
@@ -658,8 +658,8 @@ dpc_conv_z_fast_bwd_lean_kernel(const DPC_GRID_CONSTANT DpcConvZBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ dispatch
-static int dpc_xy_dbg = 0;           // diagnostics knob (dpc_debug_set key 7)
-static int dpc_ignore_host_taps = 0; // experiment knob (dpc_debug_set key 5): 1 = run the vector-register kernels even when host taps are given
+static DPC_KNOB_T dpc_xy_dbg = 0;           // diagnostics knob (dpc_debug_set key 7)
+static DPC_KNOB_T dpc_ignore_host_taps = 0; // experiment knob (dpc_debug_set key 5): 1 = run the vector-register kernels even when host taps are given
 
 static inline bool dpc_fast_k(int K) { return K == 21 || K == 11; }
 

@@ -561,8 +561,8 @@ static int dpc_tc_sm_count() {
 // Host copy of the taps for the NEXT pipeline launch on this thread (set by the C-ABI layer right before it calls a
 // launcher below, consumed and cleared there); NULL = the kernel reads the device taps.
 static thread_local const float* dpc_tcp_host_taps_next = nullptr;
-static int dpc_tcp_ns3 = 0;         // experiment knob 2 = 2: 3-slot staging ring in the x/y pipeline (what a co-resident CTA would need)
-static int dpc_tcp_pdrain = 0;      // experiment knob 2: the producer warps of the x/y pipeline store the tiles
+static DPC_KNOB_T dpc_tcp_ns3 = 0;         // experiment knob 2 = 2: 3-slot staging ring in the x/y pipeline (what a co-resident CTA would need)
+static DPC_KNOB_T dpc_tcp_pdrain = 0;      // experiment knob 2: the producer warps of the x/y pipeline store the tiles
 static inline DpcTcpTaps dpc_tcp_take_host_taps(int K) {
   DpcTcpTaps ht;
   const float* h = dpc_tcp_host_taps_next;
@@ -601,7 +601,11 @@ static inline int dpc_tc_conv_xy_launch(const float* in, float* out, const float
       return DPC_ERR_CUDA; \
     DPC_LAUNCH((dpc_tcp_conv_xy_kernel<C, MO, MI, PD>), dim3(grid), dim3(DPC_TCP_THREADS), (size_t)(98304 + xy_ns * 32768), stream, a, xymap, K, pl, ntiles, ht, xy_ns); \
     return DPC_OK; } while (0)
+#ifdef DPC_EXPERIMENTS
 #define DPC_TCP_XY_GO(C, MO, MI) do { if (dpc_tcp_pdrain) DPC_TCP_XY_GO1(C, MO, MI, true); else DPC_TCP_XY_GO1(C, MO, MI, false); } while (0)
+#else
+#define DPC_TCP_XY_GO(C, MO, MI) DPC_TCP_XY_GO1(C, MO, MI, false)
+#endif
     switch (sel) {
       case 0: DPC_TCP_XY_GO(false, false, false);
       case 1: DPC_TCP_XY_GO(false, false, true);

@@ -509,7 +509,8 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   }
 }
 
-// ------------------------------------------------------------------------------ grid zeroing
+// ------------------------------------------------------------------------------ grid zeroing (lab build: knob 10)
+#ifdef DPC_EXPERIMENTS
 // Zeroes the raw grid ahead of the splat.  Besides initialising the accumulation target this
 // leaves the grid resident (dirty) in L2, so the splat's reductions hit L2 instead of fetching
 // 32-byte sectors from HBM at random (measured: the splat kernel takes ~10 us longer on a cold grid).
@@ -557,6 +558,8 @@ dpc_zero_bulk_kernel(unsigned char* dst, size_t bytes) {
   dpc_kt_mark(DPC_KT_ZERO, 3);
 }
 #endif
+
+#endif  // DPC_EXPERIMENTS
 
 // Zeroes up to four small accumulation targets (pose / translation / focal / scale gradients) in ONE launch: every
 // stream operation costs ~2.5 us of dependency latency on B200, four cudaMemsetAsync of a few bytes each cost 10 us.

@@ -52,44 +52,50 @@ extern "C" {
 int dpc_abi_version(void);
 const char* dpc_error_string(int code);
 int dpc_last_cuda_error(void);
-/* Experiment / diagnostics knobs used by the benchmark sweeps (not needed in normal use; process-wide,
- * not thread-safe; every value gives the same results -- tests/test_gpu_parity.py::test_splat_variants_full_shape):
+/* Diagnostics switches of the PRODUCT library (process-wide, not thread-safe, off by default; they change no result):
+ *   3      1 = record CUDA events around every stage of the fused forward / backward (dpc_debug_stage_ms)
+ *   8      kernel family of the 64^3 smoothing passes: 0 FFMA2 (CUDA cores), 1 single-tile tcgen05, 2 tcgen05 pipelines
+ *          (default; falls back to 1 when the driver has no tensor-map encoder).  Exists so that the three families can
+ *          be tested behind the same ABI (tests/test_gpu_families.py).
+ *   12     1 = arm the per-kernel timeline (dpc_debug_ktrace_read)
+ * Every other key is an EXPERIMENT knob and exists only in the lab build of the same sources (-DDPC_EXPERIMENTS,
+ * libdpc_b200_lab.so; dpc_is_lab_build() == 1); the product build returns DPC_ERR_ARG for them, compiles their defaults
+ * in as constants and does not contain the experimental kernels.  Lab keys (every value gives the same results --
+ * tests/test_gpu_parity.py::test_splat_variants_full_shape):
  *   0 / 1  points per thread of the forward / backward splat kernel (1|2|4; defaults 4 / 1)
  *   2      1 = the producer warps of the x/y pipeline store the finished tiles; 2 = 3-slot staging ring (default 0)
- *   3      stage events (see dpc_debug_stage_ms)
- *   4      1 = splat backward meant to run co-resident with the x/y pass of the backward: per-sample completion
- *          counters, 3-slot staging ring (default 0; measured slower)
+ *   4      1 = the gathers of the splat backward run inside the x/y pass of the backward (csrc/dpc_fused_bwd.cuh; needs
+ *          dpc_project_params.tr_pc; default 0: measured slower, profiles/r02_f_fused_gather.md); 16 = its debug flags,
+ *          17 = 1: its 768-thread variant
  *   5      1 = ignore host copies of the taps (vector-register FFMA2 kernels / device taps in the pipelines)
  *   6      1 = cp.async tile load in the FFMA2 depth kernels
  *   7      conv_xy (FFMA2) diagnostics: 1 memory path only, 2 arithmetic only, 3 empty CTAs, 4/5 skip the x / y correlation
- *   8      smoothing-kernel family at 64^3: 0 FFMA2, 1 single-tile tcgen05, 2 tcgen05 pipelines (default)
  *   9      1 = per-tile / per-CTA trace of the pipelines (dpc_debug_trace_read)
  *   10     zeroing of the raw grid in the fused forward: 0 cudaMemsetAsync + wait-first splat (default), 1 store kernel,
  *          2 TMA bulk-store kernel -- 1 and 2 as PDL primaries of a splat that transforms ahead of its grid dependency
  *   11     1 = 16-byte reductions / gathers in the splats (default), 0 = 8-byte / scalar
- *   12     1 = arm the per-kernel timeline and the splat phase stamps (dpc_debug_ktrace_read / _phase_read)
  *   13     1 = keep the zeroing launch + dL/dscale atomics in the fused backward (default 0: folded partial sums)
  *   14     1 = the backward splat stages + transforms ahead of its grid dependency (default)
- *   15     1 = x/y pass in place, backward in the raw grid's storage: two grids per step (default) */
+ *   15     1 = x/y pass in place, backward in the raw grid's storage: two grids per step (default)
+ *   18-20  splat backward: 128-thread CTAs / compiled for 75 % occupancy / independent gathers
+ *          (profiles/r02_j_splat_bwd_occupancy.md) */
 int dpc_debug_set(int key, int value);
+int dpc_is_lab_build(void);
 /* diagnostics: after dpc_debug_set(12, 1), every kernel of the fused path folds %globaltimer (ns) into
  * out[4*k + {0: first CTA entry, 1: first CTA past its grid dependency, 2: last CTA past it, 3: last CTA exit}],
  * k = 0 zero, 1 splat fwd, 2 x/y fwd, 3 depth fwd, 4 zero4, 5 depth bwd, 6 x/y bwd, 7 splat bwd; 64 uint64 to host. */
 int dpc_debug_ktrace_read(unsigned long long* host_out);
-/* same switch: thread 0 of every CTA (first 512) of the splat kernels stamps its phases; out[((which * 512 + cta) * 8 + slot],
- * which 0 = forward {entry, points staged, transformed, tr_pc stored, past the dependency, reductions issued},
- * 1 = backward {entry, staged, transformed, past the dependency, gathers issued, chain rule done, d_pc stored}. */
-int dpc_debug_phase_read(unsigned long long* host_out);
 /* key 3 = 1: record CUDA events around every stage of the fused forward/backward; this returns the
  * six stage durations (ms) of the last instrumented step (synchronises on the last event). */
 int dpc_debug_stage_ms(float* out6);
-/* diagnostics: tcgen05.mma issue/latency micro-benchmark; out = 3 int64 per CTA in device memory
- * (cycles per repetition, cycles issuing, cycles waiting for completion). */
+#ifdef DPC_EXPERIMENTS
+/* lab build only.  phase_read: thread 0 of every CTA (first 512) of the splat kernels stamps its phases
+ * (out[((which * 512 + cta) * 8 + slot]); mma_bench: tcgen05.mma issue / latency micro-benchmark (3 int64 per CTA in
+ * device memory); trace_read: per-tile hand-offs of CTA 0 and entry / set-up / exit of every CTA of the pipelines. */
+int dpc_debug_phase_read(unsigned long long* host_out);
 int dpc_debug_mma_bench(long long* out, int nctas, int threads, int reps, int nmma, int spin, int M, int N, void* stream);
-/* diagnostics: dpc_debug_set(9, 1) makes CTA 0 of the persistent depth-pass kernel record clock64() at its
- * pipeline hand-offs (16 events x 16 tiles), and every CTA of the persistent kernels its globaltimer at entry /
- * after set-up / at exit (3 x 160); this copies both tables (256 + 480 int64) to host memory. */
 int dpc_debug_trace_read(long long* host_out);
+#endif
 /* compiled for sm_100a?  1 = real CUDA build, 0 = the CPU emulation build used by tests/emu */
 int dpc_is_cuda_build(void);
 

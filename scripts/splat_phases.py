@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 from dpc_b200 import _capi
+os.environ["DPC_LAB"] = "1"      # lab build: experiment knobs / lab-only diagnostics
 L = _capi.lib()
 dev = torch.device("cuda:0")
 pipe = bench.Pipeline(dev, 0)

@@ -4,6 +4,7 @@ import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dpc_b200 import _capi
+os.environ["DPC_LAB"] = "1"      # lab build: experiment knobs / lab-only diagnostics
 L = _capi.lib()
 dev = torch.device("cuda:0")
 P = _capi.ptr

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_functions():
     text = open(os.path.join(ROOT, "include", "dpc_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"#ifdef DPC_EXPERIMENTS.*?#endif", "", text, flags=re.S)       # lab-only diagnostics
     return sorted(set(re.findall(r"\b(dpc_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -34,6 +35,18 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_is_the_cuda_build_with_sm100a_code(lib):
     assert lib.dpc_is_cuda_build() == 1
+
+
+def test_product_build_has_no_experiment_knobs(lib):
+    """The product library exports the ABI, not the lab: experiment keys are refused, lab-only symbols are absent."""
+    assert lib.dpc_is_lab_build() == 0
+    for key in (0, 1, 2, 4, 5, 10, 11, 13, 14, 15, 16, 18):
+        assert lib.dpc_debug_set(key, 1) == -3
+    for name in ("dpc_debug_mma_bench", "dpc_debug_phase_read", "dpc_debug_trace_read"):
+        assert not hasattr(lib, name), name
+    if os.path.isfile(_capi.LAB_LIB_PATH):
+        lab = _capi.load_library(_capi.LAB_LIB_PATH)
+        assert lab.dpc_is_lab_build() == 1 and hasattr(lab, "dpc_debug_mma_bench")
     assert lib.dpc_abi_version() == 3
     assert lib.dpc_error_string(-2).decode().startswith("unsupported shape")
 

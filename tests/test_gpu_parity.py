@@ -148,16 +148,18 @@ def test_splat_variants_full_shape(knob, value):
     2 = 1 the producer warps of the x/y pipeline store the tiles; 4 = 1 the gathers of the splat backward inside the x/y pass
     of the backward (dpc_fused_bwd.cuh) + chain-rule kernel."""
     from dpc_b200 import _capi
-    L = _capi.lib()
+    L = _capi.lab_lib()             # the experiment knobs exist only in the lab build of the sources
+    product, _capi._LIB = _capi._LIB, L
     default = {2: 0, 4: 0, 10: 0, 11: 1, 13: 0, 14: 1, 15: 1}[knob]
     cfg = default_config(vox_size=64, pc_gauss_kernel_size=21)
-    L.dpc_debug_set(knob, value)
+    _capi.check(L.dpc_debug_set(knob, value))
     try:
         for spread, seed in ((0.5, 1234), (0.025, 1235)):
             pc, q, sc, gt = _bench_inputs(2, 8000, 64, spread, seed=seed)
             _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
     finally:
         L.dpc_debug_set(knob, default)
+        _capi._LIB = product
 
 
 def test_max_projection_full_shape():
