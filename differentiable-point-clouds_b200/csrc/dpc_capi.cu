@@ -653,6 +653,11 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
                                             g_tune[17], stream));
       DPC_TRY(dpc_check_launch());
       stage_mark(6, stream);
+      if (g_tune[17] == 2)       // pricing experiment: pipeline + signalling only, the whole splat backward afterwards
+        DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
+                                 p->B, p->N, p->Vz, p->V, G, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr,
+                                 w.part, 256, d_scale, stream, p->sel, p->N_src));
+      else
       DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
                                p->B, p->N, p->Vz, p->V, nullptr, nullptr, w.d_tr, d_pc, d_pose, d_trans, d_focal, nullptr,
                                w.part, 256, d_scale, stream, p->sel, p->N_src));

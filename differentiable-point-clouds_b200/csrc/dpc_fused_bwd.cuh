@@ -141,7 +141,8 @@ DPC_DEV void dpc_xyg_gather_warp(const DpcXYGatherArgs& g, unsigned target, unsi
 }
 
 // a, xymap, K, pl, ntiles, ht: as dpc_tcp_conv_xy_kernel (always: no input clip, saved clip mask applied to the output).
-// NT = 640 (6 gather warps, pipeline warps at 128 registers) or 768 (10 gather warps, pipeline warps at 112).
+// NT = 640 (6 gather warps, pipeline warps at 128 registers), 768 (10 gather warps, pipeline warps at 112) or 448 (no
+// gather warps, no setmaxnreg: the pipeline + the per-sample signalling alone, to price the signalling).
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 dpc_tcp_conv_xy_gather_kernel(const __grid_constant__ DpcConvXY64Args a, const __grid_constant__ CUtensorMap xymap, int K, int pl,
@@ -152,14 +153,16 @@ dpc_tcp_conv_xy_gather_kernel(const __grid_constant__ DpcConvXY64Args a, const _
   constexpr int NG = NT / 32 - DPC_XYG_G0;
   constexpr int PIPE_REGS = (NT == 640) ? 128 : 112;
   constexpr int START_REGS = (NT == 640) ? 96 : 80;
-  static_assert(12 * PIPE_REGS + (NT / 32 - 12) * DPC_XYG_AUX_REGS <= (NT / 32) * START_REGS, "setmaxnreg: the CTA's launch allocation is the pool");
+  static_assert(NT == 448 || 12 * PIPE_REGS + (NT / 32 - 12) * DPC_XYG_AUX_REGS <= (NT / 32) * START_REGS, "setmaxnreg: the CTA's launch allocation is the pool");
   __shared__ unsigned G_stored;         // number of (consumer warp, tile) stores completed in this CTA
   if (threadIdx.x == 0) G_stored = 0u;
   DPC_TCP_SETUP(a.taps_x, K, pl, a.rev);
-  if (warp < DPC_TCP_ISSUER) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS));
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DPC_XYG_AUX_REGS));
+  if (NT != 448) {
+    if (warp < DPC_TCP_ISSUER) {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PIPE_REGS));
+    } else {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DPC_XYG_AUX_REGS));
+    }
   }
   if (warp < 4) {
     // ---------------- producers: thread = row (slice, y)
@@ -209,7 +212,7 @@ dpc_tcp_conv_xy_gather_kernel(const __grid_constant__ DpcConvXY64Args a, const _
         dst[q * V] = v;
       }
       __syncwarp();
-      if (lane == 0) dpc_red_release_cta_shared(&G_stored, 1u);     // this warp's part of tile j is stored
+      if (lane == 0 && !(g.dbg & 32)) dpc_red_release_cta_shared(&G_stored, 1u);     // this warp's part of tile j is stored
     };
     int i = 0, prev_tile = -1;
     for (int tile = blockIdx.x; tile < ntiles; tile += step, ++i) {
@@ -280,7 +283,7 @@ dpc_tcp_conv_xy_gather_kernel(const __grid_constant__ DpcConvXY64Args a, const _
   } else if (warp == DPC_XYG_SIGNAL) {
     // ---------------- signaller: publish finished tiles.  Every consumer warp stores tile i before tile i+1 and the
     // consumers meet at a named barrier once per tile, so stored >= 8 (i + 1) <=> all eight have stored tile i.
-    if (lane == 0) {
+    if (lane == 0 && !(g.dbg & 32)) {
       int i = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += step, ++i) {
         while (dpc_ld_acquire_cta_shared(&G_stored) < 8u * (unsigned)(i + 1)) __nanosleep(64);
@@ -289,7 +292,7 @@ dpc_tcp_conv_xy_gather_kernel(const __grid_constant__ DpcConvXY64Args a, const _
       }
     }
     __syncwarp();
-  } else {
+  } else if (NG > 0) {
     // ---------------- gather warps
     dpc_xyg_gather_warp(g, 32u, blockIdx.x * NG + (unsigned)(warp - DPC_XYG_G0), gridDim.x * NG);
   }
@@ -312,7 +315,11 @@ static inline int dpc_tcp_conv_xy_gather_launch(float* grid, const float* taps, 
   if (dpc_tc_make_xymap(&xymap, grid, nslices) != DPC_OK) return DPC_ERR_CUDA;
   dpc_tcp_host_taps_next = host_taps;
   const DpcTcpTaps ht = dpc_tcp_take_host_taps(taps ? K : 0);
-  if (wide) {
+  if (wide == 2) {     // experiment: no gather warps -- the caller runs the splat backward as its own kernel afterwards
+    if (cudaFuncSetAttribute(dpc_tcp_conv_xy_gather_kernel<448>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess)
+      return DPC_ERR_CUDA;
+    DPC_LAUNCH(dpc_tcp_conv_xy_gather_kernel<448>, dim3(grid_x), dim3(448), (size_t)DPC_TCP_SMEM_BYTES, stream, a, xymap, K, pl, ntiles, ht, g);
+  } else if (wide) {
     if (cudaFuncSetAttribute(dpc_tcp_conv_xy_gather_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_TCP_SMEM_BYTES) != cudaSuccess)
       return DPC_ERR_CUDA;
     DPC_LAUNCH(dpc_tcp_conv_xy_gather_kernel<768>, dim3(grid_x), dim3(768), (size_t)DPC_TCP_SMEM_BYTES, stream, a, xymap, K, pl, ntiles, ht, g);
