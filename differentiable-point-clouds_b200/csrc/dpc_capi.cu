@@ -8,6 +8,7 @@
 #include "dpc_smooth_fast.cuh"
 #include "dpc_smooth_tc.cuh"
 #ifdef DPC_EXPERIMENTS
+#include "dpc_smooth_fused.cuh"
 #include "dpc_fused_bwd.cuh"
 #endif
 #include "dpc_chamfer.cuh"
@@ -188,7 +189,7 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
                             const float* focal, float focal_const, float cam_dist, const float* rgb,
                             int B, int N, int Vz, int V,
                             float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
-                            const int32_t* sel, int N_src, void* stream, int early = 0) {
+                            const int32_t* sel, int N_src, void* stream, int early = 0, unsigned* zero_u32 = nullptr, int n_zero = 0) {
   // early (lab build): the stream predecessor is a grid-zeroing KERNEL; the splat then transforms ahead of its dependency
   if (!pc) return DPC_ERR_NULL;
   if (sel && (N_src < N || rgb)) return DPC_ERR_ARG;
@@ -205,6 +206,7 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.early = sel ? 0 : early;
   a.red4 = g_tune[11] ? 1 : 0;
   a.sel = sel; a.N_src = N_src;
+  a.zero_u32 = zero_u32; a.n_zero = n_zero;
   const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH(dpc_splat_fwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -559,8 +561,17 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
     }
   }
   if (p->sel && p->N_src < p->N) return DPC_ERR_ARG;
+  // x/y + depth pass as ONE persistent kernel (dpc_smooth_fused.cuh) when the three passes share one tap vector
+  bool fused_xyz = false;
+#if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
+  // lab knob 21; measured (profiles/r02_m_fused_fwd.md): correct, no gain -- the boundary it removes is worth ~1.4 us and the
+  // in-kernel signalling + phase barrier cost more
+  fused_xyz = g_tune[21] && !splat_early && dpc_tc_level() == 2 && p->V == 64 && p->Vz == 64 && K == Kz && tx == tz && hxy == hz &&
+              !(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) && g_tune[15] && !drc_probs && !proj_depth;
+#endif
   DPC_TRY(splat_fwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
-                           p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, p->sel, p->N_src, stream, splat_early));
+                           p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, p->sel, p->N_src, stream, splat_early,
+                           fused_xyz ? w.cnt : nullptr, p->B));
   stage_mark(1, stream);
   // clip + x/y smoothing.  With DPC_FLAG_SCRATCH_RAW_ZERO the pass also hands the raw grid back
   // all-zero (so the next forward needs no memset).  Measured on B200 (profiles/r01_d): not a win --
@@ -568,6 +579,20 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   // so the default path keeps the memset and leaves the flag to callers that want it.
   // In place unless the caller wants the raw grid handed back zeroed: every x/y tile is a pair of whole depth slices,
   // read completely before it is written, so the pass can overwrite its input -- one 32 MiB grid less per step in L2.
+#if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
+  if (fused_xyz) {
+    DpcConvZArgs az;
+    dpc_set_taps_z(&az.ht, &az.use_ht, nullptr, 0, 0);
+    az.in = w.raw; az.taps = tz; az.K = Kz; az.pl = (Kz - 1) / 2; az.rev = 0; az.scale = scale; az.mode = p->mode; az.eps = p->clip_eps;
+    az.cam_dist = p->cam_dist; az.max_depth = p->max_depth; az.flip_y = 1; az.B = p->B; az.Vz = p->Vz; az.V = p->V; az.TY = 2;
+    az.vox_out = voxels; az.mask2_out = scale ? sv.mask2 : nullptr; az.proj = proj; az.probs = nullptr; az.depth = nullptr;
+    DPC_TRY(dpc_tcp_fwd_xyz_launch(w.raw, tx, K, (K - 1) / 2, sv.mask1, hxy, az, w.cnt, stream));
+    DPC_TRY(dpc_check_launch());
+    stage_mark(2, stream);
+    stage_mark(3, stream);
+    return DPC_OK;
+  }
+#endif
   float* xy_out = ((p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) || !g_tune[15]) ? w.tmp : w.raw;
   DPC_TRY(launch_conv_xy(w.raw, xy_out, tx, K, (K - 1) / 2, tx, K, (K - 1) / 2,
                          p->B, p->Vz, p->V, /*clip_in=*/1, sv.mask1, nullptr, /*rev=*/0,

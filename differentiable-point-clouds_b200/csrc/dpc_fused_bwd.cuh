@@ -41,19 +41,6 @@ struct DpcXYGatherArgs {
   int dbg;                   // experiments (dpc_debug_set(16, .)): 1 = do not wait, 2 = no gathers, 4 = gather warps idle, 8 = no fence
 };
 
-DPC_DEV unsigned dpc_ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-DPC_DEV unsigned dpc_ld_acquire_cta_shared(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(dpc_tc_s32(p)) : "memory");
-  return v;
-}
-DPC_DEV void dpc_red_release_cta_shared(unsigned* p, unsigned v) {
-  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(dpc_tc_s32(p)), "r"(v) : "memory");
-}
 DPC_DEV void dpc_xyg_stamp(int id, int slot, bool leader) {
   if (leader && dpc_kt_on) {
     unsigned long long t;

@@ -84,6 +84,22 @@ DPC_DEV void dpc_tcp_put_a(uint32_t tmem, int s, int h, const float* v) {
   dpc_tc_split_st32(lane_t + DPC_TCP_AHI(s) + 32u * (uint32_t)h, lane_t + DPC_TCP_ALO(s) + 32u * (uint32_t)h, v);
 }
 
+// ---- cross-CTA hand-over inside a persistent kernel (per-sample completion counters): the consumer warps of a CTA count
+// their finished tile stores in shared memory (release at CTA scope), ONE thread with no stores of its own turns that into
+// a GPU-scope release (fence + atomic on the sample's counter in global memory) and the readers acquire-poll it.
+DPC_DEV unsigned dpc_ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DPC_DEV unsigned dpc_ld_acquire_cta_shared(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(dpc_tc_s32(p)) : "memory");
+  return v;
+}
+DPC_DEV void dpc_red_release_cta_shared(unsigned* p, unsigned v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(dpc_tc_s32(p)), "r"(v) : "memory");
+}
 // The taps as launch parameters when the host knows them (sigma is a host value in the reference's schedule): the
 // prologue then builds the Toeplitz operand from the constant bank instead of waiting ~1 us for a global load that
 // misses L2 -- the prologue of these 226 KB CTAs cannot overlap the previous kernel, so it is on the critical path.

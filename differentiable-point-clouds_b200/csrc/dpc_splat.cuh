@@ -25,6 +25,7 @@ struct DpcSplatArgs {
   // f-2, point dropout consumed by the load stage (point_cloud.py:293-319): sel != NULL => pc is [B,N_src,3] and point i
   // of sample b is pc[b, sel[b*N + i]]; the points that were dropped are never read.  Outputs are [B,N,..] as usual.
   const int32_t* sel; int N_src;
+  unsigned* zero_u32; int n_zero;   // optional: words zeroed by CTA (0, 0) behind the grid dependency (per-sample counters of the fused x/y + depth kernel)
 };
 
 // Stage `n` points (3n floats) into smem: one TMA bulk copy when the 16-byte rules allow it
@@ -90,6 +91,8 @@ dpc_splat_fwd_kernel(DpcSplatArgs a) {
   dpc_ph_mark(0, 0);
   dpc_grid_dep_trigger();
   if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_F, 1); }
+  if (a.zero_u32 && blockIdx.x == 0 && blockIdx.y == 0 && !a.early)
+    for (int i = tid; i < a.n_zero; i += DPC_SPLAT_THREADS) a.zero_u32[i] = 0u;
   if (a.sel) dpc_stage_points(tile, &bar, a.pc + (size_t)b * a.N_src * 3, n, &pose_sm, a.pose, a.pose_kind, a.trans, a.focal,
                               a.focal_const, a.cam_dist, b, a.sel + (size_t)b * a.N + p_first);
   else dpc_stage_points(tile, &bar, a.pc + ((size_t)b * a.N + p_first) * 3, n, &pose_sm,
