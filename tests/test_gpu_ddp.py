@@ -1,7 +1,14 @@
 """BASELINE config 4's data-parallel train step on real GPUs (NCCL, 2 ranks, `-m gpu`; skipped with fewer than 2 GPUs):
-objects sharded over the ranks, the renderer local, ONE all-reduce of the flat gradient buffer -- the reduced gradients
-must equal the single-process gradients on the concatenated batch to 1e-4 relative (global L2) and 1e-3 of the largest
-element per parameter.
+objects sharded over the ranks, the renderer local, ONE all-reduce of the flat gradient buffer.  Two gates:
+  (1) the gradients the renderer + losses hand to the networks (at points_1, scaling_factor, poses, pose_student) on a
+      rank's shard equal the corresponding rows of the full-batch run to 1e-5 of their largest element -- this is the
+      renderer + sharding + loss-normalisation path, measured 0 .. 6e-7;
+  (2) the reduced parameter gradients equal the single-process ones on the concatenated batch: 1e-4 relative (global L2) /
+      1e-3 of the largest element per parameter for the supervised config (measured 6e-7 / 2e-6); 1e-3 / 1e-2 for the
+      unsupervised one, whose encoder runs on 8 vs 16 images: cuDNN's weight gradients of the deep conv layers then differ
+      by up to 3e-3 of their largest element (encoder.convs.8) although their upstream gradients agree to 6e-7 -- library
+      summation order, not the data-parallel path (the gloo / emulated-kernel variant, tests/test_ddp_cpu.py, is exact to
+      1e-4 for both configs).
 
 What makes that tolerance meaningful: the renderer's gradient is a discontinuous function of the point positions (a point
 crossing a cell face changes its eight target voxels) and cuDNN may choose another algorithm for another batch size, so a
@@ -123,7 +130,7 @@ def _worker(rank, world, port, name, ret):
 
 
 # (global relative L2, worst parameter relative to its largest element)
-TOL = {"chair_camera_supervision": (1e-4, 1e-3), "chair_unsupervised": (1e-4, 1e-3)}
+TOL = {"chair_camera_supervision": (1e-4, 1e-3), "chair_unsupervised": (1e-3, 1e-2)}
 
 
 @pytest.mark.parametrize("name", ["chair_camera_supervision", "chair_unsupervised"])
@@ -137,5 +144,6 @@ def test_two_rank_nccl_gradients_equal_the_full_batch_gradients(name):
     print(name, r)
     assert r is not None
     assert r["allreduce_bytes"] > 100e6
+    assert r["upstream_rel_max"] and max(r["upstream_rel_max"].values()) <= 1e-5, r
     assert r["rel_l2"] <= TOL[name][0], r
     assert r["worst_param_rel_max"] <= TOL[name][1], r
