@@ -706,10 +706,6 @@ def run_ours(args, rank, local_rank, world):
     except Exception as exc:
         print("device-resident e2e failed: %r" % (exc,), file=sys.stderr)
 
-    # BASELINE configs 3 / 4 (the train step around this path) under the same launch: every rank takes part (all-reduce)
-    train = None
-    if not args.no_train and args.scaling == "weak":
-        train = train_rows(args, rank, local_rank, world)
     line = None
     if rank == 0:
         import json as _json
@@ -787,7 +783,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": roofline,
             "roofline_step": {"algorithmic_bytes_per_projection": FULL_PATH_BYTES, "achieved": step_gbs,
                               "frac": (step_gbs / peak) if step_gbs else None, "unit": "GB/s"},
-            "train": train,
+            "train": None,
             "stages_ms": stages,
             "kernel_busy_us": busy,
             "roofline_in_step": roofline_busy,
@@ -807,6 +803,26 @@ def run_ours(args, rank, local_rank, world):
             if args.ref_batch == B:
                 # the oracle ran on the very inputs of the timed step (make_inputs(B), rank 0): compare the step's results
                 line["parity"] = parity_block(pipe, graph, kept)
+    D.barrier()
+    # BASELINE configs 3 / 4 (the train step around this path) under the same launch: every rank takes part (all-reduce).
+    # Last phase, under a watchdog: a hang inside a collective cannot be caught, and the projection line must get out
+    # whatever happens here.
+    if not args.no_train and args.scaling == "weak":
+        finished = threading.Event()
+
+        def watchdog():
+            if not finished.wait(timeout=args.train_timeout):
+                if rank == 0:
+                    line["train"] = {"error": "train phase did not finish within %d s (watchdog)" % args.train_timeout}
+                    emit(line)
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+        train = train_rows(args, rank, local_rank, world)
+        finished.set()
+        if rank == 0:
+            line["train"] = train
+    if rank == 0:
         emit(line)
     D.barrier()
 
@@ -922,6 +938,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="projection", choices=["projection", "train"])
     ap.add_argument("--no-train", action="store_true", help="skip the train-step rows (BASELINE configs 3 / 4) of the JSON line")
+    ap.add_argument("--train-timeout", type=int, default=240, help="watchdog of the train-step phase (seconds)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (the driver's contract): B=32 per GPU; strong: the B=32 batch is split over the ranks (SURVEY 8e)")
@@ -949,6 +966,10 @@ def main():
     else:
         run_ours(args, rank, local_rank, world)
     if world > 1:
+        # the line is out; never let the tear-down of the process group keep the job alive
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         torch.distributed.destroy_process_group()
 
 
