@@ -38,14 +38,14 @@ FULL_PATH_BYTES = 6 * G_BYTES + 4 * 12 * N + 64 * N + 2 * 4 * V * V
 # very command (profiles/r01_p_final_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
 # previous kernel left in L2 are re-read from HBM, and the 32 MiB of output stays in L2 until a later kernel evicts it)
 NCU_TRAFFIC_B32 = {
-    "splat_fwd": 22.190848e6 + 0.075264e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
-    "conv_xy_fwd": 33.596416e6 + 0.002560e6,
-    "conv_z_fwd": 33.591808e6 + 1.078016e6,
-    "conv_z_bwd": 35.166464e6 + 0.500224e6,
-    "conv_xy_bwd": 34.642432e6 + 0.003840e6,
-    "splat_bwd": 26.721536e6 + 0.0,
+    "splat_fwd": 22.228224e6 + 0.000256e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
+    "conv_xy_fwd": 33.595392e6 + 0.006656e6,
+    "conv_z_fwd": 33.594624e6 + 1.164032e6,
+    "conv_z_bwd": 35.166720e6 + 0.963584e6,
+    "conv_xy_bwd": 34.642176e6 + 0.0,
+    "splat_bwd": 26.727936e6 + 0.018432e6,
 }
-NCU_TRAFFIC_SOURCE = "ncu --set full, dram read+write per launch, profiles/r01_p_final_ncu_summary.md"
+NCU_TRAFFIC_SOURCE = "ncu --set full, dram read+write per launch, profiles/r02_p_final_ncu_summary.md"
 STAGE_BYTES = {
     "splat_fwd": G_BYTES + 2 * 12 * N + 32 * N,          # zero grid + read pc + write tr_pc + 8 corner RMW
     "conv_xy_fwd": 2 * G_BYTES + G_BYTES // 32,          # read raw, write xy-smoothed, clip-mask bits

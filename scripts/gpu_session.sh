@@ -31,17 +31,17 @@ for task in "$@"; do
       timeout -s KILL 300 python scripts/step_timeline.py > $O/timeline$T.txt 2>&1; say "timeline rc=$?"; tail -12 $O/timeline$T.txt ;;
     nculist)
       timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches$T.csv \
-        python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_list$T.log 2>&1; say "ncu-list rc=$?" ;;
+        python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-train > $O/ncu_list$T.log 2>&1; say "ncu-list rc=$?" ;;
     ncufull)
       timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:dpc_ -s ${NCU_SKIP:-14} -c ${NCU_COUNT:-7} -f -o $O/prof_full$T \
-        python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_full$T.log 2>&1; say "ncu-full rc=$?" ;;
+        python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-train --no-graph > $O/ncu_full$T.log 2>&1; say "ncu-full rc=$?" ;;
     l1tex)    # request / sector counters of the two splat kernels (the request-rate bound of DESIGN 4a)
       timeout -s KILL 600 ncu --clock-control none -k regex:dpc_splat -s 6 -c 4 --csv --log-file $O/l1tex$T.csv --metrics \
 gpu__time_duration.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,\
 l1tex__t_requests_pipe_lsu_mem_global_op_red.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum,\
 l1tex__m_xbar2l1tex_read_sectors.sum,l1tex__m_l1tex2xbar_write_sectors.sum,l1tex__t_sector_hit_rate.pct,\
 lts__t_sectors_op_red.sum,lts__t_sectors_op_read.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__warps_active.avg.per_cycle_active \
-        python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_l1tex$T.log 2>&1; say "ncu-l1tex rc=$?" ;;
+        python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-train --no-graph > $O/ncu_l1tex$T.log 2>&1; say "ncu-l1tex rc=$?" ;;
     memcheck|racecheck|synccheck)
       timeout -s KILL 900 compute-sanitizer --tool $task --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $O/sanitizer_$task$T.log 2>&1; say "$task rc=$?"; tail -3 $O/sanitizer_$task$T.log ;;
     racecheck_full|synccheck_full)   # one full-shape step under the tool
