@@ -247,6 +247,7 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.d_pc = d_pc; a.d_pose = d_pose; a.d_trans = d_trans; a.d_focal = d_focal; a.d_rgb = d_rgb;
   a.early = g_tune[14] ? 1 : 0;
   a.gather4 = g_tune[11] ? 1 : 0;
+  a.gather_cg = g_tune[22] ? 1 : 0;
   a.d_scale_part = d_scale_part; a.n_part = n_part; a.d_scale_out = d_scale_out;
   a.sel = sel; a.N_src = N_src;
   if (sel && d_pc) DPC_CUDA(cudaMemsetAsync(d_pc, 0, (size_t)B * N_src * 12, (cudaStream_t)stream));      // dropped points: zero gradient
@@ -257,14 +258,19 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
     // occupancy / decorrelation experiments (knobs 18: 128-thread CTAs, 19: compiled for 75 % occupancy, 20: independent gathers)
     const int sel3 = (g_tune[18] ? 4 : 0) | (g_tune[19] ? 2 : 0) | (g_tune[20] ? 1 : 0);
     dim3 g128((N + 127) / 128, B);
+    if (g_tune[20] == 2) {        // single guarded gather path
+      if (g_tune[18]) { DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, 2>), g128, dim3(128), 0, stream, a); }
+      else { DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 0, 2>), grid, dim3(256), 0, stream, a); }
+      return dpc_check_launch();
+    }
     switch (sel3) {
-      case 1: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 0, true>), grid, dim3(256), 0, stream, a); break;
-      case 2: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 6, false>), grid, dim3(256), 0, stream, a); break;
-      case 3: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 6, true>), grid, dim3(256), 0, stream, a); break;
-      case 4: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, false>), g128, dim3(128), 0, stream, a); break;
-      case 5: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, true>), g128, dim3(128), 0, stream, a); break;
-      case 6: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 12, false>), g128, dim3(128), 0, stream, a); break;
-      default: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 12, true>), g128, dim3(128), 0, stream, a); break;
+      case 1: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 0, 1>), grid, dim3(256), 0, stream, a); break;
+      case 2: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 6, 0>), grid, dim3(256), 0, stream, a); break;
+      case 3: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 6, 1>), grid, dim3(256), 0, stream, a); break;
+      case 4: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, 0>), g128, dim3(128), 0, stream, a); break;
+      case 5: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, 1>), g128, dim3(128), 0, stream, a); break;
+      case 6: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 12, 0>), g128, dim3(128), 0, stream, a); break;
+      default: DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 12, 1>), g128, dim3(128), 0, stream, a); break;
     }
     return dpc_check_launch();
   }

@@ -241,6 +241,7 @@ struct DpcSplatBwdArgs {
   float* d_pc; float* d_pose; float* d_trans; float* d_focal; float* d_rgb;
   int early;   // transform before the grid dependency (experiment knob 14)
   int gather4; // 16-byte gathers of x pairs (experiment knob 11)
+  int gather_cg; // gathers through ld.global.cg (L2 only, no L1 line allocated per scattered miss; experiment knob 22)
   // per-warp partial sums of dL/dscale left by the depth-pass backward ([B, n_part]); CTA (0, b) folds them into
   // d_scale_out[b], so the fused backward needs neither atomics on d_scale nor a launch that zeroes it
   const float* d_scale_part; int n_part; float* d_scale_out;
@@ -304,8 +305,10 @@ DPC_DEV void dpc_gather_corners(const float* dv, const DpcCell& c, int Vz, int V
 }
 
 // MINB: minimum resident CTAs per SM the kernel is compiled for (0 = unconstrained: ptxas settles at 61 registers, four 256-thread CTAs per SM);
-// INDEP: the corner gathers as independent, un-guarded loads (dpc_gather_corners) instead of four guarded ones.
-template <int DPC_SPLAT_PPT, int NT, int MINB = 0, bool INDEP = false>
+// INDEP: 0 = four guarded 16-byte gathers, a second (scalar) path for the lanes whose x pair straddles two 4-voxel groups;
+// 1 = independent, un-guarded loads (dpc_gather_corners); 2 = ONE guarded path: per row the group that holds ix and, for
+// the straddling lanes only, the next group (same lines touched as 0, without the second code path every warp walks).
+template <int DPC_SPLAT_PPT, int NT, int MINB = 0, int INDEP = 0>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(NT, MINB)
 #else
@@ -373,14 +376,29 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   // An uncoalesced warp load costs one L1 wavefront per lane, and the gathers are what this kernel waits for: the x
   // pair of a row comes in ONE 16-byte load whenever it does not straddle a 4-voxel group (3 of 4 points): 5
   // wavefronts per point on average instead of 8.
-  const bool coherent = false;
+  const bool coherent = a.gather_cg != 0;
   const bool quad = a.gather4 && dv && ((V & 3) == 0) && ((((uintptr_t)dv) & 15u) == 0);
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
     const int base = (cell[j].iz * V + cell[j].iy) * V + cell[j].ix;
     const int o4 = cell[j].ix & 3;
-    if (INDEP && quad) {
+    if (INDEP == 1 && quad) {
       dpc_gather_corners<false>(dv, cell[j], Vz, V, dw[j]);
+    } else if (INDEP == 2 && quad) {
+      const bool straddle = (o4 == 3) && (cell[j].ix + 1 < V);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const bool inb = cell[j].valid && (cell[j].iz + k < Vz) && (cell[j].iy + jj < V);
+          const float* rp = dv + base + (k * V + jj) * V - o4;
+          float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float nx = 0.0f;
+          if (inb) q4 = dpc_ld_gather4(reinterpret_cast<const float4*>(rp), coherent);
+          if (inb && straddle) nx = dpc_ld_gather(rp + 4, coherent);
+          dw[j][k * 4 + jj * 2 + 0] = o4 == 0 ? q4.x : (o4 == 1 ? q4.y : (o4 == 2 ? q4.z : q4.w));
+          dw[j][k * 4 + jj * 2 + 1] = o4 == 0 ? q4.y : (o4 == 1 ? q4.z : (o4 == 2 ? q4.w : nx));
+        }
     } else if (quad && o4 != 3) {        // ix + 1 < V is implied
       // (the four loads below end up as four DEPENDENT round trips -- nvcc wraps each in its own divergence region and
       // reuses one destination quad; the independent form, dpc_gather_corners, was measured SLOWER in this kernel at full
@@ -411,6 +429,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   __syncthreads();  // every thread has read its points: the tile can take the results
 
   // pass 2: weights' derivative, chain rule through the camera
+  const bool want_tf = (a.d_trans != nullptr) || (a.d_focal != nullptr);
 #pragma unroll
   for (int j = 0; j < DPC_SPLAT_PPT; ++j) {
     const int i = j * NT + tid;
@@ -456,7 +475,7 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
       // chain rule applied unconditionally: an invalid but finite point gets exact zeros, a NaN
       // point propagates NaN into the pose gradient exactly as TF's autodiff does (0 * NaN).
       float d0, d1, d2;
-      dpc_transform_point_bwd(P, p0[j], p1[j], p2[j], cam[j], gz, gy, gx, d0, d1, d2, acc);
+      dpc_transform_point_bwd(P, p0[j], p1[j], p2[j], cam[j], gz, gy, gx, d0, d1, d2, acc, want_tf);
       if (a.d_pc) { tile[i * 3 + 0] = d0; tile[i * 3 + 1] = d1; tile[i * 3 + 2] = d2; }
     }
   }
@@ -479,11 +498,18 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   if (a.pose_kind == DPC_POSE_NONE) return;
   const bool want_pose = a.d_pose != nullptr, want_t = a.d_trans != nullptr, want_f = a.d_focal != nullptr;
   if (!(want_pose || want_t || want_f)) return;
-  // block reduction of the per-sample pose gradients: warp shuffles, then one atomic per CTA
+  // block reduction of the per-sample pose gradients: warp shuffles, then one atomic per CTA.  Only the components
+  // somebody asked for are reduced (quaternion pose: 4 for d_pose, +3 translation, +1 focal; 10 shuffle + add
+  // instructions per component and thread -- the full 12 were 16 % of this kernel's instructions, ncu r02_p)
+  {
+    const int q_lo = (a.pose_kind == DPC_POSE_QUAT && !want_pose) ? 4 : 0;
+    const int q_hi = (a.pose_kind == DPC_POSE_QUAT) ? (want_f ? 8 : (want_t ? 7 : 4)) : 12;
 #pragma unroll
-  for (int q = 0; q < 12; ++q) {
-    const float v = dpc_warp_sum(acc[q]);
-    if (lane == 0) red[warp][q] = v;
+    for (int q = 0; q < 12; ++q) {
+      if (q < q_lo || q >= q_hi) { if (lane == 0) red[warp][q] = 0.0f; continue; }      // warp-uniform
+      const float v = dpc_warp_sum(acc[q]);
+      if (lane == 0) red[warp][q] = v;
+    }
   }
   __syncthreads();
   if (tid < 12) {

@@ -77,8 +77,8 @@ int dpc_last_cuda_error(void);
  *   13     1 = keep the zeroing launch + dL/dscale atomics in the fused backward (default 0: folded partial sums)
  *   14     1 = the backward splat stages + transforms ahead of its grid dependency (default)
  *   15     1 = x/y pass in place, backward in the raw grid's storage: two grids per step (default)
- *   18-20  splat backward: 128-thread CTAs / compiled for 75 % occupancy / independent gathers
- *          (profiles/r02_j_splat_bwd_occupancy.md)
+ *   18-20  splat backward: 128-thread CTAs / compiled for 75 % occupancy / gather style (1 = independent un-guarded
+ *          loads, 2 = one guarded path); 22 = 1: gathers through ld.global.cg (profiles/r02_j_splat_bwd_occupancy.md)
  *   21     1 = x/y pass + depth pass of the forward as ONE persistent kernel (csrc/dpc_smooth_fused.cuh; default 0:
  *          measured no faster, profiles/r02_m_fused_fwd.md) */
 int dpc_debug_set(int key, int value);
