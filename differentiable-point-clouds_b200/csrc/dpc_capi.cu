@@ -248,6 +248,7 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.early = g_tune[14] ? 1 : 0;
   a.gather4 = g_tune[11] ? 1 : 0;
   a.gather_cg = g_tune[22] ? 1 : 0;
+  a.stagger_ns = g_tune[23];
   a.d_scale_part = d_scale_part; a.n_part = n_part; a.d_scale_out = d_scale_out;
   a.sel = sel; a.N_src = N_src;
   if (sel && d_pc) DPC_CUDA(cudaMemsetAsync(d_pc, 0, (size_t)B * N_src * 12, (cudaStream_t)stream));      // dropped points: zero gradient

@@ -242,6 +242,7 @@ struct DpcSplatBwdArgs {
   int early;   // transform before the grid dependency (experiment knob 14)
   int gather4; // 16-byte gathers of x pairs (experiment knob 11)
   int gather_cg; // gathers through ld.global.cg (L2 only, no L1 line allocated per scattered miss; experiment knob 22)
+  int stagger_ns; // experiment knob 23: every other CTA sleeps this long at entry (are the phases of a wave in lock-step?)
   // per-warp partial sums of dL/dscale left by the depth-pass backward ([B, n_part]); CTA (0, b) folds them into
   // d_scale_out[b], so the fused backward needs neither atomics on d_scale nor a launch that zeroes it
   const float* d_scale_part; int n_part; float* d_scale_out;
@@ -332,6 +333,12 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
   dpc_kt_mark(DPC_KT_SPLAT_B, 0);
   dpc_ph_mark(1, 0);
   dpc_grid_dep_trigger();
+#if defined(DPC_EXPERIMENTS) && !defined(DPC_EMU)
+  if (a.stagger_ns > 0) {
+    const unsigned phase = (blockIdx.x + blockIdx.y) & 3u;
+    if (phase) __nanosleep((unsigned)a.stagger_ns * phase);
+  }
+#endif
   if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark(DPC_KT_SPLAT_B, 1); }
   if (a.sel) dpc_stage_points(tile, &bar, a.pc + (size_t)b * a.N_src * 3, n, &pose_sm, a.pose, a.pose_kind, a.trans, a.focal,
                               a.focal_const, a.cam_dist, b, a.sel + (size_t)b * a.N + p_first);
