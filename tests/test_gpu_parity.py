@@ -109,7 +109,10 @@ def _compare(res, atol=1e-5):
         assert d <= tol, "%s differs by %.3g" % (k, d)
     assert float((co["proj"] - oo["proj"]).abs().mean()) < 1e-5  # "silhouette L1 vs reference < 1e-5"
     for i, (a, b) in enumerate(zip(cg, og)):
-        scale = max(1.0, float(b.abs().max()))
+        # d_pc (i == 0): 1e-5 ABSOLUTE.  The per-sample sums (d_q, d_scale, d_trans) carry the fp32 summation noise of
+        # thousands of cancelling terms: relative to max(1, |g|) here; their absolute errors and the fp32 bound at the
+        # headline shape are measured and gated in tests/test_gpu_headline.py.
+        scale = 1.0 if i == 0 else max(1.0, float(b.abs().max()))
         d = float((a - b).abs().max())
         assert d <= atol * scale, "gradient %d differs by %.3g (scale %.3g)" % (i, d, scale)
 
