@@ -87,6 +87,7 @@ _LAB_SIGNATURES = {
     "dpc_debug_trace_read": (c_i, [c_p]),
     "dpc_debug_phase_read": (c_i, [c_p]),
     "dpc_debug_mma_bench": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "dpc_debug_gather_bench": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 
 

@@ -10,6 +10,7 @@
 #ifdef DPC_EXPERIMENTS
 #include "dpc_smooth_fused.cuh"
 #include "dpc_fused_bwd.cuh"
+#include "dpc_gather_bench.cuh"
 #endif
 #include "dpc_chamfer.cuh"
 #include "dpc_loss.cuh"
@@ -163,6 +164,36 @@ int dpc_debug_mma_bench(long long* out, int nctas, int threads, int reps, int nm
   return DPC_ERR_ARG;
 #endif
 }
+/* diagnostics: the splat backward's gather pattern alone (dpc_gather_bench.cuh); smem_pad bytes of dynamic shared memory
+ * per CTA limit the resident CTAs per SM */
+int dpc_debug_gather_bench(const float* grid, float* out, int B, int N, int V, int variant, int threads, int ppt,
+                           int share_log2, int smem_pad, int cg, void* stream) {
+#ifndef DPC_EMU
+  if (!grid || !out || B < 1 || N < 1 || V < 8 || (V & 3) || threads < 32 || threads > 1024 || ppt < 1 || smem_pad < 0 ||
+      smem_pad > 200 * 1024 || share_log2 < 0 || share_log2 > 5)
+    return DPC_ERR_ARG;
+  DpcGatherBenchArgs a{grid, out, N, V, ppt, share_log2, 0x1234567u, 0u, cg};
+  const dim3 g((unsigned)((N + threads * ppt - 1) / (threads * ppt)), (unsigned)B);
+  void (*k)(DpcGatherBenchArgs) = nullptr;
+  switch (variant) {
+    case 0: k = dpc_gather_bench_kernel<0>; break;
+    case 1: k = dpc_gather_bench_kernel<1>; break;
+    case 2: k = dpc_gather_bench_kernel<2>; break;
+    case 3: k = dpc_gather_bench_kernel<3>; break;
+    case 4: k = dpc_gather_bench_kernel<4>; break;
+    case 5: k = dpc_gather_bench_kernel<5>; break;
+    case 6: k = dpc_gather_bench_kernel<6>; break;
+    case 7: if (threads > 256) return DPC_ERR_ARG; k = dpc_gather_bench_kernel<7>; break;
+    default: return DPC_ERR_ARG;
+  }
+  if (smem_pad > 48 * 1024 &&
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pad) != cudaSuccess) return DPC_ERR_CUDA;
+  k<<<g, threads, smem_pad, (cudaStream_t)stream>>>(a);
+  return dpc_check_launch();
+#else
+  return DPC_ERR_ARG;
+#endif
+}
 #endif  // DPC_EXPERIMENTS
 int dpc_is_cuda_build(void) {
 #ifdef DPC_EMU
@@ -231,7 +262,7 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
                             const float* d_vox, const float* d_vox_rgb, const float* d_tr_pc_in,
                             float* d_pc, float* d_pose, float* d_trans, float* d_focal, float* d_rgb,
                             const float* d_scale_part, int n_part, float* d_scale_out, void* stream,
-                            const int32_t* sel = nullptr, int N_src = 0) {
+                            const int32_t* sel = nullptr, int N_src = 0, const float* tr_pc = nullptr) {
   if (!pc) return DPC_ERR_NULL;
   if (sel && (N_src < N || rgb)) return DPC_ERR_ARG;
   if (pose_kind != DPC_POSE_NONE && !pose) return DPC_ERR_NULL;
@@ -250,15 +281,41 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.gather_cg = g_tune[22] ? 1 : 0;
   a.stagger_ns = g_tune[23];
   a.d_scale_part = d_scale_part; a.n_part = n_part; a.d_scale_out = d_scale_out;
-  a.sel = sel; a.N_src = N_src;
+  a.sel = sel; a.N_src = N_src; a.tr_pc = tr_pc;
   if (sel && d_pc) DPC_CUDA(cudaMemsetAsync(d_pc, 0, (size_t)B * N_src * 12, (cudaStream_t)stream));      // dropped points: zero gradient
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
+#ifndef DPC_EMU
+  // Default whenever the forward's tr_pc is at hand (the fused path passes it): the software-pipelined form,
+  // dpc_splat_bwd_warp_kernel -- one warp per CTA, every warp resident at once, k tiles of 32 points per warp with k the
+  // smallest count for which the grid fits 28 warps per SM (13.6-14.0 us against 20.0 us of the tile-per-CTA kernel at
+  // B=32, N=8000; 24 warps per SM, i.e. k = 3: 15.1 us; profiles/r02_w_splat_bwd_warp.md).  Lab build: knob 20 = 6
+  // forces the tile-per-CTA kernel, knob 19 = warps per SM the grid is sized for.
+  if ((g_tune[20] == 0 || g_tune[20] == 4) && tr_pc && d_vox && !rgb && !d_vox_rgb && !d_rgb && !sel && (V & 3) == 0 &&
+      ((((uintptr_t)d_vox) & 15u) == 0)) {
+    const int tiles = (N + 31) / 32;
+    const int per_sm = g_tune[19] > 0 ? g_tune[19] : 28;
+    const long long cap = (long long)dpc_tc_sm_count() * per_sm;
+    const int k = (int)(((long long)B * tiles + cap - 1) / cap);
+    const int wps = (tiles + k - 1) / k;
+    void (*kw)(DpcSplatBwdArgs) = per_sm > 24 ? dpc_splat_bwd_warp_kernel<28> : dpc_splat_bwd_warp_kernel<24>;
+    // 28 x 7 KB of static shared memory per SM need the large carve-out (per device, so set on every call like the
+    // dynamic-shared-memory limits of the other launchers; a host-side attribute, legal during stream capture)
+    if (cudaFuncSetAttribute(kw, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return DPC_ERR_CUDA;
+    DPC_LAUNCH(kw, dim3(wps, B), dim3(32), 0, stream, a);
+    return dpc_check_launch();
+  }
+#endif
 #if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
-  if (ppt == 1 && (g_tune[18] || g_tune[19] || g_tune[20])) {
+  if (ppt == 1 && g_tune[20] != 6 && (g_tune[18] || g_tune[19] || g_tune[20])) {
     // occupancy / decorrelation experiments (knobs 18: 128-thread CTAs, 19: compiled for 75 % occupancy, 20: independent gathers)
     const int sel3 = (g_tune[18] ? 4 : 0) | (g_tune[19] ? 2 : 0) | (g_tune[20] ? 1 : 0);
     dim3 g128((N + 127) / 128, B);
+    if (g_tune[20] == 3) {        // predicated independent gathers (dpc_gather_corners_pred)
+      if (g_tune[18]) { DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, 3>), g128, dim3(128), 0, stream, a); }
+      else { DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 0, 3>), grid, dim3(256), 0, stream, a); }
+      return dpc_check_launch();
+    }
     if (g_tune[20] == 2) {        // single guarded gather path
       if (g_tune[18]) { DPC_LAUNCH((dpc_splat_bwd_kernel<1, 128, 0, 2>), g128, dim3(128), 0, stream, a); }
       else { DPC_LAUNCH((dpc_splat_bwd_kernel<1, 256, 0, 2>), grid, dim3(256), 0, stream, a); }
@@ -704,7 +761,8 @@ int dpc_project_fast_bwd(const dpc_project_params* p,
   stage_mark(6, stream);
   DPC_TRY(splat_bwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr, 0,
                            p->B, p->N, p->Vz, p->V, d_raw, nullptr, g_tr_pc, d_pc, d_pose, d_trans, d_focal, nullptr,
-                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream, p->sel, p->N_src));
+                           fold_scale ? w.part : nullptr, 256, fold_scale ? d_scale : nullptr, stream, p->sel, p->N_src,
+                           p->tr_pc));
   stage_mark(7, stream);
   return DPC_OK;
 }

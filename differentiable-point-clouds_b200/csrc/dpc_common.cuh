@@ -99,6 +99,17 @@ DPC_DEV void dpc_kt_mark(int id, int slot) {
     if (slot == 1) atomicMax(&dpc_kt[id * 4 + 2], t);
   }
 }
+// the same with the switch read ONCE by the caller (a kernel that stamps behind its grid dependency would otherwise put
+// a global load of the flag on its critical path)
+DPC_DEV bool dpc_kt_enabled() { return dpc_kt_on != 0; }
+DPC_DEV void dpc_kt_mark_if(bool on, int id, int slot) {
+  if (on && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (slot < 2) atomicMin(&dpc_kt[id * 4 + slot], t); else atomicMax(&dpc_kt[id * 4 + slot], t);
+    if (slot == 1) atomicMax(&dpc_kt[id * 4 + 2], t);
+  }
+}
 // per-CTA phase stamps of the two splat kernels (same switch): [which][cta < 512][8 slots]
 __device__ unsigned long long dpc_ph[2 * 512 * 8];
 DPC_DEV void dpc_ph_mark(int which, int slot) {
@@ -111,6 +122,8 @@ DPC_DEV void dpc_ph_mark(int which, int slot) {
 }
 #else
 DPC_DEV void dpc_kt_mark(int, int) {}
+DPC_DEV bool dpc_kt_enabled() { return false; }
+DPC_DEV void dpc_kt_mark_if(bool, int, int) {}
 DPC_DEV void dpc_ph_mark(int, int) {}
 #endif
 enum { DPC_KT_ZERO = 0, DPC_KT_SPLAT_F, DPC_KT_XY_F, DPC_KT_Z_F, DPC_KT_ZERO4, DPC_KT_Z_B, DPC_KT_XY_B, DPC_KT_SPLAT_B };

@@ -249,6 +249,7 @@ struct DpcSplatBwdArgs {
   // f-2 (see DpcSplatArgs): pc and d_pc are [B,N_src,3], addressed through sel[B,N]; d_pc is ZEROED by the launcher and
   // the selected rows are written (the indices of a sample are distinct: plain stores)
   const int32_t* sel; int N_src;
+  const float* tr_pc;   // the forward's tr_pc [B,N,3] or NULL: lets dpc_splat_bwd_warp_kernel start a tile's gathers before its transform
 };
 
 // gathers of dL/d(raw): through the read-only path normally; past L1 (ld.global.cg) when the producer kernel is still
@@ -305,10 +306,46 @@ DPC_DEV void dpc_gather_corners(const float* dv, const DpcCell& c, int Vz, int V
   }
 }
 
+// The same 8 corner values with PREDICATED loads (inline PTX): no divergence regions, so all loads of a point are issued
+// back to back into distinct registers (one round trip), and a lane whose predicate is off generates no wavefront --
+// the load count of the guarded code (four 16-byte loads per valid lane, four scalar loads on the straddling lanes
+// only) with the issue pattern of dpc_gather_corners.
+DPC_DEV void dpc_gather_corners_pred(const float* dv, const DpcCell& c, int Vz, int V, float* dw) {
+  const int base = (c.iz * V + c.iy) * V + c.ix;
+  const int o4 = c.ix & 3;
+  const bool straddle = (o4 == 3) && (c.ix + 1 < V);
+  float4 q[4];
+  float e[4];
+  bool ok[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = r >> 1, jj = r & 1;
+    ok[r] = c.valid && (c.iz + k < Vz) && (c.iy + jj < V);
+    const float* rp = dv + base - o4 + (k * V + jj) * V;
+    q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    e[r] = 0.0f;
+#ifndef DPC_EMU
+    asm("{\n\t.reg .pred pq;\n\tsetp.ne.u32 pq, %5, 0;\n\t@pq ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "+f"(q[r].x), "+f"(q[r].y), "+f"(q[r].z), "+f"(q[r].w) : "l"(rp), "r"((unsigned)ok[r]));
+    asm("{\n\t.reg .pred pq;\n\tsetp.ne.u32 pq, %2, 0;\n\t@pq ld.global.nc.f32 %0, [%1];\n\t}"
+        : "+f"(e[r]) : "l"(rp + 4), "r"((unsigned)(ok[r] && straddle)));
+#else
+    if (ok[r]) q[r] = *reinterpret_cast<const float4*>(rp);
+    if (ok[r] && straddle) e[r] = rp[4];
+#endif
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    dw[r * 2 + 0] = o4 == 0 ? q[r].x : (o4 == 1 ? q[r].y : (o4 == 2 ? q[r].z : q[r].w));
+    dw[r * 2 + 1] = o4 == 0 ? q[r].y : (o4 == 1 ? q[r].z : (o4 == 2 ? q[r].w : e[r]));
+  }
+}
+
 // MINB: minimum resident CTAs per SM the kernel is compiled for (0 = unconstrained: ptxas settles at 61 registers, four 256-thread CTAs per SM);
 // INDEP: 0 = four guarded 16-byte gathers, a second (scalar) path for the lanes whose x pair straddles two 4-voxel groups;
 // 1 = independent, un-guarded loads (dpc_gather_corners); 2 = ONE guarded path: per row the group that holds ix and, for
-// the straddling lanes only, the next group (same lines touched as 0, without the second code path every warp walks).
+// the straddling lanes only, the next group (same lines touched as 0, without the second code path every warp walks);
+// 3 = the loads of 2 as predicated PTX loads: independent, no divergence regions (dpc_gather_corners_pred).
 template <int DPC_SPLAT_PPT, int NT, int MINB = 0, int INDEP = 0>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(NT, MINB)
@@ -391,6 +428,8 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     const int o4 = cell[j].ix & 3;
     if (INDEP == 1 && quad) {
       dpc_gather_corners<false>(dv, cell[j], Vz, V, dw[j]);
+    } else if (INDEP == 3 && quad) {
+      dpc_gather_corners_pred(dv, cell[j], Vz, V, dw[j]);
     } else if (INDEP == 2 && quad) {
       const bool straddle = (o4 == 3) && (cell[j].ix + 1 < V);
 #pragma unroll
@@ -544,6 +583,224 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     }
   }
 }
+
+// ------------------------------------------------------------------------------ backward, software-pipelined form
+// One warp per CTA, k tiles of 32 points each (tiles j, j + wps, ... of sample blockIdx.y), every warp of the grid
+// resident at once.  What the tile-per-CTA kernel above cannot do -- its CTAs walk stage / transform / gather / chain
+// rule in lock-step, so an SM alternates between waiting for memory and being issue-bound (scripts/gather_bench.py: the
+// gathers alone take 4 us, that kernel 20) -- this one does by prefetching: the cells of the NEXT tile are known from the
+// forward's tr_pc (12 B per point, no transform needed), so its corner rows and its points are fetched with cp.async
+// (global -> shared, no destination registers, the warp does not wait) while the current tile's transform and chain
+// rule are computed.  Rows that are out of range are zero-filled through cp.async's src-size operand.  The copies of a
+// tile are issued in four portions spread over the current tile's arithmetic (a burst of 11 scattered LDGSTS backs up
+// the SM's load/store queue and the warp then stalls on the address registers it wants to reuse: ncu, r02_w).  The
+// pose gradients are accumulated in registers over all tiles of the warp (same sample) and reduced once.
+// Preconditions (the launcher falls back to dpc_splat_bwd_kernel otherwise): tr_pc given, no rgb, no dropout list,
+// V % 4 == 0 and a 16-byte aligned gradient grid.
+#ifndef DPC_EMU
+DPC_DEV void dpc_cp_async16(void* smem, const void* g, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(g), "r"(pred ? 16u : 0u) : "memory");
+}
+DPC_DEV void dpc_cp_async4(void* smem, const void* g, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(g), "r"(pred ? 4u : 0u) : "memory");
+}
+DPC_DEV void dpc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+DPC_DEV void dpc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+
+struct DpcSplatBwdWarpSmem {
+  float4 gq[2][4][32];   // per buffer, per (z, y) row of the cell: the 4-voxel group that holds ix, one per lane
+  float ge[2][4][32];    // the voxel behind that group, for the lanes whose x pair straddles two groups
+  float pts[2][96];      // the tile's points (AoS, as in global memory); reused for d_pc on the way out
+  DpcPose pose;
+};
+
+// what a lane needs to fetch the four corner rows of its next cell
+struct DpcGatherPlan {
+  const float* g0;       // the 4-voxel group of (iz, iy, ix)
+  unsigned ok;           // bit r: row r = (k, jj) is inside the grid and the point is valid; bit 4: the x pair straddles
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
+  __shared__ __align__(16) DpcSplatBwdWarpSmem sm;
+  const int lane = threadIdx.x;
+  const int b = blockIdx.y;
+  const int V = a.V, Vz = a.Vz, N = a.N;
+  const int tiles = (N + 31) >> 5;
+  const int wps = gridDim.x;
+  const float* dv = a.d_vox + (size_t)b * Vz * V * V;
+  const float* pc_b = a.pc + (size_t)b * N * 3;
+  const float* tr_b = a.tr_pc + (size_t)b * N * 3;
+  int t = blockIdx.x;
+  if (t >= tiles) return;
+  const bool kt = dpc_kt_enabled();      // read once: a load of the flag behind the grid dependency would sit on the critical path
+
+  auto issue_points = [&](int tt, int buf) {
+    const int n3 = min(32, N - tt * 32) * 3;
+    const float* src = pc_b + (size_t)tt * 96;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int i = lane + 32 * c;
+      dpc_cp_async4(&sm.pts[buf][i], i < n3 ? src + i : pc_b, i < n3);
+    }
+  };
+  auto plan = [&](float z, float y, float x) {
+    const DpcCell c = dpc_cell(z, y, x, Vz, V);
+    const int o4 = c.ix & 3;
+    DpcGatherPlan g;
+    g.g0 = dv + (c.iz * V + c.iy) * V + (c.ix - o4);
+    g.ok = 0u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (c.valid && (c.iz + (r >> 1) < Vz) && (c.iy + (r & 1) < V)) g.ok |= 1u << r;
+    if ((o4 == 3) && (c.ix + 1 < V)) g.ok |= 16u;
+    return g;
+  };
+  auto issue_row = [&](const DpcGatherPlan& g, int r, int buf) {
+    const bool ok = (g.ok >> r) & 1u, ex = ok && (g.ok & 16u);
+    const float* rp = ok ? g.g0 + ((r >> 1) * V + (r & 1)) * V : dv;
+    dpc_cp_async16(&sm.gq[buf][r][lane], rp, ok);
+    dpc_cp_async4(&sm.ge[buf][r][lane], ex ? rp + 4 : dv, ex);
+  };
+  // tr_pc of a tile: loaded one iteration before the cell is needed (the raw values stay in flight, the cell is computed late)
+  float rz, ry, rx;
+  auto load_raw = [&](int tt) {
+    const int i = tt * 32 + lane;
+    rz = ry = rx = 2.0f;        // outside the grid: an invalid cell
+    if (i < N) { rz = __ldg(tr_b + (size_t)i * 3 + 0); ry = __ldg(tr_b + (size_t)i * 3 + 1); rx = __ldg(tr_b + (size_t)i * 3 + 2); }
+  };
+
+  // prologue: tr_pc, the points and the camera are forward data (nothing in front of this kernel writes them)
+  dpc_kt_mark_if(kt, DPC_KT_SPLAT_B, 0);
+  dpc_grid_dep_trigger();
+  load_raw(t);
+  issue_points(t, 0);
+  if (lane == 0) dpc_pose_load(sm.pose, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  {
+    const DpcGatherPlan g = plan(rz, ry, rx);
+    if (t + wps < tiles) load_raw(t + wps);
+    dpc_grid_dep_wait();
+    dpc_kt_mark_if(kt, DPC_KT_SPLAT_B, 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) issue_row(g, r, 0);
+  }
+  dpc_cp_async_commit();
+  if (a.d_scale_part && blockIdx.x == 0) {
+    float v = 0.0f;
+    for (int q = lane; q < a.n_part; q += 32) v += a.d_scale_part[(size_t)b * a.n_part + q];
+    v = dpc_warp_sum(v);
+    if (lane == 0) a.d_scale_out[b] = v;
+  }
+
+  float acc[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) acc[q] = 0.0f;
+  const bool want_tf = (a.d_trans != nullptr) || (a.d_focal != nullptr);
+  int buf = 0;
+  for (; t < tiles; t += wps, buf ^= 1) {
+    const int tn = t + wps;
+    const bool more = tn < tiles;                  // warp-uniform
+    dpc_cp_async_wait<0>();                        // this tile's points and corners (issued during the previous tile)
+    __syncwarp();                                  // ... of every lane; also: the pose (first iteration)
+    DpcGatherPlan gn;
+    gn.g0 = dv; gn.ok = 0u;
+    if (more) {
+      issue_points(tn, buf ^ 1);
+      gn = plan(rz, ry, rx);
+      issue_row(gn, 0, buf ^ 1);
+      if (tn + wps < tiles) load_raw(tn + wps);
+    }
+
+    const int i = t * 32 + lane;
+    const int n = min(32, N - t * 32);
+    const bool live = lane < n;
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, z = 0.f, y = 0.f, x = 0.f;
+    DpcCamPoint cam;
+    cam.xs = cam.ys = 0.f; cam.zs = 1.f;
+    if (live) {
+      p0 = sm.pts[buf][lane * 3 + 0]; p1 = sm.pts[buf][lane * 3 + 1]; p2 = sm.pts[buf][lane * 3 + 2];
+      dpc_transform_point(sm.pose, p0, p1, p2, z, y, x, cam);
+    }
+    if (more) issue_row(gn, 1, buf ^ 1);
+    DpcCell c = dpc_cell(z, y, x, Vz, V);      // the forward's cell again: same code, same inputs as the prefetch's tr_pc
+    c.valid = c.valid && live;
+    float gz = 0.f, gy = 0.f, gx = 0.f;
+    if (c.valid) {
+      const int o4 = c.ix & 3;
+      const float wz[2] = {1.0f - c.rz, c.rz}, wy[2] = {1.0f - c.ry, c.ry}, wx[2] = {1.0f - c.rx, c.rx};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = r >> 1, jj = r & 1;
+        const float4 q4 = sm.gq[buf][r][lane];
+        const float e = sm.ge[buf][r][lane];
+        const float w0 = o4 == 0 ? q4.x : (o4 == 1 ? q4.y : (o4 == 2 ? q4.z : q4.w));
+        const float w1 = o4 == 0 ? q4.y : (o4 == 1 ? q4.z : (o4 == 2 ? q4.w : e));
+        if (c.iz + k < Vz && c.iy + jj < V) {
+          // same expression order as dpc_splat_bwd_kernel (corner ii = 0 before ii = 1)
+          gz += (k ? w0 : -w0) * (wy[jj] * wx[0]);
+          gy += (jj ? w0 : -w0) * (wz[k] * wx[0]);
+          gx += (-w0) * (wz[k] * wy[jj]);
+          if (c.ix + 1 < V) {
+            gz += (k ? w1 : -w1) * (wy[jj] * wx[1]);
+            gy += (jj ? w1 : -w1) * (wz[k] * wx[1]);
+            gx += w1 * (wz[k] * wy[jj]);
+          }
+        }
+      }
+      gz *= (float)(Vz - 1); gy *= (float)(V - 1); gx *= (float)(V - 1);
+    }
+    if (more) { issue_row(gn, 2, buf ^ 1); issue_row(gn, 3, buf ^ 1); }
+    dpc_cp_async_commit();
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (live) {
+      const size_t pi = (size_t)b * N + i;
+      if (a.d_tr_pc_in) { gz += a.d_tr_pc_in[pi * 3 + 0]; gy += a.d_tr_pc_in[pi * 3 + 1]; gx += a.d_tr_pc_in[pi * 3 + 2]; }
+      dpc_transform_point_bwd(sm.pose, p0, p1, p2, cam, gz, gy, gx, d0, d1, d2, acc, want_tf);
+    }
+    if (a.d_pc) {
+      if (live) { sm.pts[buf][lane * 3 + 0] = d0; sm.pts[buf][lane * 3 + 1] = d1; sm.pts[buf][lane * 3 + 2] = d2; }
+      __syncwarp();
+      float* dst = a.d_pc + ((size_t)b * N + (size_t)t * 32) * 3;
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int q = lane + 32 * cc;
+        if (q < n * 3) dst[q] = sm.pts[buf][q];
+      }
+    }
+    __syncwarp();   // the buffer is free for the prefetch of the tile after next
+  }
+  dpc_cp_async_wait<0>();
+  dpc_kt_mark_if(kt, DPC_KT_SPLAT_B, 3);
+  if (a.pose_kind == DPC_POSE_NONE) return;
+  const bool want_pose = a.d_pose != nullptr, want_t = a.d_trans != nullptr, want_f = a.d_focal != nullptr;
+  if (!(want_pose || want_t || want_f)) return;
+  const int q_lo = (a.pose_kind == DPC_POSE_QUAT && !want_pose) ? 4 : 0;
+  const int q_hi = (a.pose_kind == DPC_POSE_QUAT) ? (want_f ? 8 : (want_t ? 7 : 4)) : 12;
+  float red[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) red[q] = (q < q_lo || q >= q_hi) ? 0.0f : dpc_warp_sum(acc[q]);
+  if (lane == 0) {
+    if (a.pose_kind == DPC_POSE_QUAT) {
+      if (want_pose) {
+        float dq[4];
+        dpc_quat_norm_bwd(sm.pose, red, dq);
+        for (int q = 0; q < 4; ++q) atomicAdd(a.d_pose + b * 4 + q, dq[q]);
+      }
+      if (want_t) for (int q = 0; q < 3; ++q) atomicAdd(a.d_trans + b * 3 + q, red[4 + q]);
+      if (want_f) atomicAdd(a.d_focal + b, red[7]);
+    } else if (want_pose) {
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(a.d_pose + b * 16 + 0 + k, red[0 + k]);
+        atomicAdd(a.d_pose + b * 16 + 4 + k, red[4 + k] * a.focal_const);
+        atomicAdd(a.d_pose + b * 16 + 8 + k, red[8 + k] * a.focal_const);
+      }
+    }
+  }
+}
+#endif
 
 // ------------------------------------------------------------------------------ grid zeroing (lab build: knob 10)
 #ifdef DPC_EXPERIMENTS

@@ -97,6 +97,11 @@ int dpc_debug_stage_ms(float* out6);
 int dpc_debug_phase_read(unsigned long long* host_out);
 int dpc_debug_mma_bench(long long* out, int nctas, int threads, int reps, int nmma, int spin, int M, int N, void* stream);
 int dpc_debug_trace_read(long long* host_out);
+/* gather_bench: the splat backward's access pattern alone (B x N threads each gather the 2 x 2 rows of a random cell of a
+ * [B,V,V,V] grid); variant 0 = the product kernel's loads issued ideally, 1-6 see csrc/dpc_gather_bench.cuh;
+ * scripts/gather_bench.py */
+int dpc_debug_gather_bench(const float* grid, float* out, int B, int N, int V, int variant, int threads, int ppt,
+                           int share_log2, int smem_pad, int cg, void* stream);
 #endif
 /* compiled for sm_100a?  1 = real CUDA build, 0 = the CPU emulation build used by tests/emu */
 int dpc_is_cuda_build(void);
