@@ -238,6 +238,21 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.red4 = g_tune[11] ? 1 : 0;
   a.sel = sel; a.N_src = N_src;
   a.zero_u32 = zero_u32; a.n_zero = n_zero;
+#ifndef DPC_EMU
+  // software-pipelined form (dpc_splat_fwd_warp_kernel), same grid sizing as the backward's; lab build: knob 0 = 1 / 2 /
+  // 8 selects the tile-per-CTA kernel with 1 / 2 / 4 points per thread, knob 19 = warps per SM the grid is sized for
+  if (g_tune[0] == 4 && !rgb && !sel && !zero_u32) {
+    const int tiles = (N + 31) / 32;
+    const int per_sm = g_tune[19] > 0 ? g_tune[19] : 28;
+    const long long cap = (long long)dpc_tc_sm_count() * per_sm;
+    const int k = (int)(((long long)B * tiles + cap - 1) / cap);
+    const int wps = (tiles + k - 1) / k;
+    const dim3 g((wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC, B), blk(32 * DPC_SPLAT_WPC);
+    if (per_sm > 24) { DPC_LAUNCH(dpc_splat_fwd_warp_kernel<7>, g, blk, 0, stream, a); }
+    else { DPC_LAUNCH(dpc_splat_fwd_warp_kernel<6>, g, blk, 0, stream, a); }
+    return dpc_check_launch();
+  }
+#endif
   const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH(dpc_splat_fwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -287,7 +302,7 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   dim3 grid((N + tile - 1) / tile, B);
 #ifndef DPC_EMU
   // Default whenever the forward's tr_pc is at hand (the fused path passes it): the software-pipelined form,
-  // dpc_splat_bwd_warp_kernel -- one warp per CTA, every warp resident at once, k tiles of 32 points per warp with k the
+  // dpc_splat_bwd_warp_kernel -- independent warps, every warp resident at once, k tiles of 32 points per warp with k the
   // smallest count for which the grid fits 28 warps per SM (13.6-14.0 us against 20.0 us of the tile-per-CTA kernel at
   // B=32, N=8000; 24 warps per SM, i.e. k = 3: 15.1 us; profiles/r02_w_splat_bwd_warp.md).  Lab build: knob 20 = 6
   // forces the tile-per-CTA kernel, knob 19 = warps per SM the grid is sized for.
@@ -298,11 +313,11 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
     const long long cap = (long long)dpc_tc_sm_count() * per_sm;
     const int k = (int)(((long long)B * tiles + cap - 1) / cap);
     const int wps = (tiles + k - 1) / k;
-    void (*kw)(DpcSplatBwdArgs) = per_sm > 24 ? dpc_splat_bwd_warp_kernel<28> : dpc_splat_bwd_warp_kernel<24>;
+    void (*kw)(DpcSplatBwdArgs) = per_sm > 24 ? dpc_splat_bwd_warp_kernel<7> : dpc_splat_bwd_warp_kernel<6>;
     // 28 x 7 KB of static shared memory per SM need the large carve-out (per device, so set on every call like the
     // dynamic-shared-memory limits of the other launchers; a host-side attribute, legal during stream capture)
     if (cudaFuncSetAttribute(kw, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return DPC_ERR_CUDA;
-    DPC_LAUNCH(kw, dim3(wps, B), dim3(32), 0, stream, a);
+    DPC_LAUNCH(kw, dim3((wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC, B), dim3(32 * DPC_SPLAT_WPC), 0, stream, a);
     return dpc_check_launch();
   }
 #endif

@@ -585,8 +585,8 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------ backward, software-pipelined form
-// One warp per CTA, k tiles of 32 points each (tiles j, j + wps, ... of sample blockIdx.y), every warp of the grid
-// resident at once.  What the tile-per-CTA kernel above cannot do -- its CTAs walk stage / transform / gather / chain
+// Every warp is an independent worker with k tiles of 32 points each (tiles j, j + wps, ... of sample blockIdx.y;
+// DPC_SPLAT_WPC warps share a CTA only for the launch rate and the sample's camera), every warp of the grid resident at once.  What the tile-per-CTA kernel above cannot do -- its CTAs walk stage / transform / gather / chain
 // rule in lock-step, so an SM alternates between waiting for memory and being issue-bound (scripts/gather_bench.py: the
 // gathers alone take 4 us, that kernel 20) -- this one does by prefetching: the cells of the NEXT tile are known from the
 // forward's tr_pc (12 B per point, no transform needed), so its corner rows and its points are fetched with cp.async
@@ -610,12 +610,13 @@ DPC_DEV void dpc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "
 template <int N_PENDING>
 DPC_DEV void dpc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
 
-struct DpcSplatBwdWarpSmem {
+struct DpcSplatBwdWarpSmem {   // per warp
   float4 gq[2][4][32];   // per buffer, per (z, y) row of the cell: the 4-voxel group that holds ix, one per lane
   float ge[2][4][32];    // the voxel behind that group, for the lanes whose x pair straddles two groups
   float pts[2][96];      // the tile's points (AoS, as in global memory); reused for d_pc on the way out
-  DpcPose pose;
 };
+#define DPC_SPLAT_WPC 4      // warps per CTA of the software-pipelined splat kernels: the warps are independent workers, the
+                             // CTA only exists because 1-warp CTAs launch at ~0.45 per ns (4000 of them: 9 us)
 
 // what a lane needs to fetch the four corner rows of its next cell
 struct DpcGatherPlan {
@@ -624,18 +625,19 @@ struct DpcGatherPlan {
 };
 
 template <int MINB>
-__global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
-  __shared__ __align__(16) DpcSplatBwdWarpSmem sm;
-  const int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
+  __shared__ __align__(16) DpcSplatBwdWarpSmem sm_all[DPC_SPLAT_WPC];
+  __shared__ DpcPose pose_sm;
+  DpcSplatBwdWarpSmem& sm = sm_all[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int V = a.V, Vz = a.Vz, N = a.N;
   const int tiles = (N + 31) >> 5;
-  const int wps = gridDim.x;
+  const int wps = gridDim.x * DPC_SPLAT_WPC;
   const float* dv = a.d_vox + (size_t)b * Vz * V * V;
   const float* pc_b = a.pc + (size_t)b * N * 3;
   const float* tr_b = a.tr_pc + (size_t)b * N * 3;
-  int t = blockIdx.x;
-  if (t >= tiles) return;
+  int t = blockIdx.x * DPC_SPLAT_WPC + (threadIdx.x >> 5);
   const bool kt = dpc_kt_enabled();      // read once: a load of the flag behind the grid dependency would sit on the critical path
 
   auto issue_points = [&](int tt, int buf) {
@@ -676,9 +678,10 @@ __global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBw
   // prologue: tr_pc, the points and the camera are forward data (nothing in front of this kernel writes them)
   dpc_kt_mark_if(kt, DPC_KT_SPLAT_B, 0);
   dpc_grid_dep_trigger();
-  load_raw(t);
-  issue_points(t, 0);
-  if (lane == 0) dpc_pose_load(sm.pose, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  if (t < tiles) { load_raw(t); issue_points(t, 0); }
+  if (threadIdx.x == 0) dpc_pose_load(pose_sm, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  __syncthreads();               // the only CTA-wide step: the camera of the sample
+  if (t >= tiles) return;
   {
     const DpcGatherPlan g = plan(rz, ry, rx);
     if (t + wps < tiles) load_raw(t + wps);
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBw
     for (int r = 0; r < 4; ++r) issue_row(g, r, 0);
   }
   dpc_cp_async_commit();
-  if (a.d_scale_part && blockIdx.x == 0) {
+  if (a.d_scale_part && blockIdx.x == 0 && threadIdx.x < 32) {
     float v = 0.0f;
     for (int q = lane; q < a.n_part; q += 32) v += a.d_scale_part[(size_t)b * a.n_part + q];
     v = dpc_warp_sum(v);
@@ -704,7 +707,7 @@ __global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBw
     const int tn = t + wps;
     const bool more = tn < tiles;                  // warp-uniform
     dpc_cp_async_wait<0>();                        // this tile's points and corners (issued during the previous tile)
-    __syncwarp();                                  // ... of every lane; also: the pose (first iteration)
+    __syncwarp();                                  // ... of every lane
     DpcGatherPlan gn;
     gn.g0 = dv; gn.ok = 0u;
     if (more) {
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBw
     cam.xs = cam.ys = 0.f; cam.zs = 1.f;
     if (live) {
       p0 = sm.pts[buf][lane * 3 + 0]; p1 = sm.pts[buf][lane * 3 + 1]; p2 = sm.pts[buf][lane * 3 + 2];
-      dpc_transform_point(sm.pose, p0, p1, p2, z, y, x, cam);
+      dpc_transform_point(pose_sm, p0, p1, p2, z, y, x, cam);
     }
     if (more) issue_row(gn, 1, buf ^ 1);
     DpcCell c = dpc_cell(z, y, x, Vz, V);      // the forward's cell again: same code, same inputs as the prefetch's tr_pc
@@ -758,7 +761,7 @@ __global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBw
     if (live) {
       const size_t pi = (size_t)b * N + i;
       if (a.d_tr_pc_in) { gz += a.d_tr_pc_in[pi * 3 + 0]; gy += a.d_tr_pc_in[pi * 3 + 1]; gx += a.d_tr_pc_in[pi * 3 + 2]; }
-      dpc_transform_point_bwd(sm.pose, p0, p1, p2, cam, gz, gy, gx, d0, d1, d2, acc, want_tf);
+      dpc_transform_point_bwd(pose_sm, p0, p1, p2, cam, gz, gy, gx, d0, d1, d2, acc, want_tf);
     }
     if (a.d_pc) {
       if (live) { sm.pts[buf][lane * 3 + 0] = d0; sm.pts[buf][lane * 3 + 1] = d1; sm.pts[buf][lane * 3 + 2] = d2; }
@@ -786,7 +789,7 @@ __global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBw
     if (a.pose_kind == DPC_POSE_QUAT) {
       if (want_pose) {
         float dq[4];
-        dpc_quat_norm_bwd(sm.pose, red, dq);
+        dpc_quat_norm_bwd(pose_sm, red, dq);
         for (int q = 0; q < 4; ++q) atomicAdd(a.d_pose + b * 4 + q, dq[q]);
       }
       if (want_t) for (int q = 0; q < 3; ++q) atomicAdd(a.d_trans + b * 3 + q, red[4 + q]);
@@ -799,6 +802,147 @@ __global__ void __launch_bounds__(32, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBw
       }
     }
   }
+}
+#endif
+
+// ------------------------------------------------------------------------------ forward, software-pipelined form
+// The forward splat in the shape of dpc_splat_bwd_warp_kernel: independent warps, k tiles of 32 points per warp, every
+// warp resident at once, the next tile's points prefetched with cp.async while the current tile is transformed, written
+// back as tr_pc and reduced into the grid.  The tile-per-CTA kernel above runs 256 CTAs of 1024 points on 148 SMs (108
+// SMs get two CTAs, 40 get one) with 8-16 warps per SM; here every SM gets its 54 tiles and 27 warps.
+// Same device functions for the transform and the cell => tr_pc and the voxel indices stay bit-exact.
+// Preconditions (launcher): no rgb, no dropout list, no counters to zero.
+#ifndef DPC_EMU
+template <int MINB>
+__global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
+  __shared__ __align__(16) float pts_all[DPC_SPLAT_WPC][2][96];
+  __shared__ DpcPose pose_sm;
+  float (*pts)[96] = pts_all[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int V = a.V, Vz = a.Vz, N = a.N;
+  const int tiles = (N + 31) >> 5;
+  const int wps = gridDim.x * DPC_SPLAT_WPC;
+  const float* pc_b = a.pc + (size_t)b * N * 3;
+  int t = blockIdx.x * DPC_SPLAT_WPC + (threadIdx.x >> 5);
+  const bool kt = dpc_kt_enabled();
+  auto issue_points = [&](int tt, int buf) {
+    const int n3 = min(32, N - tt * 32) * 3;
+    const float* src = pc_b + (size_t)tt * 96;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int i = lane + 32 * c;
+      dpc_cp_async4(&pts[buf][i], i < n3 ? src + i : pc_b, i < n3);
+    }
+  };
+  dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 0);
+  dpc_grid_dep_trigger();
+  // the points and the camera are inputs: nothing in front of this kernel writes them (see dpc_splat_fwd_kernel)
+  if (t < tiles) issue_points(t, 0);
+  dpc_cp_async_commit();
+  if (threadIdx.x == 0) dpc_pose_load(pose_sm, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
+  __syncthreads();               // the only CTA-wide step: the camera of the sample
+  if (t >= tiles) return;
+  bool waited = false;
+  if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
+  float* grid = a.vox ? a.vox + (size_t)b * Vz * V * V : nullptr;
+  const bool quad_al = a.red4 && ((V & 3) == 0) && ((((uintptr_t)a.vox) & 15u) == 0);
+  const bool pair_al = ((V & 1) == 0) && ((((uintptr_t)a.vox) & 7u) == 0);
+  int buf = 0;
+  for (; t < tiles; t += wps, buf ^= 1) {
+    const int tn = t + wps;
+    dpc_cp_async_wait<0>();
+    __syncwarp();
+    if (tn < tiles) issue_points(tn, buf ^ 1);
+    dpc_cp_async_commit();
+    const int n = min(32, N - t * 32);
+    const bool live = lane < n;
+    float z = 0.f, y = 0.f, x = 0.f;
+    if (live) {
+      DpcCamPoint cam;
+      dpc_transform_point(pose_sm, pts[buf][lane * 3 + 0], pts[buf][lane * 3 + 1], pts[buf][lane * 3 + 2], z, y, x, cam);
+    }
+    if (a.tr_pc) {
+      if (live) { pts[buf][lane * 3 + 0] = z; pts[buf][lane * 3 + 1] = y; pts[buf][lane * 3 + 2] = x; }
+      __syncwarp();
+      float* dst = a.tr_pc + ((size_t)b * N + (size_t)t * 32) * 3;
+      if (!waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }   // first global write
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int q = lane + 32 * cc;
+        if (q < n * 3) dst[q] = pts[buf][q];
+      }
+    }
+    if (!waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
+    DpcCell c = dpc_cell(z, y, x, Vz, V);
+    c.valid = c.valid && live;
+    if (live) {
+      const size_t pi = (size_t)b * N + (size_t)t * 32 + lane;
+      if (a.idx_out) { a.idx_out[pi * 3 + 0] = c.iz; a.idx_out[pi * 3 + 1] = c.iy; a.idx_out[pi * 3 + 2] = c.ix; }
+      if (a.valid_out) a.valid_out[pi] = c.valid ? 1 : 0;
+    }
+    if (grid) {
+      // corner weights, reference association: (rr[k].z * rr[j].y) * rr[i].x  (point_cloud.py:99)
+      const float wz[2] = {__fsub_rn(1.0f, c.rz), c.rz};
+      const float wy[2] = {__fsub_rn(1.0f, c.ry), c.ry};
+      const float wx[2] = {__fsub_rn(1.0f, c.rx), c.rx};
+      float w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w[q] = c.valid ? __fmul_rn(__fmul_rn(wz[q >> 2], wy[(q >> 1) & 1]), wx[q & 1]) : 0.0f;
+      const int base = (c.iz * V + c.iy) * V + c.ix;
+      // warp aggregation of lanes that share a base voxel (see dpc_splat_fwd_kernel)
+      const int key = c.valid ? base : (-1 - lane);
+      const unsigned peers = __match_any_sync(DPC_FULL, key);
+      const int cnt = __popc(peers);
+      const int maxcnt = __reduce_max_sync(DPC_FULL, cnt);
+      if (maxcnt > 1) {
+        float s8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s8[q] = w[q];
+        unsigned rem = peers & ~(1u << lane);
+        for (int it = 1; it < maxcnt; ++it) {
+          const int src = rem ? (__ffs(rem) - 1) : lane;
+          rem &= rem - 1;
+          const bool take = it < cnt;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float v = __shfl_sync(DPC_FULL, w[q], src);
+            if (take) s8[q] += v;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w[q] = s8[q];
+      }
+      if (c.valid && (lane == (__ffs(peers) - 1))) {
+        float* g = grid + base;
+        const int o4 = c.ix & 3;
+        const bool quad_ok = quad_al && (o4 != 3);
+        const bool pair_ok = pair_al && ((c.ix & 1) == 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (c.iz + k >= Vz) continue;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            if (c.iy + jj >= V) continue;
+            float* row = g + (k * V + jj) * V;
+            const float w0 = w[k * 4 + jj * 2 + 0], w1 = w[k * 4 + jj * 2 + 1];
+            if (quad_ok) {
+              dpc_red_add4(row - o4, o4 == 0 ? w0 : 0.0f, o4 == 0 ? w1 : (o4 == 1 ? w0 : 0.0f),
+                           o4 == 1 ? w1 : (o4 == 2 ? w0 : 0.0f), o4 == 2 ? w1 : 0.0f);
+            } else if (pair_ok) {
+              dpc_red_add2(row, w0, w1);
+            } else {
+              dpc_red_add(row, w0);
+              if (c.ix + 1 < V) dpc_red_add(row + 1, w1);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  dpc_cp_async_wait<0>();
+  dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 3);
 }
 #endif
 
