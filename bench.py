@@ -38,14 +38,14 @@ FULL_PATH_BYTES = 6 * G_BYTES + 4 * 12 * N + 64 * N + 2 * 4 * V * V
 # very command (profiles/r01_p_final_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
 # previous kernel left in L2 are re-read from HBM, and the 32 MiB of output stays in L2 until a later kernel evicts it)
 NCU_TRAFFIC_B32 = {
-    "splat_fwd": 22.228224e6 + 0.000256e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
-    "conv_xy_fwd": 33.595392e6 + 0.006656e6,
-    "conv_z_fwd": 33.594624e6 + 1.164032e6,
-    "conv_z_bwd": 35.166720e6 + 0.963584e6,
-    "conv_xy_bwd": 34.642176e6 + 0.0,
-    "splat_bwd": 26.727936e6 + 0.018432e6,
+    "splat_fwd": 22.458880e6 + 0.077056e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
+    "conv_xy_fwd": 33.595904e6 + 0.047104e6,
+    "conv_z_fwd": 33.594112e6 + 0.878336e6,
+    "conv_z_bwd": 35.167232e6 + 0.461568e6,
+    "conv_xy_bwd": 34.641920e6 + 0.022016e6,
+    "splat_bwd": 29.796864e6 + 0.000768e6,      # the software-pipelined form also reads the forward's tr_pc (3 MB)
 }
-NCU_TRAFFIC_SOURCE = "ncu --set full, dram read+write per launch, profiles/r02_p_final_ncu_summary.md"
+NCU_TRAFFIC_SOURCE = "ncu --set full, dram read+write per launch, profiles/r02_w_final_ncu_summary.md"
 STAGE_BYTES = {
     "splat_fwd": G_BYTES + 2 * 12 * N + 32 * N,          # zero grid + read pc + write tr_pc + 8 corner RMW
     "conv_xy_fwd": 2 * G_BYTES + G_BYTES // 32,          # read raw, write xy-smoothed, clip-mask bits
