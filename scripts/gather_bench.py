@@ -55,7 +55,11 @@ for threads in (64, 128, 256, 512):
     print("  %4d threads: " % threads + "  ".join("ppt %d %6.2f" % (p, run(0, threads, p)) for p in (1, 2, 4, 8)), flush=True)
 print("\n-- product pattern: resident CTAs per SM limited by dynamic shared memory (128-thread CTAs)")
 for pad_kb, label in ((0, "unlimited"), (14, "16/SM"), (28, "8/SM"), (37, "6/SM"), (56, "4/SM"), (75, "3/SM"), (112, "2/SM"), (200, "1/SM")):
-    print("  %-10s %6.2f us   var 1: %6.2f   var 3 (dependent): %6.2f   var 7 (cp.async): %6.2f" % (label, run(0, pad=pad_kb * 1024), run(1, pad=pad_kb * 1024), run(3, pad=pad_kb * 1024), run(7, pad=max(0, pad_kb - 6) * 1024)), flush=True)
+    try:        # variant 7 holds 5 KB of static shared memory itself
+        v7 = "%6.2f" % run(7, pad=max(0, pad_kb - 6) * 1024)
+    except Exception as exc:
+        v7 = "n/a (%s)" % (str(exc)[:40],)
+    print("  %-10s %6.2f us   var 1: %6.2f   var 3 (dependent): %6.2f   var 7 (cp.async): %s" % (label, run(0, pad=pad_kb * 1024), run(1, pad=pad_kb * 1024), run(3, pad=pad_kb * 1024), v7), flush=True)
 print("\n-- lanes sharing a cell in groups of 2^s (distinct lines per load instruction / 2^s; sectors from L2 / 2^s)")
 for s in range(6):
     print("  s=%d: var 0 %6.2f   var 1 %6.2f   var 2 %6.2f   var 6 %6.2f" % (s, run(0, share=s), run(1, share=s), run(2, share=s), run(6, share=s)), flush=True)
