@@ -62,7 +62,9 @@ int dpc_last_cuda_error(void);
  * libdpc_b200_lab.so; dpc_is_lab_build() == 1); the product build returns DPC_ERR_ARG for them, compiles their defaults
  * in as constants and does not contain the experimental kernels.  Lab keys (every value gives the same results --
  * tests/test_gpu_parity.py::test_splat_variants_full_shape):
- *   0 / 1  points per thread of the forward / backward splat kernel (1|2|4; defaults 4 / 1)
+ *   0 / 1  points per thread of the tile-per-CTA forward / backward splat kernel (1|2|4; defaults 4 / 1).  Key 0 also
+ *          selects the forward kernel: 4 (default) = the software-pipelined dpc_splat_fwd_warp_kernel, 8 = the
+ *          tile-per-CTA kernel with 4 points per thread, 1 / 2 = that kernel with 1 / 2
  *   2      1 = the producer warps of the x/y pipeline store the finished tiles; 2 = 3-slot staging ring (default 0)
  *   4      1 = the gathers of the splat backward run inside the x/y pass of the backward (csrc/dpc_fused_bwd.cuh; needs
  *          dpc_project_params.tr_pc; default 0: measured slower, profiles/r02_f_fused_gather.md); 16 = its debug flags,
@@ -77,8 +79,12 @@ int dpc_last_cuda_error(void);
  *   13     1 = keep the zeroing launch + dL/dscale atomics in the fused backward (default 0: folded partial sums)
  *   14     1 = the backward splat stages + transforms ahead of its grid dependency (default)
  *   15     1 = x/y pass in place, backward in the raw grid's storage: two grids per step (default)
- *   18-20  splat backward: 128-thread CTAs / compiled for 75 % occupancy / gather style (1 = independent un-guarded
- *          loads, 2 = one guarded path); 22 = 1: gathers through ld.global.cg (profiles/r02_j_splat_bwd_occupancy.md)
+ *   18-20  tile-per-CTA splat backward: 128-thread CTAs / compiled for 75 % occupancy / gather style (1 = independent
+ *          un-guarded loads, 2 = one guarded path, 3 = predicated independent loads); 22 = 1: gathers through
+ *          ld.global.cg (profiles/r02_j_splat_bwd_occupancy.md).  Key 20 also selects the kernel: 0 (default) or 4 = the
+ *          software-pipelined dpc_splat_bwd_warp_kernel whenever dpc_project_params.tr_pc is given, 6 = the tile-per-CTA
+ *          kernel; with the pipelined kernels key 19 = the number of warps per SM the grid is sized for (default 28)
+ *          (profiles/r02_w_splat_bwd_warp.md)
  *   21     1 = x/y pass + depth pass of the forward as ONE persistent kernel (csrc/dpc_smooth_fused.cuh; default 0:
  *          measured no faster, profiles/r02_m_fused_fwd.md) */
 int dpc_debug_set(int key, int value);
@@ -196,9 +202,11 @@ typedef struct {
   const float* taps_xy_host;   /* optional host copy of taps_xy (K floats), or NULL */
   const float* taps_z_host;    /* optional host copy of taps_z (Kz floats), or NULL */
   const float* tr_pc;          /* backward only, optional (device, [B,N,3]): the tr_pc the forward of this call wrote.
-                                  With it (64^3 grids, training case) the gathers of the splat backward run inside the
-                                  x/y pass of the backward, on the cells the forward used; NULL = the splat backward
-                                  recomputes the camera transform and runs as its own kernel behind that pass */
+                                  With it the splat backward runs in its software-pipelined form: the cell of a point is
+                                  known without redoing the camera transform, so the gathers of the next 32 points are
+                                  prefetched while the current ones are computed (10 us instead of 20 us at B=32,
+                                  N=8000).  NULL = the tile-per-CTA kernel, which recomputes the transform first.  The
+                                  results are the same either way (the transform is recomputed for the chain rule in both) */
   const int32_t* sel;          /* optional (device, [B,N] int32): point dropout consumed by the splat's load stage
                                   (point_cloud.py:293-319).  pc and d_pc are then [B,N_src,3]; point i of sample b is
                                   pc[b, sel[b*N + i]] (indices of a sample distinct), tr_pc stays [B,N,3]; dropped points
