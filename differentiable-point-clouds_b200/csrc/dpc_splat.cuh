@@ -865,8 +865,7 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_k
     if (a.tr_pc) {
       if (live) { pts[buf][lane * 3 + 0] = z; pts[buf][lane * 3 + 1] = y; pts[buf][lane * 3 + 2] = x; }
       __syncwarp();
-      float* dst = a.tr_pc + ((size_t)b * N + (size_t)t * 32) * 3;
-      if (!waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }   // first global write
+      float* dst = a.tr_pc + ((size_t)b * N + (size_t)t * 32) * 3;    // early mode: written ahead of the dependency, as in dpc_splat_fwd_kernel
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
         const int q = lane + 32 * cc;
