@@ -143,18 +143,21 @@ def test_full_benchmark_shape_clustered_and_translation():
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0, trans=tr, host_sigma=True))
 
 
-@pytest.mark.parametrize("knob,value", [(2, 1), (4, 1), (10, 1), (10, 2), (11, 0), (13, 1), (14, 0), (15, 0)])
+@pytest.mark.parametrize("knob,value", [(2, 1), (4, 1), (10, 1), (10, 2), (11, 0), (13, 1), (14, 0), (15, 0),
+                                        (0, 8), (20, 6), (20, 3), (19, 1), (19, 24)])
 def test_splat_variants_full_shape(knob, value):
     """The experiment knobs of the fused path give the same results as the defaults, spread and clustered clouds:
     10 = 1 zeroing kernel + forward transform ahead of the grid dependency (default: cudaMemsetAsync); 11 = 0 8-byte /
     scalar reductions and gathers (default: 16-byte); 13 = 1 zeroing launch + dL/dscale atomics in the backward (default:
     folded partials); 14 = 0 wait-first backward splat; 15 = 0 x/y pass out of place, backward in the second grid;
     2 = 1 the producer warps of the x/y pipeline store the tiles; 4 = 1 the gathers of the splat backward inside the x/y pass
-    of the backward (dpc_fused_bwd.cuh) + chain-rule kernel."""
+    of the backward (dpc_fused_bwd.cuh) + chain-rule kernel; 0 = 8 / 20 = 6 the tile-per-CTA forward / backward splat
+    kernels instead of the software-pipelined ones, 20 = 3 predicated gathers in the tile-per-CTA backward; 19 = the
+    number of warps per SM the pipelined kernels' grids are sized for (1: four tiles per warp at this shape, 24: one)."""
     from dpc_b200 import _capi
     L = _capi.lab_lib()             # the experiment knobs exist only in the lab build of the sources
     product, _capi._LIB = _capi._LIB, L
-    default = {2: 0, 4: 0, 10: 0, 11: 1, 13: 0, 14: 1, 15: 1}[knob]
+    default = {2: 0, 4: 0, 10: 0, 11: 1, 13: 0, 14: 1, 15: 1, 0: 4, 19: 0, 20: 0}[knob]
     cfg = default_config(vox_size=64, pc_gauss_kernel_size=21)
     _capi.check(L.dpc_debug_set(knob, value))
     try:
@@ -163,6 +166,29 @@ def test_splat_variants_full_shape(knob, value):
             _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
     finally:
         L.dpc_debug_set(knob, default)
+        _capi._LIB = product
+
+
+@pytest.mark.parametrize("n,b,v", [(4001, 3, 32), (1000, 5, 32), (33, 2, 64)])
+def test_pipelined_splat_ragged_multi_tile(n, b, v):
+    """The software-pipelined splat kernels with several tiles per warp AND a ragged last tile (N % 32 != 0): the grid is
+    sized for ONE warp per SM (lab knob 19 = 1), so at N = 4001, B = 3 every warp walks three tiles of its sample."""
+    from dpc_b200 import _capi
+    L = _capi.lab_lib()
+    product, _capi._LIB = _capi._LIB, L
+    cfg = default_config(vox_size=v, pc_gauss_kernel_size=11)
+    _capi.check(L.dpc_debug_set(19, 1))
+    try:
+        g = torch.Generator().manual_seed(n)
+        pc = torch.tanh(0.5 * torch.randn(b, n, 3, generator=g)) / 2
+        q = torch.randn(b, 4, generator=g)
+        sc = torch.sigmoid(torch.randn(b, 1, generator=g))
+        gt = (torch.rand(b, v, v, 1, generator=g) > 0.5).float()
+        tr = 0.05 * torch.randn(b, 3, generator=g)
+        _compare(_run_both(cfg, pc, q, sc, gt, 3.0))
+        _compare(_run_both(cfg, pc, q, sc, gt, 3.0, trans=tr))
+    finally:
+        L.dpc_debug_set(19, 0)
         _capi._LIB = product
 
 
