@@ -220,7 +220,10 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
                             const float* focal, float focal_const, float cam_dist, const float* rgb,
                             int B, int N, int Vz, int V,
                             float* tr_pc, float* vox, float* vox_rgb, int32_t* idx_out, uint8_t* valid_out,
-                            const int32_t* sel, int N_src, void* stream, int early = 0, unsigned* zero_u32 = nullptr, int n_zero = 0) {
+                            const int32_t* sel, int N_src, void* stream, int early = 0, unsigned* zero_u32 = nullptr, int n_zero = 0,
+                            bool* zeroes_grid = nullptr) {
+  // zeroes_grid != NULL: the caller has NOT zeroed `vox`; *zeroes_grid comes back true when the splat kernel does it
+  // itself (dpc_splat_fwd_warp_kernel<.., true>, cooperative launch), false when the caller has to (then nothing was launched)
   // early (lab build): the stream predecessor is a grid-zeroing KERNEL; the splat then transforms ahead of its dependency
   if (!pc) return DPC_ERR_NULL;
   if (sel && (N_src < N || rgb)) return DPC_ERR_ARG;
@@ -245,14 +248,43 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
     const int tiles = (N + 31) / 32;
     const int per_sm = g_tune[19] > 0 ? g_tune[19] : 28;
     const long long cap = (long long)dpc_tc_sm_count() * per_sm;
-    const int k = (int)(((long long)B * tiles + cap - 1) / cap);
-    const int wps = (tiles + k - 1) / k;
-    const dim3 g((wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC, B), blk(32 * DPC_SPLAT_WPC);
-    if (per_sm > 24) { DPC_LAUNCH(dpc_splat_fwd_warp_kernel<7>, g, blk, 0, stream, a); }
-    else { DPC_LAUNCH(dpc_splat_fwd_warp_kernel<6>, g, blk, 0, stream, a); }
+    int k = (int)(((long long)B * tiles + cap - 1) / cap);
+    int wps = (tiles + k - 1) / k;
+    dim3 g((wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC, B);
+    const dim3 blk(32 * DPC_SPLAT_WPC);
+    if (zeroes_grid) {
+      // in-kernel zeroing needs every CTA resident (grid-wide barrier): cooperative launch, grid shrunk until it fits.
+      // Lab build only (knob 10 = 3): measured slower than the driver's memset in front of the kernel (zeros + barrier
+      // take 10 us inside the kernel, the memset 5 us: step 98.5 vs 96.4 us; profiles/r02_w_timeline_coop_zero.txt)
+      *zeroes_grid = false;
+#ifdef DPC_EXPERIMENTS
+      void (*kz)(DpcSplatArgs) = dpc_splat_fwd_warp_kernel<7, true>;
+      int per = 0;
+      if (g_tune[10] == 3 && vox && (V & 3) == 0 && ((((uintptr_t)vox) & 15u) == 0) &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kz, 32 * DPC_SPLAT_WPC, 0) == cudaSuccess && per > 0) {
+        const long long fit = (long long)per * dpc_tc_sm_count();
+        while ((long long)g.x * B > fit && wps > 1) { ++k; wps = (tiles + k - 1) / k; g.x = (wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC; }
+        if ((long long)g.x * B <= fit) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = g; cfg.blockDim = blk; cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeCooperative;
+          attr[0].val.cooperative = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          a.early = 0;
+          if (cudaLaunchKernelEx(&cfg, kz, a) == cudaSuccess) { *zeroes_grid = true; return dpc_check_launch(); }
+          cudaGetLastError();      // not launchable cooperatively here: the caller zeroes, the plain kernel follows
+        }
+      }
+#endif
+      return DPC_OK;
+    }
+    if (per_sm > 24) { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<7, false>), g, blk, 0, stream, a); }
+    else { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<6, false>), g, blk, 0, stream, a); }
     return dpc_check_launch();
   }
 #endif
+  if (zeroes_grid) { *zeroes_grid = false; return DPC_OK; }
   const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
   if (ppt == 4) { DPC_LAUNCH(dpc_splat_fwd_kernel<4>, grid, dim3(DPC_SPLAT_THREADS), 0, stream, a); }
@@ -623,7 +655,7 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
     } else
 #endif
 #ifdef DPC_EXPERIMENTS
-    if (g_tune[10]) {
+    if (g_tune[10] && g_tune[10] != 3) {
       const size_t n4 = (size_t)g / 4;
 #ifdef DPC_EMU
       const int zgrid = 2;
@@ -636,7 +668,15 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
     } else
 #endif
     {
-      DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
+      // lab knob 10 = 3: the splat kernel zeroes the grid itself (cooperative launch, dpc_splat_fwd_warp_kernel<.., true>)
+      bool done = false;
+      if (g_tune[10] == 3 && !(p->sel) && !g_tune[21]) {
+        DPC_TRY(splat_fwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
+                                 p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, nullptr, 0, stream, 0,
+                                 nullptr, 0, &done));
+      }
+      if (done) splat_early = 2;      // the splat has been launched already
+      else DPC_CUDA(cudaMemsetAsync(w.raw, 0, (size_t)g * 4, (cudaStream_t)stream));
     }
   }
   if (p->sel && p->N_src < p->N) return DPC_ERR_ARG;
@@ -648,9 +688,10 @@ int dpc_project_fast_fwd(const dpc_project_params* p,
   fused_xyz = g_tune[21] && !splat_early && dpc_tc_level() == 2 && p->V == 64 && p->Vz == 64 && K == Kz && tx == tz && hxy == hz &&
               !(p->flags & DPC_FLAG_SCRATCH_RAW_ZERO) && g_tune[15] && !drc_probs && !proj_depth;
 #endif
-  DPC_TRY(splat_fwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
-                           p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, p->sel, p->N_src, stream, splat_early,
-                           fused_xyz ? w.cnt : nullptr, p->B));
+  if (splat_early != 2)
+    DPC_TRY(splat_fwd_launch(pc, pose, p->pose_kind, trans, focal, p->focal_const, p->cam_dist, nullptr,
+                             p->B, p->N, p->Vz, p->V, tr_pc, w.raw, nullptr, nullptr, nullptr, p->sel, p->N_src, stream, splat_early,
+                             fused_xyz ? w.cnt : nullptr, p->B));
   stage_mark(1, stream);
   // clip + x/y smoothing.  With DPC_FLAG_SCRATCH_RAW_ZERO the pass also hands the raw grid back
   // all-zero (so the next forward needs no memset).  Measured on B200 (profiles/r01_d): not a win --

@@ -8,6 +8,9 @@
 // 8 corner weights are added to the single grid with warp-aggregated REDG (v2 where aligned).
 #pragma once
 #include "dpc_math.cuh"
+#ifndef DPC_EMU
+#include <cooperative_groups.h>
+#endif
 
 #define DPC_SPLAT_THREADS 256
 #define DPC_SPLAT_MAX_PPT 4
@@ -811,9 +814,12 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_bwd_warp_k
 // back as tr_pc and reduced into the grid.  The tile-per-CTA kernel above runs 256 CTAs of 1024 points on 148 SMs (108
 // SMs get two CTAs, 40 get one) with 8-16 warps per SM; here every SM gets its 54 tiles and 27 warps.
 // Same device functions for the transform and the cell => tr_pc and the voxel indices stay bit-exact.
+// ZERO: the kernel also zeroes the grid it reduces into (cooperative launch: every CTA stores its share of zeros right
+// after issuing its first loads, transforms its first tile while they drain, then a grid-wide barrier separates the zeros
+// from the first reduction) -- the fused forward then needs no memset node in front of it.
 // Preconditions (launcher): no rgb, no dropout list, no counters to zero.
 #ifndef DPC_EMU
-template <int MINB>
+template <int MINB, bool ZERO>
 __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
   __shared__ __align__(16) float pts_all[DPC_SPLAT_WPC][2][96];
   __shared__ DpcPose pose_sm;
@@ -841,38 +847,56 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_k
   if (t < tiles) issue_points(t, 0);
   dpc_cp_async_commit();
   if (threadIdx.x == 0) dpc_pose_load(pose_sm, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
-  __syncthreads();               // the only CTA-wide step: the camera of the sample
-  if (t >= tiles) return;
-  bool waited = false;
-  if (!a.early) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
+  if (ZERO) {
+    // launched without a programmatic dependency (everything older has completed): the zeros may go out at once
+    float4* z4 = reinterpret_cast<float4*>(a.vox);
+    const size_t n4 = (size_t)a.B * Vz * V * (V >> 2);
+    const size_t nth = (size_t)gridDim.x * gridDim.y * blockDim.x;
+    const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += nth) z4[i] = zz;
+  }
+  __syncthreads();               // the camera of the sample
+  bool waited = ZERO;
+  if (!ZERO && !a.early) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
   float* grid = a.vox ? a.vox + (size_t)b * Vz * V * V : nullptr;
   const bool quad_al = a.red4 && ((V & 3) == 0) && ((((uintptr_t)a.vox) & 15u) == 0);
   const bool pair_al = ((V & 1) == 0) && ((((uintptr_t)a.vox) & 7u) == 0);
-  int buf = 0;
-  for (; t < tiles; t += wps, buf ^= 1) {
-    const int tn = t + wps;
+  // front half of a tile: its points have been requested; transform them, write tr_pc, request the next tile's points
+  float z = 0.f, y = 0.f, x = 0.f;
+  bool live = false;
+  auto front = [&](int tt, int buf) {
     dpc_cp_async_wait<0>();
     __syncwarp();
-    if (tn < tiles) issue_points(tn, buf ^ 1);
+    if (tt + wps < tiles) issue_points(tt + wps, buf ^ 1);
     dpc_cp_async_commit();
-    const int n = min(32, N - t * 32);
-    const bool live = lane < n;
-    float z = 0.f, y = 0.f, x = 0.f;
+    const int n = min(32, N - tt * 32);
+    live = lane < n;
+    z = y = x = 0.f;
     if (live) {
       DpcCamPoint cam;
       dpc_transform_point(pose_sm, pts[buf][lane * 3 + 0], pts[buf][lane * 3 + 1], pts[buf][lane * 3 + 2], z, y, x, cam);
     }
-    if (a.tr_pc) {
+    if (a.tr_pc) {       // (early mode: written ahead of the grid dependency, as in dpc_splat_fwd_kernel)
       if (live) { pts[buf][lane * 3 + 0] = z; pts[buf][lane * 3 + 1] = y; pts[buf][lane * 3 + 2] = x; }
       __syncwarp();
-      float* dst = a.tr_pc + ((size_t)b * N + (size_t)t * 32) * 3;    // early mode: written ahead of the dependency, as in dpc_splat_fwd_kernel
+      float* dst = a.tr_pc + ((size_t)b * N + (size_t)tt * 32) * 3;
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
         const int q = lane + 32 * cc;
         if (q < n * 3) dst[q] = pts[buf][q];
       }
     }
-    if (!waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
+  };
+  if (t < tiles) front(t, 0);
+  if (ZERO) {
+    __threadfence();                         // my zeros are visible device-wide ...
+    cooperative_groups::this_grid().sync();  // ... and so are everybody else's: the grid is zero from here on
+    dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1);
+  }
+  if (t >= tiles) return;
+  if (!waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
+  int buf = 0;
+  while (true) {
     DpcCell c = dpc_cell(z, y, x, Vz, V);
     c.valid = c.valid && live;
     if (live) {
@@ -939,6 +963,10 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_k
       }
     }
     __syncwarp();
+    t += wps;
+    buf ^= 1;
+    if (t >= tiles) break;
+    front(t, buf);
   }
   dpc_cp_async_wait<0>();
   dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 3);

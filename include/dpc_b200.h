@@ -74,7 +74,8 @@ int dpc_last_cuda_error(void);
  *   7      conv_xy (FFMA2) diagnostics: 1 memory path only, 2 arithmetic only, 3 empty CTAs, 4/5 skip the x / y correlation
  *   9      1 = per-tile / per-CTA trace of the pipelines (dpc_debug_trace_read)
  *   10     zeroing of the raw grid in the fused forward: 0 cudaMemsetAsync + wait-first splat (default), 1 store kernel,
- *          2 TMA bulk-store kernel -- 1 and 2 as PDL primaries of a splat that transforms ahead of its grid dependency
+ *          2 TMA bulk-store kernel -- 1 and 2 as PDL primaries of a splat that transforms ahead of its grid dependency;
+ *          3 = the forward splat kernel zeroes the grid itself (cooperative launch, grid barrier before the reductions)
  *   11     1 = 16-byte reductions / gathers in the splats (default), 0 = 8-byte / scalar
  *   13     1 = keep the zeroing launch + dL/dscale atomics in the fused backward (default 0: folded partial sums)
  *   14     1 = the backward splat stages + transforms ahead of its grid dependency (default)

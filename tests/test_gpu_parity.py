@@ -143,11 +143,12 @@ def test_full_benchmark_shape_clustered_and_translation():
     _compare(_run_both(cfg, pc, q, sc, gt, 3.0, trans=tr, host_sigma=True))
 
 
-@pytest.mark.parametrize("knob,value", [(2, 1), (4, 1), (10, 1), (10, 2), (11, 0), (13, 1), (14, 0), (15, 0),
+@pytest.mark.parametrize("knob,value", [(2, 1), (4, 1), (10, 1), (10, 2), (10, 3), (11, 0), (13, 1), (14, 0), (15, 0),
                                         (0, 8), (20, 6), (20, 3), (19, 1), (19, 24)])
 def test_splat_variants_full_shape(knob, value):
     """The experiment knobs of the fused path give the same results as the defaults, spread and clustered clouds:
-    10 = 1 zeroing kernel + forward transform ahead of the grid dependency (default: cudaMemsetAsync); 11 = 0 8-byte /
+    10 = 1 / 2 zeroing kernel + forward transform ahead of the grid dependency, 3 = the splat zeroes its grid itself behind a
+    grid-wide barrier (default: cudaMemsetAsync); 11 = 0 8-byte /
     scalar reductions and gathers (default: 16-byte); 13 = 1 zeroing launch + dL/dscale atomics in the backward (default:
     folded partials); 14 = 0 wait-first backward splat; 15 = 0 x/y pass out of place, backward in the second grid;
     2 = 1 the producer warps of the x/y pipeline store the tiles; 4 = 1 the gathers of the splat backward inside the x/y pass
