@@ -35,7 +35,7 @@ G_BYTES = V * V * V * 4
 FULL_PATH_BYTES = 6 * G_BYTES + 4 * 12 * N + 64 * N + 2 * 4 * V * V
 # per-launch algorithmic bytes of each stage, per projection (DESIGN.md "kernels and rooflines")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B=32, from the committed `ncu --set full` capture of this
-# very command (profiles/r01_p_final_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
+# very command (profiles/r02_w_final_ncu_summary.md; cold caches: ncu flushes L2 before every kernel, so grids the
 # previous kernel left in L2 are re-read from HBM, and the 32 MiB of output stays in L2 until a later kernel evicts it)
 NCU_TRAFFIC_B32 = {
     "splat_fwd": 22.458880e6 + 0.077056e6,      # + 33.55 MB zero fill by cudaMemsetAsync (not a kernel of ours)
