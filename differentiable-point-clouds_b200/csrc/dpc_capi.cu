@@ -43,6 +43,14 @@ static DPC_KNOB_T g_tune[24] = {4, 1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 1, 0, 0, 1, 1, 
 //      instead of three)
 // measured after the 16-byte gathers (profiles/r01_m_*): forward 4 / 2 / 1 points per thread = 10.2 / 10.7 / 13.9 us,
 // backward 21.5 / 28.5 / 20.6 us -> forward 4 (250 CTAs), backward 1 (1000 CTAs)
+// SMs the pipelined splat kernels size their grids for (CPU emulation: 4, so that its tests walk several tiles per warp)
+static int splat_sm_count() {
+#ifndef DPC_EMU
+  return dpc_tc_sm_count();
+#else
+  return 4;
+#endif
+}
 static int tune_ppt(int which) { int v = g_tune[which]; return (v == 1 || v == 2 || v == 4) ? v : 4; }
 
 // ---- optional stage instrumentation of the fused path (dpc_debug_set(3, 1)): CUDA events are
@@ -241,13 +249,12 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.red4 = g_tune[11] ? 1 : 0;
   a.sel = sel; a.N_src = N_src;
   a.zero_u32 = zero_u32; a.n_zero = n_zero;
-#ifndef DPC_EMU
   // software-pipelined form (dpc_splat_fwd_warp_kernel), same grid sizing as the backward's; lab build: knob 0 = 1 / 2 /
   // 8 selects the tile-per-CTA kernel with 1 / 2 / 4 points per thread, knob 19 = warps per SM the grid is sized for
   if (g_tune[0] == 4 && !rgb && !sel && !zero_u32) {
     const int tiles = (N + 31) / 32;
     const int per_sm = g_tune[19] > 0 ? g_tune[19] : 28;
-    const long long cap = (long long)dpc_tc_sm_count() * per_sm;
+    const long long cap = (long long)splat_sm_count() * per_sm;
     int k = (int)(((long long)B * tiles + cap - 1) / cap);
     int wps = (tiles + k - 1) / k;
     dim3 g((wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC, B);
@@ -257,7 +264,7 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
       // Lab build only (knob 10 = 3): measured slower than the driver's memset in front of the kernel (zeros + barrier
       // take 10 us inside the kernel, the memset 5 us: step 98.5 vs 96.4 us; profiles/r02_w_timeline_coop_zero.txt)
       *zeroes_grid = false;
-#ifdef DPC_EXPERIMENTS
+#if defined(DPC_EXPERIMENTS) && !defined(DPC_EMU)
       void (*kz)(DpcSplatArgs) = dpc_splat_fwd_warp_kernel<7, true>;
       int per = 0;
       if (g_tune[10] == 3 && vox && (V & 3) == 0 && ((((uintptr_t)vox) & 15u) == 0) &&
@@ -283,7 +290,6 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
     else { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<6, false>), g, blk, 0, stream, a); }
     return dpc_check_launch();
   }
-#endif
   if (zeroes_grid) { *zeroes_grid = false; return DPC_OK; }
   const int ppt = tune_ppt(0), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
@@ -332,7 +338,6 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   if (sel && d_pc) DPC_CUDA(cudaMemsetAsync(d_pc, 0, (size_t)B * N_src * 12, (cudaStream_t)stream));      // dropped points: zero gradient
   const int ppt = tune_ppt(1), tile = DPC_SPLAT_THREADS * ppt;
   dim3 grid((N + tile - 1) / tile, B);
-#ifndef DPC_EMU
   // Default whenever the forward's tr_pc is at hand (the fused path passes it): the software-pipelined form,
   // dpc_splat_bwd_warp_kernel -- independent warps, every warp resident at once, k tiles of 32 points per warp with k the
   // smallest count for which the grid fits 28 warps per SM (13.6-14.0 us against 20.0 us of the tile-per-CTA kernel at
@@ -342,17 +347,18 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
       ((((uintptr_t)d_vox) & 15u) == 0)) {
     const int tiles = (N + 31) / 32;
     const int per_sm = g_tune[19] > 0 ? g_tune[19] : 28;
-    const long long cap = (long long)dpc_tc_sm_count() * per_sm;
+    const long long cap = (long long)splat_sm_count() * per_sm;
     const int k = (int)(((long long)B * tiles + cap - 1) / cap);
     const int wps = (tiles + k - 1) / k;
     void (*kw)(DpcSplatBwdArgs) = per_sm > 24 ? dpc_splat_bwd_warp_kernel<7> : dpc_splat_bwd_warp_kernel<6>;
+#ifndef DPC_EMU
     // 28 x 7 KB of static shared memory per SM need the large carve-out (per device, so set on every call like the
     // dynamic-shared-memory limits of the other launchers; a host-side attribute, legal during stream capture)
     if (cudaFuncSetAttribute(kw, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return DPC_ERR_CUDA;
+#endif
     DPC_LAUNCH(kw, dim3((wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC, B), dim3(32 * DPC_SPLAT_WPC), 0, stream, a);
     return dpc_check_launch();
   }
-#endif
 #if !defined(DPC_EMU) && defined(DPC_EXPERIMENTS)
   if (ppt == 1 && g_tune[20] != 6 && (g_tune[18] || g_tune[19] || g_tune[20])) {
     // occupancy / decorrelation experiments (knobs 18: 128-thread CTAs, 19: compiled for 75 % occupancy, 20: independent gathers)

@@ -612,6 +612,14 @@ DPC_DEV void dpc_cp_async4(void* smem, const void* g, bool pred) {
 DPC_DEV void dpc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_PENDING>
 DPC_DEV void dpc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+#else
+// CPU emulation (tests/emu): the copies complete at once; the zero-fill of the src-size operand is kept
+DPC_DEV void dpc_cp_async16(void* smem, const void* g, bool pred) { if (pred) memcpy(smem, g, 16); else memset(smem, 0, 16); }
+DPC_DEV void dpc_cp_async4(void* smem, const void* g, bool pred) { if (pred) memcpy(smem, g, 4); else memset(smem, 0, 4); }
+DPC_DEV void dpc_cp_async_commit() {}
+template <int N_PENDING>
+DPC_DEV void dpc_cp_async_wait() {}
+#endif
 
 struct DpcSplatBwdWarpSmem {   // per warp
   float4 gq[2][4][32];   // per buffer, per (z, y) row of the cell: the 4-voxel group that holds ix, one per lane
@@ -628,7 +636,12 @@ struct DpcGatherPlan {
 };
 
 template <int MINB>
-__global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB)
+#else
+static void
+#endif
+dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
   __shared__ __align__(16) DpcSplatBwdWarpSmem sm_all[DPC_SPLAT_WPC];
   __shared__ DpcPose pose_sm;
   DpcSplatBwdWarpSmem& sm = sm_all[threadIdx.x >> 5];
@@ -806,7 +819,6 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_bwd_warp_k
     }
   }
 }
-#endif
 
 // ------------------------------------------------------------------------------ forward, software-pipelined form
 // The forward splat in the shape of dpc_splat_bwd_warp_kernel: independent warps, k tiles of 32 points per warp, every
@@ -818,9 +830,13 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_bwd_warp_k
 // after issuing its first loads, transforms its first tile while they drain, then a grid-wide barrier separates the zeros
 // from the first reduction) -- the fused forward then needs no memset node in front of it.
 // Preconditions (launcher): no rgb, no dropout list, no counters to zero.
-#ifndef DPC_EMU
 template <int MINB, bool ZERO>
-__global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
+#ifndef DPC_EMU
+__global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB)
+#else
+static void
+#endif
+dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
   __shared__ __align__(16) float pts_all[DPC_SPLAT_WPC][2][96];
   __shared__ DpcPose pose_sm;
   float (*pts)[96] = pts_all[threadIdx.x >> 5];
@@ -888,11 +904,13 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_k
     }
   };
   if (t < tiles) front(t, 0);
+#ifndef DPC_EMU
   if (ZERO) {
     __threadfence();                         // my zeros are visible device-wide ...
     cooperative_groups::this_grid().sync();  // ... and so are everybody else's: the grid is zero from here on
     dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1);
   }
+#endif
   if (t >= tiles) return;
   if (!waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
   int buf = 0;
@@ -971,7 +989,6 @@ __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB) dpc_splat_fwd_warp_k
   dpc_cp_async_wait<0>();
   dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 3);
 }
-#endif
 
 // ------------------------------------------------------------------------------ grid zeroing (lab build: knob 10)
 #ifdef DPC_EXPERIMENTS

@@ -40,6 +40,25 @@ def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
         emu.dpc_debug_set(1, 1)
 
 
+@pytest.mark.parametrize("knobs", [{19: 1}, {19: 2}, {0: 8, 20: 6}])
+def test_pipelined_splat_kernels(emu, knobs):  # noqa: F811
+    """The software-pipelined splat kernels (product default; the tests above run them with one tile per warp): knob 19 = 1 / 2
+    sizes their grids for 1 / 2 warps per SM of the emulator's 4 SMs, so every warp walks 4 - 16 tiles of its sample, the
+    last one ragged; {0: 8, 20: 6} = the tile-per-CTA kernels they replaced (still the path for rgb / dropout / no tr_pc)."""
+    for k, v in knobs.items():
+        emu.dpc_debug_set(k, v)
+    try:
+        for name in ("cfg1_drc_k11", "clustered_init", "trans_focal", "edge_points", "matrix_pose", "extra_upstream", "single_point"):
+            if name not in SMALL:
+                continue
+            fx = cases.load_golden(name)
+            outs, grads = cases.run_impl(Product, fx)
+            cases.assert_parity(fx, outs, grads)
+    finally:
+        for k in knobs:
+            emu.dpc_debug_set(k, {0: 4, 19: 0, 20: 0}[k])
+
+
 KNOB_DEFAULTS = {10: 0, 11: 1, 13: 0, 14: 1, 15: 1}
 
 
