@@ -6,6 +6,11 @@
 // into shared memory by the TMA engine (cp.async.bulk, mbarrier completion), transformed in
 // registers with the reference's exact fp32 op order, written back coalesced as tr_pc, and its
 // 8 corner weights are added to the single grid with warp-aggregated REDG (v2 where aligned).
+//
+// Two generations of kernels live here.  dpc_splat_fwd_kernel / dpc_splat_bwd_kernel: one tile of points per CTA
+// (TMA-staged); they serve the rgb grid, the dropout index list and a backward without the forward's tr_pc.
+// dpc_splat_fwd_warp_kernel / dpc_splat_bwd_warp_kernel (further down, the default): every warp an independent worker
+// over several 32-point tiles, next tile prefetched with cp.async -- twice as fast in the backward.
 #pragma once
 #include "dpc_math.cuh"
 #ifndef DPC_EMU
@@ -451,7 +456,8 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
     } else if (quad && o4 != 3) {        // ix + 1 < V is implied
       // (the four loads below end up as four DEPENDENT round trips -- nvcc wraps each in its own divergence region and
       // reuses one destination quad; the independent form, dpc_gather_corners, was measured SLOWER in this kernel at full
-      // occupancy: 23.8 vs 20.2 us, profiles/r02_b_timeline_sep.txt -- the L1 miss path, not the latency chain, bounds it)
+      // occupancy: 23.8 vs 20.2 us, profiles/r02_b_timeline_sep.txt.  Neither the chain nor the L1 miss path bounds this
+      // kernel -- its lock-step shape does, see dpc_splat_bwd_warp_kernel and profiles/r02_w_splat_bwd_warp.md)
 #pragma unroll
       for (int k = 0; k < 2; ++k)
 #pragma unroll
