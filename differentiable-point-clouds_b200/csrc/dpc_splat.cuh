@@ -639,6 +639,7 @@ struct DpcSplatBwdWarpSmem {   // per warp
 struct DpcGatherPlan {
   const float* g0;       // the 4-voxel group of (iz, iy, ix)
   unsigned ok;           // bit r: row r = (k, jj) is inside the grid and the point is valid; bit 4: the x pair straddles
+  int base;              // linear index of the cell, -1 for a lane without a valid point: what the plan was made for
 };
 
 template <int MINB>
@@ -671,10 +672,10 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
       dpc_cp_async4(&sm.pts[buf][i], i < n3 ? src + i : pc_b, i < n3);
     }
   };
-  auto plan = [&](float z, float y, float x) {
-    const DpcCell c = dpc_cell(z, y, x, Vz, V);
+  auto plan = [&](const DpcCell& c) {      // c.valid already says whether the lane has a point at all
     const int o4 = c.ix & 3;
     DpcGatherPlan g;
+    g.base = c.valid ? (c.iz * V + c.iy) * V + c.ix : -1;
     g.g0 = dv + (c.iz * V + c.iy) * V + (c.ix - o4);
     g.ok = 0u;
 #pragma unroll
@@ -704,13 +705,13 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
   if (threadIdx.x == 0) dpc_pose_load(pose_sm, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   __syncthreads();               // the only CTA-wide step: the camera of the sample
   if (t >= tiles) return;
+  DpcGatherPlan gc = plan(dpc_cell(rz, ry, rx, Vz, V));    // the plan the CURRENT tile's corners were requested with
   {
-    const DpcGatherPlan g = plan(rz, ry, rx);
     if (t + wps < tiles) load_raw(t + wps);
     dpc_grid_dep_wait();
     dpc_kt_mark_if(kt, DPC_KT_SPLAT_B, 1);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) issue_row(g, r, 0);
+    for (int r = 0; r < 4; ++r) issue_row(gc, r, 0);
   }
   dpc_cp_async_commit();
   if (a.d_scale_part && blockIdx.x == 0 && threadIdx.x < 32) {
@@ -731,10 +732,10 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
     dpc_cp_async_wait<0>();                        // this tile's points and corners (issued during the previous tile)
     __syncwarp();                                  // ... of every lane
     DpcGatherPlan gn;
-    gn.g0 = dv; gn.ok = 0u;
+    gn.g0 = dv; gn.ok = 0u; gn.base = -1;
     if (more) {
       issue_points(tn, buf ^ 1);
-      gn = plan(rz, ry, rx);
+      gn = plan(dpc_cell(rz, ry, rx, Vz, V));
       issue_row(gn, 0, buf ^ 1);
       if (tn + wps < tiles) load_raw(tn + wps);
     }
@@ -753,14 +754,24 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
     DpcCell c = dpc_cell(z, y, x, Vz, V);      // the forward's cell again: same code, same inputs as the prefetch's tr_pc
     c.valid = c.valid && live;
     float gz = 0.f, gy = 0.f, gx = 0.f;
+    // The prefetch was aimed by tr_pc, the result must not depend on it: a lane whose recomputed cell is not the one its
+    // corners were requested for (tr_pc is not the tr_pc of this call's forward) fetches its rows now, the slow way.
+    const bool stale = gc.base != (c.valid ? (c.iz * V + c.iy) * V + c.ix : -1);
     if (c.valid) {
       const int o4 = c.ix & 3;
       const float wz[2] = {1.0f - c.rz, c.rz}, wy[2] = {1.0f - c.ry, c.ry}, wx[2] = {1.0f - c.rx, c.rx};
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int k = r >> 1, jj = r & 1;
-        const float4 q4 = sm.gq[buf][r][lane];
-        const float e = sm.ge[buf][r][lane];
+        float4 q4 = sm.gq[buf][r][lane];
+        float e = sm.ge[buf][r][lane];
+        if (stale) {
+          const DpcGatherPlan pv = plan(c);
+          const bool ok = (pv.ok >> r) & 1u;
+          const float* rp = pv.g0 + (k * V + jj) * V;
+          q4 = ok ? __ldg(reinterpret_cast<const float4*>(rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          e = (ok && (pv.ok & 16u)) ? __ldg(rp + 4) : 0.0f;
+        }
         const float w0 = o4 == 0 ? q4.x : (o4 == 1 ? q4.y : (o4 == 2 ? q4.z : q4.w));
         const float w1 = o4 == 0 ? q4.y : (o4 == 1 ? q4.z : (o4 == 2 ? q4.w : e));
         if (c.iz + k < Vz && c.iy + jj < V) {
@@ -796,6 +807,7 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
       }
     }
     __syncwarp();   // the buffer is free for the prefetch of the tile after next
+    gc = gn;
   }
   dpc_cp_async_wait<0>();
   dpc_kt_mark_if(kt, DPC_KT_SPLAT_B, 3);

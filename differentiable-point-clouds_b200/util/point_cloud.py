@@ -422,7 +422,7 @@ class _ProjectFastFn(torch.autograd.Function):
         L = _capi.lib()
         pc, pose, trans, focal, scale, taps_xy, taps_z, voxels, saved, tr_pc, sel = ctx.saved_tensors
         params = ctx.params
-        params.tr_pc = ptr(tr_pc)      # the cells the forward used: the backward's gathers run inside its x/y pass
+        params.tr_pc = ptr(tr_pc)      # the cells the forward used: the splat backward prefetches its gathers from them
         b = params.B
 
         def opt(g):

@@ -207,7 +207,9 @@ typedef struct {
                                   known without redoing the camera transform, so the gathers of the next 32 points are
                                   prefetched while the current ones are computed (10 us instead of 20 us at B=32,
                                   N=8000).  NULL = the tile-per-CTA kernel, which recomputes the transform first.  The
-                                  results are the same either way (the transform is recomputed for the chain rule in both) */
+                                  results are the same either way, and they do not depend on the CONTENT of tr_pc: the
+                                  transform is recomputed for the chain rule anyway, and a point whose recomputed cell is
+                                  not the one its gathers were aimed at (a stale tr_pc) fetches its corners again */
   const int32_t* sel;          /* optional (device, [B,N] int32): point dropout consumed by the splat's load stage
                                   (point_cloud.py:293-319).  pc and d_pc are then [B,N_src,3]; point i of sample b is
                                   pc[b, sel[b*N + i]] (indices of a sample distinct), tr_pc stays [B,N,3]; dropped points

@@ -59,6 +59,44 @@ def test_pipelined_splat_kernels(emu, knobs):  # noqa: F811
             emu.dpc_debug_set(k, {0: 4, 19: 0, 20: 0}[k])
 
 
+def _grads_before_and_after_corrupting_tr_pc(fx):
+    """ONE forward (its atomics are unordered, two forwards would not be bit-comparable), two backwards: the second
+    sees a tr_pc that is not the forward's."""
+    cfg = cases.make_cfg(fx["cfg_over"])
+    pc = torch.from_numpy(fx["in_point_cloud"]).clone().requires_grad_(True)
+    q = torch.from_numpy(fx["in_transform"]).clone().requires_grad_(True)
+    sc = torch.from_numpy(fx["in_scaling_factor"]).clone().requires_grad_(True)
+    kernel = gk.smoothing_kernel(cfg, float(fx["in_sigma"]))
+    out = pcm.pointcloud_project_fast(cfg, pc, q, None, None, kernel, sc)
+    up = torch.randn(out["proj"].shape, generator=torch.Generator().manual_seed(3))
+    good = [x.clone() for x in torch.autograd.grad(out["proj"], (pc, q, sc), grad_outputs=up, retain_graph=True)]
+    t = out["tr_pc"].data                # .data: no version bump, autograd hands the corrupted tensor to the backward
+    t.copy_(torch.roll(t, 7, dims=1))
+    t[:, ::5] = float("nan")
+    t[:, 1::5] *= -1.0
+    bad = [x.clone() for x in torch.autograd.grad(out["proj"], (pc, q, sc), grad_outputs=up)]
+    return good, bad
+
+
+@pytest.mark.parametrize("name,per_sm", [("cfg1_drc_k11", 1), ("clustered_init", 0), ("v64_small", 1)])
+def test_backward_does_not_depend_on_the_tr_pc_hint(emu, name, per_sm):  # noqa: F811
+    """dpc_project_params.tr_pc only AIMS the prefetch of the pipelined splat backward: a lane whose recomputed cell is
+    not the one its corners were requested for fetches them again.  A wrong tr_pc (another forward's; here rolled by 7
+    points, every fifth NaN, every fifth negated) therefore gives the same gradients: d_pc bit for bit, the per-sample
+    sums (pose: one atomic per warp, unordered) to rounding."""
+    if name not in SMALL:
+        pytest.skip("fixture not present")
+    fx = cases.load_golden(name)
+    emu.dpc_debug_set(19, per_sm)
+    try:
+        good, bad = _grads_before_and_after_corrupting_tr_pc(fx)
+    finally:
+        emu.dpc_debug_set(19, 0)
+    assert torch.equal(good[0], bad[0]), "d_pc changed with the tr_pc hint"
+    for g, b in zip(good[1:], bad[1:]):
+        assert float((g - b).abs().max()) <= 1e-6 * max(1.0, float(g.abs().max()))
+
+
 KNOB_DEFAULTS = {10: 0, 11: 1, 13: 0, 14: 1, 15: 1}
 
 

@@ -193,6 +193,27 @@ def test_pipelined_splat_ragged_multi_tile(n, b, v):
         _capi._LIB = product
 
 
+def test_backward_does_not_depend_on_the_tr_pc_hint():
+    """dpc_project_params.tr_pc only aims the prefetch of the pipelined splat backward (a lane whose recomputed cell is not
+    the one its corners were requested for fetches them again): ONE forward at the headline shape, a backward, then tr_pc
+    corrupted in place (rolled by 7 points, every fifth NaN, every fifth negated) and the backward again -- same d_pc bit
+    for bit, per-sample sums (one atomic per warp, unordered) to rounding."""
+    cfg = default_config(vox_size=64, pc_gauss_kernel_size=21)
+    pc, q, sc, gt = _bench_inputs(8, 8000, 64, 0.5, seed=4321)
+    leaves = [t.clone().to(DEV).requires_grad_(True) for t in (pc, q, sc)]
+    out = pcm.pointcloud_project_fast(cfg, leaves[0], leaves[1], None, None, gk.smoothing_kernel(cfg, 3.0), leaves[2])
+    up = (out["proj"].detach() - gt.to(DEV)) / 8
+    good = [x.clone() for x in torch.autograd.grad(out["proj"], leaves, grad_outputs=up, retain_graph=True)]
+    t = out["tr_pc"].data
+    t.copy_(torch.roll(t, 7, dims=1))
+    t[:, ::5] = float("nan")
+    t[:, 1::5] *= -1.0
+    bad = [x.clone() for x in torch.autograd.grad(out["proj"], leaves, grad_outputs=up)]
+    assert torch.equal(good[0], bad[0]), "d_pc changed with the tr_pc hint"
+    for g, b in zip(good[1:], bad[1:]):
+        assert float((g - b).abs().max()) <= 1e-6 * max(1.0, float(g.abs().max()))
+
+
 def test_max_projection_full_shape():
     cfg = default_config(vox_size=64, pc_gauss_kernel_size=21, ptn_max_projection=True)
     pc, q, sc, gt = _bench_inputs(2, 8000, 64, 0.5)
