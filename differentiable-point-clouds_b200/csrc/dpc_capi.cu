@@ -251,7 +251,7 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
   a.zero_u32 = zero_u32; a.n_zero = n_zero;
   // software-pipelined form (dpc_splat_fwd_warp_kernel), same grid sizing as the backward's; lab build: knob 0 = 1 / 2 /
   // 8 selects the tile-per-CTA kernel with 1 / 2 / 4 points per thread, knob 19 = warps per SM the grid is sized for
-  if (g_tune[0] == 4 && !rgb && !sel && !zero_u32) {
+  if (g_tune[0] == 4 && !rgb && !zero_u32) {
     const int tiles = (N + 31) / 32;
     const int per_sm = g_tune[19] > 0 ? g_tune[19] : 28;
     const long long cap = (long long)splat_sm_count() * per_sm;
@@ -343,7 +343,7 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
   // smallest count for which the grid fits 28 warps per SM (13.6-14.0 us against 20.0 us of the tile-per-CTA kernel at
   // B=32, N=8000; 24 warps per SM, i.e. k = 3: 15.1 us; profiles/r02_w_splat_bwd_warp.md).  Lab build: knob 20 = 6
   // forces the tile-per-CTA kernel, knob 19 = warps per SM the grid is sized for.
-  if ((g_tune[20] == 0 || g_tune[20] == 4) && tr_pc && d_vox && !rgb && !d_vox_rgb && !d_rgb && !sel && (V & 3) == 0 &&
+  if ((g_tune[20] == 0 || g_tune[20] == 4) && tr_pc && d_vox && !rgb && !d_vox_rgb && !d_rgb && (V & 3) == 0 &&
       ((((uintptr_t)d_vox) & 15u) == 0)) {
     const int tiles = (N + 31) / 32;
     const int per_sm = g_tune[19] > 0 ? g_tune[19] : 28;

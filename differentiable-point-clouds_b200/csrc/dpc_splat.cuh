@@ -604,8 +604,8 @@ dpc_splat_bwd_kernel(DpcSplatBwdArgs a) {
 // tile are issued in four portions spread over the current tile's arithmetic (a burst of 11 scattered LDGSTS backs up
 // the SM's load/store queue and the warp then stalls on the address registers it wants to reuse: ncu, r02_w).  The
 // pose gradients are accumulated in registers over all tiles of the warp (same sample) and reduced once.
-// Preconditions (the launcher falls back to dpc_splat_bwd_kernel otherwise): tr_pc given, no rgb, no dropout list,
-// V % 4 == 0 and a 16-byte aligned gradient grid.
+// Preconditions (the launcher falls back to dpc_splat_bwd_kernel otherwise): tr_pc given, no rgb, V % 4 == 0 and a
+// 16-byte aligned gradient grid.
 #ifndef DPC_EMU
 DPC_DEV void dpc_cp_async16(void* smem, const void* g, bool pred) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -658,12 +658,26 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
   const int tiles = (N + 31) >> 5;
   const int wps = gridDim.x * DPC_SPLAT_WPC;
   const float* dv = a.d_vox + (size_t)b * Vz * V * V;
-  const float* pc_b = a.pc + (size_t)b * N * 3;
+  // f-2 (dropout list): pc / d_pc are [B,N_src,3] and point i of the sample is row sel[b*N + i]; tr_pc stays [B,N,3]
+  const int32_t* sel_b = a.sel ? a.sel + (size_t)b * N : nullptr;
+  const float* pc_b = a.pc + (size_t)b * (sel_b ? a.N_src : N) * 3;
   const float* tr_b = a.tr_pc + (size_t)b * N * 3;
   int t = blockIdx.x * DPC_SPLAT_WPC + (threadIdx.x >> 5);
   const bool kt = dpc_kt_enabled();      // read once: a load of the flag behind the grid dependency would sit on the critical path
 
+  int row_next = 0, row_cur = 0;         // dropout list: this lane's source row in the tile being fetched / computed
+  auto load_row = [&](int tt) {
+    const int i = tt * 32 + lane;
+    row_next = (sel_b && i < N) ? __ldg(sel_b + i) : 0;
+  };
   auto issue_points = [&](int tt, int buf) {
+    if (sel_b) {                         // the lane's own point: three 4-byte copies from its row (row_next = sel of tile tt)
+      const bool live = tt * 32 + lane < N;
+      const float* src = pc_b + (size_t)row_next * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dpc_cp_async4(&sm.pts[buf][lane * 3 + c], live ? src + c : pc_b, live);
+      return;
+    }
     const int n3 = min(32, N - tt * 32) * 3;
     const float* src = pc_b + (size_t)tt * 96;
 #pragma unroll
@@ -701,7 +715,13 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
   // prologue: tr_pc, the points and the camera are forward data (nothing in front of this kernel writes them)
   dpc_kt_mark_if(kt, DPC_KT_SPLAT_B, 0);
   dpc_grid_dep_trigger();
-  if (t < tiles) { load_raw(t); issue_points(t, 0); }
+  if (t < tiles) {
+    load_raw(t);
+    load_row(t);
+    issue_points(t, 0);
+    row_cur = row_next;
+    if (t + wps < tiles) load_row(t + wps);
+  }
   if (threadIdx.x == 0) dpc_pose_load(pose_sm, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   __syncthreads();               // the only CTA-wide step: the camera of the sample
   if (t >= tiles) return;
@@ -733,11 +753,13 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
     __syncwarp();                                  // ... of every lane
     DpcGatherPlan gn;
     gn.g0 = dv; gn.ok = 0u; gn.base = -1;
+    const int row_here = row_cur;                  // dropout list: where this tile's d_pc rows go
     if (more) {
-      issue_points(tn, buf ^ 1);
+      issue_points(tn, buf ^ 1);                   // (uses row_next = the list entries of tile tn)
+      row_cur = row_next;
       gn = plan(dpc_cell(rz, ry, rx, Vz, V));
       issue_row(gn, 0, buf ^ 1);
-      if (tn + wps < tiles) load_raw(tn + wps);
+      if (tn + wps < tiles) { load_raw(tn + wps); load_row(tn + wps); }
     }
 
     const int i = t * 32 + lane;
@@ -796,7 +818,12 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
       if (a.d_tr_pc_in) { gz += a.d_tr_pc_in[pi * 3 + 0]; gy += a.d_tr_pc_in[pi * 3 + 1]; gx += a.d_tr_pc_in[pi * 3 + 2]; }
       dpc_transform_point_bwd(pose_sm, p0, p1, p2, cam, gz, gy, gx, d0, d1, d2, acc, want_tf);
     }
-    if (a.d_pc) {
+    if (a.d_pc && sel_b) {                         // rows of a sample's list are distinct: plain stores (the launcher zeroed d_pc)
+      if (live) {
+        float* dst = a.d_pc + ((size_t)b * a.N_src + (size_t)row_here) * 3;
+        dst[0] = d0; dst[1] = d1; dst[2] = d2;
+      }
+    } else if (a.d_pc) {
       if (live) { sm.pts[buf][lane * 3 + 0] = d0; sm.pts[buf][lane * 3 + 1] = d1; sm.pts[buf][lane * 3 + 2] = d2; }
       __syncwarp();
       float* dst = a.d_pc + ((size_t)b * N + (size_t)t * 32) * 3;
@@ -847,7 +874,7 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
 // ZERO: the kernel also zeroes the grid it reduces into (cooperative launch: every CTA stores its share of zeros right
 // after issuing its first loads, transforms its first tile while they drain, then a grid-wide barrier separates the zeros
 // from the first reduction) -- the fused forward then needs no memset node in front of it.
-// Preconditions (launcher): no rgb, no dropout list, no counters to zero.
+// Preconditions (launcher): no rgb, no counters to zero.
 template <int MINB, bool ZERO>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB)
@@ -863,10 +890,25 @@ dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
   const int V = a.V, Vz = a.Vz, N = a.N;
   const int tiles = (N + 31) >> 5;
   const int wps = gridDim.x * DPC_SPLAT_WPC;
-  const float* pc_b = a.pc + (size_t)b * N * 3;
+  // f-2 (dropout list): pc is [B,N_src,3] and point i of the sample is row sel[b*N + i]; the list is written by the
+  // kernel in front of this one (dpc_dropout_indices), so with a list everything waits for the grid dependency first
+  const int32_t* sel_b = a.sel ? a.sel + (size_t)b * N : nullptr;
+  const float* pc_b = a.pc + (size_t)b * (sel_b ? a.N_src : N) * 3;
   int t = blockIdx.x * DPC_SPLAT_WPC + (threadIdx.x >> 5);
   const bool kt = dpc_kt_enabled();
+  int row_next = 0;
+  auto load_row = [&](int tt) {
+    const int i = tt * 32 + lane;
+    row_next = (sel_b && i < N) ? __ldg(sel_b + i) : 0;
+  };
   auto issue_points = [&](int tt, int buf) {
+    if (sel_b) {                         // the lane's own point: three 4-byte copies from its row (row_next = sel of tile tt)
+      const bool lv = tt * 32 + lane < N;
+      const float* src = pc_b + (size_t)row_next * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dpc_cp_async4(&pts[buf][lane * 3 + c], lv ? src + c : pc_b, lv);
+      return;
+    }
     const int n3 = min(32, N - tt * 32) * 3;
     const float* src = pc_b + (size_t)tt * 96;
 #pragma unroll
@@ -877,8 +919,14 @@ dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
   };
   dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 0);
   dpc_grid_dep_trigger();
+  bool waited = ZERO;
+  if (sel_b && !waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
   // the points and the camera are inputs: nothing in front of this kernel writes them (see dpc_splat_fwd_kernel)
-  if (t < tiles) issue_points(t, 0);
+  if (t < tiles) {
+    load_row(t);
+    issue_points(t, 0);
+    if (t + wps < tiles) load_row(t + wps);
+  }
   dpc_cp_async_commit();
   if (threadIdx.x == 0) dpc_pose_load(pose_sm, a.pose, a.pose_kind, a.trans, a.focal, a.focal_const, a.cam_dist, b);
   if (ZERO) {
@@ -890,8 +938,7 @@ dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
     for (size_t i = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += nth) z4[i] = zz;
   }
   __syncthreads();               // the camera of the sample
-  bool waited = ZERO;
-  if (!ZERO && !a.early) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
+  if (!waited && !a.early) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
   float* grid = a.vox ? a.vox + (size_t)b * Vz * V * V : nullptr;
   const bool quad_al = a.red4 && ((V & 3) == 0) && ((((uintptr_t)a.vox) & 15u) == 0);
   const bool pair_al = ((V & 1) == 0) && ((((uintptr_t)a.vox) & 7u) == 0);
@@ -901,7 +948,10 @@ dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
   auto front = [&](int tt, int buf) {
     dpc_cp_async_wait<0>();
     __syncwarp();
-    if (tt + wps < tiles) issue_points(tt + wps, buf ^ 1);
+    if (tt + wps < tiles) {
+      issue_points(tt + wps, buf ^ 1);             // (uses row_next = the list entries of that tile)
+      if (tt + 2 * wps < tiles) load_row(tt + 2 * wps);
+    }
     dpc_cp_async_commit();
     const int n = min(32, N - tt * 32);
     live = lane < n;

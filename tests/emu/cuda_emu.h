@@ -112,6 +112,7 @@ static inline float atomicAdd(float* addr, float v) {
 }
 static inline float __ldg(const float* p) { return *p; }
 static inline float4 __ldg(const float4* p) { return *p; }
+static inline int __ldg(const int* p) { return *p; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -84,6 +84,19 @@ def test_fused_dropout_matches_oracle_emulated(emu):  # noqa: F811
     _fused_matches_oracle("cpu", b=2, n=600, k=42, v=16, ksize=5)
 
 
+@pytest.mark.parametrize("knobs", [{19: 1}, {0: 8, 20: 6}])
+def test_fused_dropout_kernel_variants_emulated(emu, knobs):  # noqa: F811
+    """The index list in the software-pipelined splat kernels with several (ragged) tiles per warp (knob 19 = 1: grids sized
+    for one warp per SM of the emulator's four), and in the tile-per-CTA kernels (knobs 0 = 8, 20 = 6)."""
+    for k, v in knobs.items():
+        emu.dpc_debug_set(k, v)
+    try:
+        _fused_matches_oracle("cpu", b=2, n=600, k=333, v=16, ksize=5)
+    finally:
+        for k in knobs:
+            emu.dpc_debug_set(k, {0: 4, 19: 0, 20: 0}[k])
+
+
 @pytest.mark.gpu
 def test_dropout_indices_gpu():
     _index_properties("cuda:0")
