@@ -265,9 +265,9 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
       // take 10 us inside the kernel, the memset 5 us: step 98.5 vs 96.4 us; profiles/r02_w_timeline_coop_zero.txt)
       *zeroes_grid = false;
 #if defined(DPC_EXPERIMENTS) && !defined(DPC_EMU)
-      void (*kz)(DpcSplatArgs) = dpc_splat_fwd_warp_kernel<7, true>;
+      void (*kz)(DpcSplatArgs) = dpc_splat_fwd_warp_kernel<7, true, false>;
       int per = 0;
-      if (g_tune[10] == 3 && vox && (V & 3) == 0 && ((((uintptr_t)vox) & 15u) == 0) &&
+      if (g_tune[10] == 3 && !sel && vox && (V & 3) == 0 && ((((uintptr_t)vox) & 15u) == 0) &&
           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kz, 32 * DPC_SPLAT_WPC, 0) == cudaSuccess && per > 0) {
         const long long fit = (long long)per * dpc_tc_sm_count();
         while ((long long)g.x * B > fit && wps > 1) { ++k; wps = (tiles + k - 1) / k; g.x = (wps + DPC_SPLAT_WPC - 1) / DPC_SPLAT_WPC; }
@@ -286,8 +286,9 @@ static int splat_fwd_launch(const float* pc, const float* pose, int pose_kind, c
 #endif
       return DPC_OK;
     }
-    if (per_sm > 24) { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<7, false>), g, blk, 0, stream, a); }
-    else { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<6, false>), g, blk, 0, stream, a); }
+    if (sel) { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<7, false, true>), g, blk, 0, stream, a); }
+    else if (per_sm > 24) { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<7, false, false>), g, blk, 0, stream, a); }
+    else { DPC_LAUNCH((dpc_splat_fwd_warp_kernel<6, false, false>), g, blk, 0, stream, a); }
     return dpc_check_launch();
   }
   if (zeroes_grid) { *zeroes_grid = false; return DPC_OK; }
@@ -350,7 +351,8 @@ static int splat_bwd_launch(const float* pc, const float* pose, int pose_kind, c
     const long long cap = (long long)splat_sm_count() * per_sm;
     const int k = (int)(((long long)B * tiles + cap - 1) / cap);
     const int wps = (tiles + k - 1) / k;
-    void (*kw)(DpcSplatBwdArgs) = per_sm > 24 ? dpc_splat_bwd_warp_kernel<7> : dpc_splat_bwd_warp_kernel<6>;
+    void (*kw)(DpcSplatBwdArgs) = sel ? dpc_splat_bwd_warp_kernel<7, true>
+                                  : (per_sm > 24 ? dpc_splat_bwd_warp_kernel<7, false> : dpc_splat_bwd_warp_kernel<6, false>);
 #ifndef DPC_EMU
     // 28 x 7 KB of static shared memory per SM need the large carve-out (per device, so set on every call like the
     // dynamic-shared-memory limits of the other launchers; a host-side attribute, legal during stream capture)

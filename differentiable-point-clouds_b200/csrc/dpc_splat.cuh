@@ -642,7 +642,9 @@ struct DpcGatherPlan {
   int base;              // linear index of the cell, -1 for a lane without a valid point: what the plan was made for
 };
 
-template <int MINB>
+// SEL: the dropout index list (f-2) is compiled in only where it is used -- the instantiation without it is instruction
+// for instruction the kernel that was tuned above (the list's bookkeeping cost 1.2 us when it was a run-time branch).
+template <int MINB, bool SEL>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB)
 #else
@@ -659,19 +661,20 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
   const int wps = gridDim.x * DPC_SPLAT_WPC;
   const float* dv = a.d_vox + (size_t)b * Vz * V * V;
   // f-2 (dropout list): pc / d_pc are [B,N_src,3] and point i of the sample is row sel[b*N + i]; tr_pc stays [B,N,3]
-  const int32_t* sel_b = a.sel ? a.sel + (size_t)b * N : nullptr;
-  const float* pc_b = a.pc + (size_t)b * (sel_b ? a.N_src : N) * 3;
+  const int32_t* sel_b = SEL ? a.sel + (size_t)b * N : nullptr;
+  const float* pc_b = a.pc + (size_t)b * (SEL ? a.N_src : N) * 3;
   const float* tr_b = a.tr_pc + (size_t)b * N * 3;
   int t = blockIdx.x * DPC_SPLAT_WPC + (threadIdx.x >> 5);
   const bool kt = dpc_kt_enabled();      // read once: a load of the flag behind the grid dependency would sit on the critical path
 
   int row_next = 0, row_cur = 0;         // dropout list: this lane's source row in the tile being fetched / computed
   auto load_row = [&](int tt) {
+    if (!SEL) return;
     const int i = tt * 32 + lane;
-    row_next = (sel_b && i < N) ? __ldg(sel_b + i) : 0;
+    row_next = (i < N) ? __ldg(sel_b + i) : 0;
   };
   auto issue_points = [&](int tt, int buf) {
-    if (sel_b) {                         // the lane's own point: three 4-byte copies from its row (row_next = sel of tile tt)
+    if (SEL) {                           // the lane's own point: three 4-byte copies from its row (row_next = sel of tile tt)
       const bool live = tt * 32 + lane < N;
       const float* src = pc_b + (size_t)row_next * 3;
 #pragma unroll
@@ -756,7 +759,7 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
     const int row_here = row_cur;                  // dropout list: where this tile's d_pc rows go
     if (more) {
       issue_points(tn, buf ^ 1);                   // (uses row_next = the list entries of tile tn)
-      row_cur = row_next;
+      if (SEL) row_cur = row_next;
       gn = plan(dpc_cell(rz, ry, rx, Vz, V));
       issue_row(gn, 0, buf ^ 1);
       if (tn + wps < tiles) { load_raw(tn + wps); load_row(tn + wps); }
@@ -818,7 +821,7 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
       if (a.d_tr_pc_in) { gz += a.d_tr_pc_in[pi * 3 + 0]; gy += a.d_tr_pc_in[pi * 3 + 1]; gx += a.d_tr_pc_in[pi * 3 + 2]; }
       dpc_transform_point_bwd(pose_sm, p0, p1, p2, cam, gz, gy, gx, d0, d1, d2, acc, want_tf);
     }
-    if (a.d_pc && sel_b) {                         // rows of a sample's list are distinct: plain stores (the launcher zeroed d_pc)
+    if (SEL && a.d_pc) {                           // rows of a sample's list are distinct: plain stores (the launcher zeroed d_pc)
       if (live) {
         float* dst = a.d_pc + ((size_t)b * a.N_src + (size_t)row_here) * 3;
         dst[0] = d0; dst[1] = d1; dst[2] = d2;
@@ -875,7 +878,7 @@ dpc_splat_bwd_warp_kernel(DpcSplatBwdArgs a) {
 // after issuing its first loads, transforms its first tile while they drain, then a grid-wide barrier separates the zeros
 // from the first reduction) -- the fused forward then needs no memset node in front of it.
 // Preconditions (launcher): no rgb, no counters to zero.
-template <int MINB, bool ZERO>
+template <int MINB, bool ZERO, bool SEL>
 #ifndef DPC_EMU
 __global__ void __launch_bounds__(32 * DPC_SPLAT_WPC, MINB)
 #else
@@ -892,17 +895,18 @@ dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
   const int wps = gridDim.x * DPC_SPLAT_WPC;
   // f-2 (dropout list): pc is [B,N_src,3] and point i of the sample is row sel[b*N + i]; the list is written by the
   // kernel in front of this one (dpc_dropout_indices), so with a list everything waits for the grid dependency first
-  const int32_t* sel_b = a.sel ? a.sel + (size_t)b * N : nullptr;
-  const float* pc_b = a.pc + (size_t)b * (sel_b ? a.N_src : N) * 3;
+  const int32_t* sel_b = SEL ? a.sel + (size_t)b * N : nullptr;
+  const float* pc_b = a.pc + (size_t)b * (SEL ? a.N_src : N) * 3;
   int t = blockIdx.x * DPC_SPLAT_WPC + (threadIdx.x >> 5);
   const bool kt = dpc_kt_enabled();
   int row_next = 0;
   auto load_row = [&](int tt) {
+    if (!SEL) return;
     const int i = tt * 32 + lane;
-    row_next = (sel_b && i < N) ? __ldg(sel_b + i) : 0;
+    row_next = (i < N) ? __ldg(sel_b + i) : 0;
   };
   auto issue_points = [&](int tt, int buf) {
-    if (sel_b) {                         // the lane's own point: three 4-byte copies from its row (row_next = sel of tile tt)
+    if (SEL) {                           // the lane's own point: three 4-byte copies from its row (row_next = sel of tile tt)
       const bool lv = tt * 32 + lane < N;
       const float* src = pc_b + (size_t)row_next * 3;
 #pragma unroll
@@ -920,7 +924,7 @@ dpc_splat_fwd_warp_kernel(DpcSplatArgs a) {
   dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 0);
   dpc_grid_dep_trigger();
   bool waited = ZERO;
-  if (sel_b && !waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
+  if (SEL && !waited) { dpc_grid_dep_wait(); dpc_kt_mark_if(kt, DPC_KT_SPLAT_F, 1); waited = true; }
   // the points and the camera are inputs: nothing in front of this kernel writes them (see dpc_splat_fwd_kernel)
   if (t < tiles) {
     load_row(t);
