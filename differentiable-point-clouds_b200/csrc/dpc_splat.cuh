@@ -8,7 +8,7 @@
 // 8 corner weights are added to the single grid with warp-aggregated REDG (v2 where aligned).
 //
 // Two generations of kernels live here.  dpc_splat_fwd_kernel / dpc_splat_bwd_kernel: one tile of points per CTA
-// (TMA-staged); they serve the rgb grid, the dropout index list and a backward without the forward's tr_pc.
+// (TMA-staged); they serve the rgb grid and a backward without the forward's tr_pc.
 // dpc_splat_fwd_warp_kernel / dpc_splat_bwd_warp_kernel (further down, the default): every warp an independent worker
 // over several 32-point tiles, next tile prefetched with cp.async -- twice as fast in the backward.
 #pragma once

@@ -44,7 +44,7 @@ def test_splat_points_per_thread_variants(emu, ppt):  # noqa: F811
 def test_pipelined_splat_kernels(emu, knobs):  # noqa: F811
     """The software-pipelined splat kernels (product default; the tests above run them with one tile per warp): knob 19 = 1 / 2
     sizes their grids for 1 / 2 warps per SM of the emulator's 4 SMs, so every warp walks 4 - 16 tiles of its sample, the
-    last one ragged; {0: 8, 20: 6} = the tile-per-CTA kernels they replaced (still the path for rgb / dropout / no tr_pc)."""
+    last one ragged; {0: 8, 20: 6} = the tile-per-CTA kernels they replaced (still the path for rgb / no tr_pc)."""
     for k, v in knobs.items():
         emu.dpc_debug_set(k, v)
     try:
