@@ -48,7 +48,8 @@ def test_pipelined_splat_kernels(emu, knobs):  # noqa: F811
     for k, v in knobs.items():
         emu.dpc_debug_set(k, v)
     try:
-        for name in ("cfg1_drc_k11", "clustered_init", "trans_focal", "edge_points", "matrix_pose", "extra_upstream", "single_point"):
+        names = ("cfg1_drc_k11", "trans_focal", "edge_points", "matrix_pose", "extra_upstream", "single_point")
+        for name in (names if knobs.get(19) != 2 else names[:2]):
             if name not in SMALL:
                 continue
             fx = cases.load_golden(name)
